@@ -1,0 +1,106 @@
+"""ViT feature-extractor configurations and weight containers (host side, no device code).
+
+The memory's feature extractor plug-point is `preload_dino` (reference memory_2.py:43-46): any object with
+`forward_features(x) -> {'x_norm_patchtokens': (B, n_patch, D)}`.  The reference loads DINOv2 ViT-L/14 with
+4 register tokens (args.py:50); BASELINE.json's north_star names CLIP ViT-L/14.  One engine covers both via
+the switches below.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, replace
+
+import torch
+
+
+@dataclass(frozen=True)
+class ViTConfig:
+    name: str
+    image: int = 224
+    patch: int = 14
+    dim: int = 1024
+    depth: int = 24
+    heads: int = 16
+    mlp: int = 4096
+    n_reg: int = 0            # register tokens inserted after cls (DINOv2-reg: 4)
+    layerscale: bool = False  # DINOv2
+    act: str = "gelu"         # "gelu" (erf) | "quick_gelu" (x*sigmoid(1.702x), CLIP)
+    ln_pre: bool = False      # CLIP pre-LayerNorm
+    ln_eps: float = 1e-6
+    patch_bias: bool = True
+
+    @property
+    def grid(self) -> int:
+        return self.image // self.patch
+
+    @property
+    def n_patch(self) -> int:
+        return self.grid * self.grid
+
+    @property
+    def tokens(self) -> int:
+        return 1 + self.n_reg + self.n_patch
+
+    @property
+    def patch_k(self) -> int:
+        return 3 * self.patch * self.patch
+
+    def flops_per_frame(self) -> float:
+        """2*[Np*Kp*D + L*(T*D*3D + T*D*D + 2*T*D*M + 2*T^2*D)]."""
+        T, D, L, M = self.tokens, self.dim, self.depth, self.mlp
+        return 2.0 * (self.n_patch * self.patch_k * D + L * (T * D * 3 * D + T * D * D + 2 * T * D * M + 2 * T * T * D))
+
+
+CLIP_L14 = ViTConfig("clip-vit-l14", act="quick_gelu", ln_pre=True, ln_eps=1e-5, patch_bias=False)
+DINOV2_L14_REG = ViTConfig("dinov2-vitl14-reg", n_reg=4, layerscale=True, act="gelu", ln_eps=1e-6, patch_bias=True)
+CLIP_B32 = ViTConfig("clip-vit-b32", patch=32, dim=768, depth=12, heads=12, mlp=3072, act="quick_gelu",
+                     ln_pre=True, ln_eps=1e-5, patch_bias=False)
+
+CONFIGS = {c.name: c for c in (CLIP_L14, DINOV2_L14_REG, CLIP_B32)}
+# torch.hub entry names the reference passes as --dino_size (args.py:50)
+CONFIGS["dinov2_vitl14_reg"] = DINOV2_L14_REG
+
+
+def tiny(cfg: ViTConfig, dim=128, depth=2, heads=2, mlp=256) -> ViTConfig:
+    """Same architecture switches at test size."""
+    return replace(cfg, name=cfg.name + "-tiny", dim=dim, depth=depth, heads=heads, mlp=mlp)
+
+
+def random_weights(cfg: ViTConfig, seed: int = 0, perturb: bool = False, std: float = 0.02) -> dict:
+    """Seeded random-init weights: linear/embedding ~ N(0, std), LN = 1/0, LayerScale = 1.
+
+    perturb=True additionally randomises LN affine / LayerScale / biases so every epilogue term is exercised
+    by parity tests.  Layout (fp32, CPU): patch_w (D, 3*P*P) in (c,ky,kx) order, qkv_w (3D, D) = [q;k;v].
+    """
+    g = torch.Generator().manual_seed(seed)
+    D, M = cfg.dim, cfg.mlp
+
+    def n(*shape, s=std):
+        return torch.randn(*shape, generator=g) * s
+
+    def ln_pair():
+        if perturb:
+            return 1.0 + n(D, s=0.1), n(D, s=0.1)
+        return torch.ones(D), torch.zeros(D)
+
+    w = {
+        "patch_w": n(D, cfg.patch_k),
+        "patch_b": n(D) if cfg.patch_bias else torch.zeros(D),
+        "cls": n(D),
+        "reg": n(max(cfg.n_reg, 1), D)[: cfg.n_reg] if cfg.n_reg else torch.zeros(0, D),
+        "pos": n(1 + cfg.n_patch, D),
+    }
+    if cfg.ln_pre:
+        w["ln_pre_w"], w["ln_pre_b"] = ln_pair()
+    for i in range(cfg.depth):
+        p = f"l{i}."
+        w[p + "ln1_w"], w[p + "ln1_b"] = ln_pair()
+        w[p + "qkv_w"], w[p + "qkv_b"] = n(3 * D, D), n(3 * D)
+        w[p + "proj_w"], w[p + "proj_b"] = n(D, D), n(D)
+        w[p + "ln2_w"], w[p + "ln2_b"] = ln_pair()
+        w[p + "fc1_w"], w[p + "fc1_b"] = n(M, D), n(M)
+        w[p + "fc2_w"], w[p + "fc2_b"] = n(D, M), n(D)
+        if cfg.layerscale:
+            w[p + "ls1"] = 1.0 + n(D, s=0.1) if perturb else torch.ones(D)
+            w[p + "ls2"] = 1.0 + n(D, s=0.1) if perturb else torch.ones(D)
+    w["ln_post_w"], w["ln_post_b"] = ln_pair()
+    return w

@@ -1,0 +1,335 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a -- see gemm_tcgen05.cuh for the design.
+#include "gemm_tcgen05.cuh"
+
+namespace bscnav {
+
+static constexpr int BM = 128;           // UMMA M (cta_group::1)
+static constexpr int BK = 64;            // one 128-byte swizzle atom of fp16 along K
+static constexpr int UK = 16;            // UMMA K for 16-bit operands
+static constexpr int kGemmThreads = 192;
+
+template <int BN> struct Cfg {
+  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmem = kStages * kStageBytes + kBarBytes + 1024;   // + slack for 1024-byte alignment
+  static constexpr int kTmemCols = 2 * BN;                                  // two accumulator stages
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile in shared memory, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart.
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64) = 2)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor: c_format f32 (1) [4,6), a/b format f16 (0), a/b K-major (0), N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float act_fn(float v, int act) {
+  if (act == 0) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));   // GELU (erf)
+  return v / (1.0f + expf(-1.702f * v));                                          // QuickGELU
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M, int N, int K,
+           const GemmEpilogue epi) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* bars = smem + C::kStages * C::kStageBytes;
+  const uint32_t full_bar = smem_u32(bars);                       // kStages x 8 B
+  const uint32_t empty_bar = full_bar + 8 * C::kStages;           // kStages x 8 B
+  const uint32_t tfull_bar = empty_bar + 8 * C::kStages;          // 2 x 8 B
+  const uint32_t tempty_bar = tfull_bar + 16;                     // 2 x 8 B
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 * (2 * C::kStages + 4));
+  const uint32_t smem_base = smem_u32(smem);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (M + BM - 1) / BM, n_tiles = N / BN, k_blocks = K / BK;
+  const int total_tiles = m_tiles * n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          const uint32_t a_dst = smem_base + stage * C::kStageBytes;
+          const uint32_t b_dst = a_dst + C::kABytes;
+          mbar_arrive_expect_tx(full_bar + 8 * stage, C::kStageBytes);
+          tma_load_2d(a_dst, &map_a, full_bar + 8 * stage, kb * BK, m_blk * BM);
+          tma_load_2d(b_dst, &map_w, full_bar + 8 * stage, kb * BK, n_blk * BN);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_base + stage * C::kStageBytes;
+          const uint64_t a_desc = umma_desc_sw128(a_addr);
+          const uint64_t b_desc = umma_desc_sw128(a_addr + C::kABytes);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            // advance 32 bytes (16 fp16) inside the swizzle atom: +2 in the (addr >> 4) field
+            tcgen05_mma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tcgen05_commit(empty_bar + 8 * stage);        // smem stage reusable once these MMAs have read it
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        tcgen05_commit(tfull_bar + 8 * acc);             // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global
+    const int quarter = warp & 3;                        // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      tcgen05_fence_after();
+      const int m = m_blk * BM + quarter * 32 + lane;
+      const bool in_m = m < M;
+      long long out_row = m;
+      const float* table_row = nullptr;
+      if (epi.mode == kOutPatchEmbed && in_m) {
+        const int f = m / epi.np, p = m - f * epi.np;
+        out_row = (long long)f * epi.tokens + epi.row_off + p;
+        table_row = epi.table + (long long)p * N;
+      }
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+        tmem_ld_wait();
+        const int n0 = n_blk * BN + c * 32;
+        if (in_m) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (epi.bias ? __ldg(epi.bias + n0 + j) : 0.f);
+          if (epi.mode == kOutHalf || epi.mode == kOutHalfAct) {
+            if (epi.mode == kOutHalfAct) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = act_fn(v[j], epi.act);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<__half*>(epi.out) + out_row * epi.ld_out + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __half2 h0 = __floats2half2_rn(v[8 * j + 0], v[8 * j + 1]), h1 = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
+              __half2 h2 = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]), h3 = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
+              uint4 u;
+              u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+              u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+              dst[j] = u;
+            }
+          } else {
+            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(epi.out) + out_row * epi.ld_out + n0);
+            if (epi.mode == kOutResidual) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 o = dst[j];
+                o.x += v[4 * j]; o.y += v[4 * j + 1]; o.z += v[4 * j + 2]; o.w += v[4 * j + 3];
+                dst[j] = o;
+              }
+            } else {
+              if (epi.mode == kOutPatchEmbed) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += __ldg(table_row + n0 + j);
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(tempty_bar + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_operand_map(CUtensorMap* map, const void* ptr, long long rows, long long K, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { snprintf(g_last_error, sizeof(g_last_error), "cuTensorMapEncodeTiled entry point not found"); return BSCNAV_ECUDA; }
+  if (!ptr || rows <= 0 || K <= 0 || K % BK != 0 || (reinterpret_cast<uintptr_t>(ptr) & 15)) return BSCNAV_EINVAL;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(g_last_error, sizeof(g_last_error), "cuTensorMapEncodeTiled failed: %d", (int)r); return BSCNAV_ECUDA; }
+  return BSCNAV_OK;
+}
+
+int gemm_block_n(int N) { return (N % 256 == 0 && N >= 2048) ? 256 : 128; }
+
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN>
+static int launch_bn(const CUtensorMap* map_a, const CUtensorMap* map_w, int M, int N, int K, const GemmEpilogue& epi,
+                     cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    BSC_CUDA(cudaFuncSetAttribute(k_gemm_f16<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem));
+    attr_set = true;
+  }
+  const int tiles = ((M + BM - 1) / BM) * (N / BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  BSC_LAUNCH(k_gemm_f16<BN>, grid, kGemmThreads, Cfg<BN>::kSmem, stream, *map_a, *map_w, M, N, K, epi);
+  return BSCNAV_OK;
+}
+
+int gemm_f16_launch(const CUtensorMap* map_a, const CUtensorMap* map_w, int M, int N, int K, const GemmEpilogue& epi,
+                    cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || N % 128 != 0 || K % BK != 0 || !epi.out) return BSCNAV_EINVAL;
+  if (gemm_block_n(N) == 256) return launch_bn<256>(map_a, map_w, M, N, K, epi, stream);
+  return launch_bn<128>(map_a, map_w, M, N, K, epi, stream);
+}
+
+}  // namespace bscnav
+
+using namespace bscnav;
+
+extern "C" int bscnav_gemm_f16(const void* a, const void* w, const float* bias, void* out, int32_t m, int32_t n, int32_t k,
+                               int32_t out_mode, int32_t act, void* stream) {
+  if (!a || !w || !out || m <= 0 || n <= 0 || k <= 0 || n % 128 != 0 || k % 64 != 0) return BSCNAV_EINVAL;
+  if (out_mode != kOutHalf && out_mode != kOutHalfAct && out_mode != kOutResidual && out_mode != kOutFloat) return BSCNAV_EINVAL;
+  CUtensorMap ma, mw;
+  if (int e = make_operand_map(&ma, a, m, k, BM)) return e;
+  if (int e = make_operand_map(&mw, w, n, k, gemm_block_n(n))) return e;
+  GemmEpilogue epi{};
+  epi.out = out; epi.bias = bias; epi.table = nullptr; epi.ld_out = n; epi.mode = out_mode; epi.act = act;
+  return gemm_f16_launch(&ma, &mw, m, n, k, epi, (cudaStream_t)stream);
+}

@@ -1,0 +1,42 @@
+// Persistent warp-specialised fp16 GEMM on the 5th-generation tensor cores (sm_100a):
+//   out[M,N] (+)= A[M,K] * W[N,K]^T (+ bias, activation / residual / row-remap epilogues)
+// A and W are K-major fp16; accumulation is fp32 in TMEM.
+//
+//   warp 0      TMA producer   cp.async.bulk.tensor (128B swizzle) -> smem ring, mbarrier complete_tx
+//   warp 1      MMA issuer     one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (UMMA 128 x BN x 16),
+//                              tcgen05.commit releases smem stages and publishes the TMEM accumulator
+//   warps 2..5  epilogue       tcgen05.ld (32 lanes x 32 columns per warp-instruction) -> registers -> global
+// Two TMEM accumulator stages (2 x BN columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace bscnav {
+
+enum GemmOut : int {
+  kOutHalf = 0,        // fp16 out = acc + bias
+  kOutHalfAct = 1,     // fp16 out = act(acc + bias)
+  kOutResidual = 2,    // fp32 out += acc + bias           (residual stream)
+  kOutPatchEmbed = 3,  // fp32 out[remap(m)] = acc + bias + table[m % np]   (patch embedding + position embedding)
+  kOutFloat = 4,       // fp32 out = acc (+ bias)           (similarity matrices)
+};
+
+struct GemmEpilogue {
+  void* out;
+  const float* bias;    // [N] or null
+  const float* table;   // kOutPatchEmbed: [np, N]
+  long long ld_out;     // elements per output row
+  int mode;
+  int act;              // 0 = GELU(erf), 1 = QuickGELU
+  int np, tokens, row_off;  // kOutPatchEmbed: out row = (m / np) * tokens + row_off + m % np
+};
+
+int gemm_f16_launch(const CUtensorMap* map_a, const CUtensorMap* map_w, int M, int N, int K, const GemmEpilogue& epi,
+                    cudaStream_t stream);
+
+// 2-D K-major fp16 operand [rows, K] -> tensor map with box {64, box_rows}, 128-byte swizzle
+int make_operand_map(CUtensorMap* map, const void* ptr, long long rows, long long K, int box_rows);
+
+int gemm_block_n(int N);   // 256 when N % 256 == 0 and the tile count fills the machine, else 128
+
+}  // namespace bscnav

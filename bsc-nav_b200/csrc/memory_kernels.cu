@@ -1,0 +1,807 @@
+// Spatial-memory build + query kernels (sm_100a): depth unprojection + pose transform + voxel index (float64),
+// deterministic slot assignment, top-C winner selection with 64-bit atomics, 128-bit feature-row commit,
+// cosine / per-cell max / top-K query.  HBM-bound integer/byte work: coalesced 16-byte records, warp-level
+// pre-aggregation in front of the atomics, grid sizes in multiples of the SM count.
+//
+// Reference semantics restated here (each kernel cites its lines): memory_2.py:744-756, 842-894, 326-358,
+// 623-671; utils.py:153-214.
+#include "common.cuh"
+
+namespace bscnav {
+
+thread_local char g_last_error[256] = {0};
+std::atomic<long long> g_launches{0};
+
+static constexpr int kThreads = 256;
+static constexpr int kItems = 4;                 // points per thread in the ordered-scan kernels
+static constexpr int kTile = kThreads * kItems;  // 1024 points per block
+static constexpr uint32_t kNoTouch = 0xFFFFFFFFu;
+static constexpr int kSrcBits = 20;              // record.aux = src_row | (h << 20)
+static constexpr uint32_t kSrcMask = (1u << kSrcBits) - 1;
+
+// One record per visited point (16 B, written/read as one 128-bit access):
+//   x = linear cell or -1 (rejected)   y = aux (token source row | h << 20)   z = ordinal   w = float bits of r^2
+// key = (w << 32) | z : smaller is better (r^2 >= 0 so its float bits order as unsigned), ties -> lower ordinal.
+__device__ __forceinline__ uint64_t rec_key(const uint4& r) { return ((uint64_t)r.w << 32) | r.z; }
+
+// row-vector times column with the FMA chain numpy/OpenBLAS dgemm uses (k ascending, accumulator starts at a0*b0):
+// reproduces `cam_mat_inv @ p_2d`, `pose @ pc_homo`, `cam_mat @ p` of utils.py:168,197,209 bit for bit.
+__device__ __forceinline__ double dot3(const double* m, double a, double b, double c) {
+  return __fma_rn(m[2], c, __fma_rn(m[1], b, __dmul_rn(m[0], a)));
+}
+__device__ __forceinline__ double dot4(const double* m, double a, double b, double c, double d) {
+  return __fma_rn(m[3], d, __fma_rn(m[2], c, __fma_rn(m[1], b, __dmul_rn(m[0], a))));
+}
+// python int(x) on a float64: truncation toward zero, saturated so the range test below rejects it
+__device__ __forceinline__ int trunc_i32(double v) {
+  if (!(v > -2.0e9)) return -2000000000;
+  if (!(v < 2.0e9)) return 2000000000;
+  return (int)v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1: unproject + pose + voxel index + patch projection + winner key.          (a3-a7 of SURVEY 8a)
+__global__ void __launch_bounds__(kThreads)
+k_index_points(const bscnav_geom_t g, const float* __restrict__ depth, const double* __restrict__ poses,
+               const uint32_t* __restrict__ ord_base, const int32_t* __restrict__ sample_idx, int n_points,
+               long long total, uint4* __restrict__ rec, const int32_t* __restrict__ occupied,
+               uint32_t* __restrict__ first_touch) {
+  const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int cell = -1;
+  uint32_t aux = 0, ord = 0, r2bits = 0;
+  if (i < total) {
+    const int b = (int)(i / n_points);
+    const int j = (int)(i - (long long)b * n_points);
+    const int pix = sample_idx ? sample_idx[i] : j;
+    const int hw = g.height * g.width;
+    ord = ord_base[b] + (uint32_t)j;
+    const double z = (double)depth[(long long)b * hw + pix];
+    const int v = pix / g.width, u = pix - v * g.width;
+    const double x = (double)u + 0.5, y = (double)v + 0.5;
+    // utils.py:166-171  pc = (cam_mat_inv @ [x,y,1]) * z
+    const double p0 = __dmul_rn(dot3(g.kinv + 0, x, y, 1.0), z);
+    const double p1 = __dmul_rn(dot3(g.kinv + 3, x, y, 1.0), z);
+    const double p2 = __dmul_rn(dot3(g.kinv + 6, x, y, 1.0), z);
+    if (p2 > g.min_depth && p2 < g.max_depth) {                   // utils.py:174-176 (strict)
+      const double* M = poses + (long long)b * 16;
+      const double gx = dot4(M + 0, p0, p1, p2, 1.0);             // utils.py:195-197
+      const double gy = dot4(M + 4, p0, p1, p2, 1.0);
+      const double gz = dot4(M + 8, p0, p1, p2, 1.0);
+      const double half = (double)g.gs / 2.0;
+      // utils.py:201-205  row = int(gs/2 - int(x/cs)) ...
+      const int row = trunc_i32(__dsub_rn(half, (double)trunc_i32(__ddiv_rn(gx, g.cs))));
+      const int col = trunc_i32(__dsub_rn(half, (double)trunc_i32(__ddiv_rn(gy, g.cs))));
+      const int h = trunc_i32(__ddiv_rn(gz, g.cs));
+      const bool out = col >= g.gs || row >= g.gs || h >= g.maxh || col < 0 || row < 0 || h < g.minh;  // memory_2.py:755-756
+      if (!out) {
+        // utils.py:208-214 with the patch intrinsics (memory_2.py:857,871)
+        const double q0 = dot3(g.kpatch + 0, p0, p1, p2), q1 = dot3(g.kpatch + 3, p0, p1, p2),
+                     q2 = dot3(g.kpatch + 6, p0, p1, p2);
+        const int ppx = trunc_i32(__dsub_rn(__ddiv_rn(q0, q2), 0.5));
+        const int ppy = trunc_i32(__dsub_rn(__ddiv_rn(q1, q2), 0.5));
+        if (!(ppx < 0 || ppy < 0 || ppx >= g.n_patch_h || ppy >= g.n_patch_w)) {   // memory_2.py:878 (token array is (W', H', D))
+          const int hh = h - g.minh;                                               // memory_2.py:867
+          cell = (g.levels == 1) ? row * g.gs + col : (row * g.gs + col) * g.levels + hh;
+          const uint32_t src = (uint32_t)(b * (g.n_patch_h * g.n_patch_w) + ppy * g.n_patch_h + ppx);
+          aux = src | ((uint32_t)hh << kSrcBits);
+          // memory_2.py:873,885  float32(np.sum(np.square(p_local)))
+          const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(p0, p0), __dmul_rn(p1, p1)), __dmul_rn(p2, p2));
+          r2bits = __float_as_uint(__double2float_rn(r2));
+        }
+      }
+    }
+    rec[i] = make_uint4((uint32_t)cell, aux, ord, r2bits);
+  }
+  // first-touch ordinal of still-unassigned cells; within a warp only the head of a run of equal cells issues
+  // the atomic (ordinals ascend with the lane, so the head holds the run's minimum)
+  const int prev = __shfl_up_sync(0xffffffffu, cell, 1);
+  if (cell >= 0 && (lane == 0 || prev != cell) && occupied[cell] < 0) atomicMin(&first_touch[cell], ord);
+}
+
+// block-wide exclusive scan of one int per thread (kThreads threads); returns exclusive prefix, total via *sum
+__device__ __forceinline__ int block_excl_scan(int v, int* sum) {
+  __shared__ int warp_tot[kThreads / 32];
+  __shared__ int block_tot;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int t = lane < kThreads / 32 ? warp_tot[lane] : 0;
+    int ti = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int s = __shfl_up_sync(0xffffffffu, ti, o);
+      if (lane >= o) ti += s;
+    }
+    if (lane < kThreads / 32) warp_tot[lane] = ti - t;
+    if (lane == 31) block_tot = ti;
+  }
+  __syncthreads();
+  *sum = block_tot;
+  const int r = warp_tot[w] + inc - v;
+  __syncthreads();
+  return r;
+}
+
+__device__ __forceinline__ bool is_first_toucher(const uint4& r, const int32_t* occupied, const uint32_t* first_touch) {
+  const int cell = (int)r.x;
+  return cell >= 0 && occupied[cell] < 0 && first_touch[cell] == r.z;
+}
+
+// K2a: number of newly touched cells per 1024-point tile (a point is the "first toucher" of an unassigned cell)
+__global__ void __launch_bounds__(kThreads)
+k_count_new(const uint4* __restrict__ rec, long long total, const int32_t* __restrict__ occupied,
+            const uint32_t* __restrict__ first_touch, int* __restrict__ tile_count) {
+  const long long base = (long long)blockIdx.x * kTile + threadIdx.x * kItems;
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k)
+    if (base + k < total) c += is_first_toucher(rec[base + k], occupied, first_touch) ? 1 : 0;
+  int tot;
+  block_excl_scan(c, &tot);
+  if (threadIdx.x == 0) tile_count[blockIdx.x] = tot;
+}
+
+// K2b: exclusive scan of the tile counts (single block), slot-range reservation, capacity check
+__global__ void __launch_bounds__(kThreads)
+k_scan_tiles(const int* __restrict__ tile_count, int* __restrict__ tile_off, int n_tiles, int* __restrict__ hdr,
+             int32_t* __restrict__ counters, int max_slots) {
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_tiles; base += kThreads) {
+    const int idx = base + threadIdx.x;
+    const int v = idx < n_tiles ? tile_count[idx] : 0;
+    int tot;
+    const int ex = block_excl_scan(v, &tot);
+    if (idx < n_tiles) tile_off[idx] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int base_slot = counters[0];
+    const bool ok = (long long)base_slot + carry <= (long long)max_slots;
+    hdr[0] = base_slot;
+    hdr[1] = ok ? 1 : 0;
+    if (ok) counters[0] = base_slot + carry; else counters[1] = 1;   // overflow: nothing from this batch is assigned
+  }
+}
+
+// K2c: slots in first-touch order == the reference's sequential numbering (memory_2.py:888-894)
+__global__ void __launch_bounds__(kThreads)
+k_assign_slots(const uint4* __restrict__ rec, long long total, int32_t* __restrict__ occupied,
+               const uint32_t* __restrict__ first_touch, const int* __restrict__ tile_off,
+               const int* __restrict__ hdr, int32_t* __restrict__ slot_cell) {
+  if (!hdr[1]) return;
+  const long long base = (long long)blockIdx.x * kTile + threadIdx.x * kItems;
+  bool f[kItems];
+  int cells[kItems];
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    f[k] = false;
+    cells[k] = -1;
+    if (base + k < total) {
+      const uint4 r = rec[base + k];
+      f[k] = is_first_toucher(r, occupied, first_touch);
+      cells[k] = (int)r.x;
+    }
+    c += f[k] ? 1 : 0;
+  }
+  int tot;
+  int rank = block_excl_scan(c, &tot) + tile_off[blockIdx.x] + hdr[0];
+  // note: `occupied` is written below while other threads may still be reading it in is_first_toucher above:
+  // safe because a flagged cell is written by exactly one point (its first toucher) and only cells whose
+  // first_touch ordinal equals the reader's own ordinal can flip the reader's flag -- i.e. its own cell.
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kItems; ++k)
+    if (f[k]) {
+      slot_cell[rank] = cells[k];
+      occupied[cells[k]] = rank;
+      ++rank;
+    }
+}
+
+// K3: top-C winner selection.  C == 1: warp-segmented min then one 64-bit atomicMin per run of equal cells.
+// C > 1: lock-free sorted insertion -- offer the key to slot position 0..C-1 with atomicMin and carry the
+// displaced key forward; position j ends up holding the (j+1)-th smallest key whatever the arrival order.
+__global__ void __launch_bounds__(kThreads)
+k_select(const uint4* __restrict__ rec, long long total, const int32_t* __restrict__ occupied,
+         uint32_t* __restrict__ first_touch, unsigned long long* __restrict__ slot_keys, int C) {
+  const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int cell = -1, slot = -1;
+  unsigned long long key = BSCNAV_KEY_EMPTY;
+  if (i < total) {
+    const uint4 r = rec[i];
+    cell = (int)r.x;
+    if (cell >= 0) {
+      first_touch[cell] = kNoTouch;      // restore the scratch invariant for the next batch
+      slot = occupied[cell];             // < 0 only after a capacity overflow
+      key = rec_key(r);
+    }
+  }
+  if (C == 1) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long k2 = __shfl_down_sync(0xffffffffu, key, d);
+      const int c2 = __shfl_down_sync(0xffffffffu, cell, d);
+      if (lane + d < 32 && c2 == cell && k2 < key) key = k2;
+    }
+    const int prev = __shfl_up_sync(0xffffffffu, cell, 1);
+    if (slot >= 0 && (lane == 0 || prev != cell) && key < slot_keys[slot]) atomicMin(&slot_keys[slot], key);
+  } else if (slot >= 0) {
+    unsigned long long* ks = slot_keys + (long long)slot * C;
+    if (key < ks[C - 1]) {
+      for (int j = 0; j < C; ++j) {
+        const unsigned long long old = atomicMin(&ks[j], key);
+        if (old > key) {
+          key = old;
+          if (key == BSCNAV_KEY_EMPTY) break;
+        }
+      }
+    }
+  }
+}
+
+// K4: winners copy their 4 KB token row into the store with 128-bit loads/stores, one warp per row.
+__global__ void __launch_bounds__(kThreads)
+k_commit(const uint4* __restrict__ rec, long long total, const int32_t* __restrict__ occupied,
+         const unsigned long long* __restrict__ slot_keys, unsigned long long* __restrict__ row_key,
+         int32_t* __restrict__ tok_h, float* __restrict__ norm2, float* __restrict__ feat,
+         const float* __restrict__ tokens, int C, int D) {
+  const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  long long dst_row = -1;
+  uint32_t aux = 0;
+  if (i < total) {
+    const uint4 r = rec[i];
+    const int cell = (int)r.x;
+    const int slot = cell >= 0 ? occupied[cell] : -1;
+    if (slot >= 0) {
+      const unsigned long long key = rec_key(r);
+      aux = r.y;
+      const unsigned long long* ks = slot_keys + (long long)slot * C;
+      if (C == 1) {
+        if (ks[0] == key) { dst_row = slot; row_key[slot] = key; }
+      } else {
+        bool win = false;
+        for (int j = 0; j < C && ks[j] <= key; ++j) win |= (ks[j] == key);
+        if (win) {
+          // claim a physical row whose current token is no longer among the kept keys (or was never used)
+          unsigned long long* rk = row_key + (long long)slot * C;
+          for (int rr = 0; rr < C && dst_row < 0; ++rr) {
+            const unsigned long long cur = rk[rr];
+            bool kept = false;
+            for (int j = 0; j < C; ++j) kept |= (ks[j] == cur);
+            if (cur == BSCNAV_KEY_EMPTY) kept = false;
+            if (!kept && atomicCAS(&rk[rr], cur, key) == cur) dst_row = (long long)slot * C + rr;
+          }
+        }
+      }
+    }
+  }
+  unsigned winners = __ballot_sync(0xffffffffu, dst_row >= 0);
+  const int nvec = D >> 2;
+  while (winners) {
+    const int src_lane = __ffs(winners) - 1;
+    winners &= winners - 1;
+    const long long row = __shfl_sync(0xffffffffu, dst_row, src_lane);
+    const uint32_t a = __shfl_sync(0xffffffffu, aux, src_lane);
+    const float4* s = reinterpret_cast<const float4*>(tokens + (long long)(a & kSrcMask) * D);
+    float4* d = reinterpret_cast<float4*>(feat + row * D);
+    float acc = 0.f;
+    for (int c = lane; c < nvec; c += 32) {
+      const float4 v = s[c];
+      d[c] = v;
+      acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) { norm2[row] = acc; tok_h[row] = (int)(a >> kSrcBits); }
+  }
+}
+
+__global__ void k_fill_u32(uint32_t* p, long long n, uint32_t v) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void k_fill_u64(unsigned long long* p, long long n, unsigned long long v) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// records for a compacted delta (multi-GPU merge): cell, source row i | h << 20, key
+__global__ void k_delta_records(const int32_t* __restrict__ d_cell, const unsigned long long* __restrict__ d_key,
+                                const int32_t* __restrict__ d_h, int n, uint4* __restrict__ rec,
+                                const int32_t* __restrict__ occupied, uint32_t* __restrict__ first_touch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int cell = d_cell[i];
+  const unsigned long long key = d_key[i];
+  rec[i] = make_uint4((uint32_t)cell, (uint32_t)i | ((uint32_t)d_h[i] << kSrcBits), (uint32_t)key, (uint32_t)(key >> 32));
+  if (cell >= 0 && occupied[cell] < 0) atomicMin(&first_touch[cell], (uint32_t)key);
+}
+
+// ordered compaction of the rows whose ordinal lies in [lo, hi): count / scan / write (same 3-kernel shape as K2)
+__device__ __forceinline__ bool row_in_range(const unsigned long long* row_key, long long r, uint32_t lo, uint32_t hi) {
+  const unsigned long long k = row_key[r];
+  if (k == BSCNAV_KEY_EMPTY) return false;
+  const uint32_t o = (uint32_t)k;
+  return o >= lo && o < hi;
+}
+__global__ void __launch_bounds__(kThreads)
+k_export_count(const unsigned long long* __restrict__ row_key, const int32_t* __restrict__ counters, int C, uint32_t lo,
+               uint32_t hi, int* __restrict__ tile_count) {
+  const long long n_rows = (long long)counters[0] * C;
+  const long long base = (long long)blockIdx.x * kTile + threadIdx.x * kItems;
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k)
+    if (base + k < n_rows) c += row_in_range(row_key, base + k, lo, hi) ? 1 : 0;
+  int tot;
+  block_excl_scan(c, &tot);
+  if (threadIdx.x == 0) tile_count[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(kThreads)
+k_export_scan(const int* __restrict__ tile_count, int* __restrict__ tile_off, int n_tiles, int* __restrict__ out_n, int max_out) {
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_tiles; base += kThreads) {
+    const int idx = base + threadIdx.x;
+    const int v = idx < n_tiles ? tile_count[idx] : 0;
+    int tot;
+    const int ex = block_excl_scan(v, &tot);
+    if (idx < n_tiles) tile_off[idx] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out_n = carry < max_out ? carry : max_out;
+}
+__global__ void __launch_bounds__(kThreads)
+k_export_write(const unsigned long long* __restrict__ row_key, const int32_t* __restrict__ counters,
+               const int32_t* __restrict__ slot_cell, const int32_t* __restrict__ tok_h, const float* __restrict__ feat,
+               int C, int D, uint32_t lo, uint32_t hi, const int* __restrict__ tile_off, int32_t* __restrict__ d_cell,
+               unsigned long long* __restrict__ d_key, int32_t* __restrict__ d_h, float* __restrict__ d_feat, int max_out) {
+  const long long n_rows = (long long)counters[0] * C;
+  const long long base = (long long)blockIdx.x * kTile + threadIdx.x * kItems;
+  bool f[kItems];
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    f[k] = base + k < n_rows && row_in_range(row_key, base + k, lo, hi);
+    c += f[k] ? 1 : 0;
+  }
+  int tot;
+  int rank = block_excl_scan(c, &tot) + tile_off[blockIdx.x];
+  long long my_dst = -1, my_src = -1;   // each thread publishes its rows one at a time for a warp-wide copy
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    my_dst = -1;
+    if (f[k]) {
+      if (rank < max_out) {
+        my_dst = rank;
+        my_src = base + k;
+        d_cell[rank] = slot_cell[(base + k) / C];
+        d_key[rank] = row_key[base + k];
+        d_h[rank] = tok_h[base + k];
+      }
+      ++rank;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, my_dst >= 0);
+    while (m) {
+      const int sl = __ffs(m) - 1;
+      m &= m - 1;
+      const long long dr = __shfl_sync(0xffffffffu, my_dst, sl), sr = __shfl_sync(0xffffffffu, my_src, sl);
+      const float4* s = reinterpret_cast<const float4*>(feat + sr * D);
+      float4* d = reinterpret_cast<float4*>(d_feat + dr * D);
+      for (int q = lane; q < (D >> 2); q += 32) d[q] = s[q];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Query.  Q1: one warp per slot: cosine of up to kQ queries against the slot's C rows, per-slot max,
+// candidate filter, composite sort key  (~orderable(sim) << 32) | cell  -> ascending key == descending sim,
+// ties by ascending (row, col, h) because cell is the row-major linear index.
+static constexpr int kQ = 8;
+__device__ __forceinline__ uint32_t orderable(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float from_orderable(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
+}
+
+template <int NV>   // NV = D / 128 float4 per lane
+__global__ void __launch_bounds__(kThreads)
+k_query_slots(const bscnav_geom_t g, const float* __restrict__ feat, const float* __restrict__ norm2,
+              const unsigned long long* __restrict__ row_key, const int32_t* __restrict__ slot_cell,
+              const int32_t* __restrict__ tok_h, const int32_t* __restrict__ counters, const float* __restrict__ q,
+              int q0, int nq, const bscnav_filter_t flt, unsigned long long* __restrict__ keys, long long key_stride) {
+  extern __shared__ float4 sq[];            // nq * D floats
+  __shared__ float q_n2[kQ];
+  const int D = NV * 128;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < nq * (D >> 2); i += kThreads) sq[i] = reinterpret_cast<const float4*>(q + (long long)q0 * D)[i];
+  __syncthreads();
+  if (wib < nq) {      // w1 = sum(q*q), same association as the rows' norm2 (lane-strided fma, shuffle tree)
+    float acc = 0.f;
+    for (int c = lane; c < (D >> 2); c += 32) {
+      const float4 v = sq[wib * (D >> 2) + c];
+      acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) q_n2[wib] = acc;
+  }
+  __syncthreads();
+  const int n_slots = counters[0];
+  const int C = g.cache;
+  const int warps = gridDim.x * (kThreads / 32);
+  for (int slot = blockIdx.x * (kThreads / 32) + wib; slot < n_slots; slot += warps) {
+    const int cell = slot_cell[slot];
+    float best[kQ];
+#pragma unroll
+    for (int k = 0; k < kQ; ++k) best[k] = -INFINITY;
+    // candidate filter (memory_2.py:624-640)
+    int row, col, h;
+    if (g.levels == 1) { row = cell / g.gs; col = cell - row * g.gs; h = -1; }
+    else { h = cell % g.levels; const int rc = cell / g.levels; row = rc / g.gs; col = rc - row * g.gs; }
+    bool cand = true;
+    for (int j = 0; j < C; ++j) {
+      const long long r = (long long)slot * C + j;
+      if (row_key[r] == BSCNAV_KEY_EMPTY) continue;
+      if (g.levels == 1) {            // BEV keys: the token's own height takes part in the filter
+        h = tok_h[r];
+      }
+      bool ok = true;
+      if (flt.radius2 >= 0) {
+        const long long dr = row - flt.cur[0], dc = col - flt.cur[1], dh = h - flt.cur[2];
+        ok = dr * dr + dc * dc + dh * dh <= flt.radius2;
+      }
+      if (flt.floor_min <= flt.floor_max) ok = ok && h >= flt.floor_min && h <= flt.floor_max;
+      if (!ok) { if (g.levels != 1) { cand = false; break; } else continue; }
+      float4 v[NV];
+      const float4* fr = reinterpret_cast<const float4*>(feat + r * D);
+#pragma unroll
+      for (int c = 0; c < NV; ++c) v[c] = ld_stream_f4(fr + lane + 32 * c);
+      const float n2 = norm2[r];
+#pragma unroll
+      for (int k = 0; k < kQ; ++k) {
+        if (k < nq) {
+          float acc = 0.f;
+#pragma unroll
+          for (int c = 0; c < NV; ++c) {
+            const float4 qq = sq[k * (D >> 2) + lane + 32 * c];
+            acc = fmaf(v[c].x, qq.x, acc); acc = fmaf(v[c].y, qq.y, acc);
+            acc = fmaf(v[c].z, qq.z, acc); acc = fmaf(v[c].w, qq.w, acc);
+          }
+          acc = warp_sum(acc);
+          // F.cosine_similarity (memory_2.py:656): w12 / sqrt(clamp(w1*w2, eps^2)), eps = 1e-8
+          const float s = acc / sqrtf(fmaxf(q_n2[k] * n2, 1e-16f));
+          best[k] = fmaxf(best[k], s);
+        }
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < kQ; ++k)
+        if (k < nq) {
+          unsigned long long key = BSCNAV_KEY_EMPTY;
+          if (cand && best[k] > -INFINITY) key = ((unsigned long long)(~orderable(best[k])) << 32) | (uint32_t)cell;
+          keys[(long long)k * key_stride + slot] = key;
+        }
+    }
+  }
+}
+
+// Q2: per-chunk top-K by bitonic sort in shared memory; applied repeatedly until one chunk remains.
+static constexpr int kChunk = 4096;
+__global__ void __launch_bounds__(1024)
+k_topk_chunks(const unsigned long long* __restrict__ in, long long in_stride, const int32_t* __restrict__ n_dev, int n_host,
+              unsigned long long* __restrict__ out, long long out_stride, int k) {
+  __shared__ unsigned long long s[kChunk];
+  const int n = n_dev ? *n_dev : n_host;
+  const int qi = blockIdx.y;
+  const long long base = (long long)blockIdx.x * kChunk;
+  for (int i = threadIdx.x; i < kChunk; i += 1024) {
+    const long long idx = base + i;
+    s[i] = idx < n ? in[(long long)qi * in_stride + idx] : BSCNAV_KEY_EMPTY;
+  }
+  __syncthreads();
+  for (int size = 2; size <= kChunk; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < kChunk / 2; t += 1024) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const unsigned long long a = s[lo], b = s[hi];
+        if ((a > b) == up) { s[lo] = b; s[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < k; i += 1024) out[(long long)qi * out_stride + (long long)blockIdx.x * k + i] = s[i];
+}
+
+// Q3: decode the K winners: similarity from the key, (row, col, h) from the cell; BEV keys report the height
+// of the best-scoring token of the cell (recomputed here, K*C dot products).
+__global__ void __launch_bounds__(kThreads)
+k_topk_decode(const bscnav_geom_t g, const unsigned long long* __restrict__ keys, long long key_stride, int k,
+              const int32_t* __restrict__ occupied, const unsigned long long* __restrict__ row_key,
+              const int32_t* __restrict__ tok_h, const float* __restrict__ feat, const float* __restrict__ norm2,
+              const float* __restrict__ q, int q0, float* __restrict__ out_sim, int32_t* __restrict__ out_pos,
+              int32_t* __restrict__ out_count) {
+  const int qi = blockIdx.x;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int D = g.dim, C = g.cache;
+  __shared__ int cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  int local = 0;
+  for (int i = wib; i < k; i += kThreads / 32) {
+    const unsigned long long key = keys[(long long)qi * key_stride + i];
+    float sim = -INFINITY;
+    int row = -1, col = -1, h = -1;
+    if (key != BSCNAV_KEY_EMPTY) {
+      sim = from_orderable(~(uint32_t)(key >> 32));
+      const int cell = (int)(uint32_t)key;
+      if (g.levels == 1) {
+        row = cell / g.gs; col = cell - row * g.gs;
+        const int slot = occupied[cell];
+        float best = -INFINITY;
+        const float* qv = q + (long long)(q0 + qi) * D;
+        float qn = 0.f;
+        for (int c = lane; c < D; c += 32) qn = fmaf(qv[c], qv[c], qn);
+        qn = warp_sum(qn);
+        for (int j = 0; j < C; ++j) {
+          const long long r = (long long)slot * C + j;
+          if (row_key[r] == BSCNAV_KEY_EMPTY) continue;
+          float acc = 0.f;
+          for (int c = lane; c < D; c += 32) acc = fmaf(feat[r * D + c], qv[c], acc);
+          acc = warp_sum(acc);
+          const float s = acc / sqrtf(fmaxf(qn * norm2[r], 1e-16f));
+          if (s > best) { best = s; h = tok_h[r]; }
+        }
+      } else {
+        h = cell % g.levels; const int rc = cell / g.levels; row = rc / g.gs; col = rc - row * g.gs;
+      }
+      ++local;
+    }
+    if (lane == 0) {
+      out_sim[(long long)qi * k + i] = sim;
+      int32_t* p = out_pos + ((long long)qi * k + i) * 3;
+      p[0] = row; p[1] = col; p[2] = h;
+    }
+  }
+  if (lane == 0 && local) atomicAdd(&cnt, local);
+  __syncthreads();
+  if (threadIdx.x == 0) out_count[qi] = cnt;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static int check_geom(const bscnav_geom_t* g) {
+  if (!g) return BSCNAV_EINVAL;
+  if (g->height <= 0 || g->width <= 0 || g->gs <= 0 || g->levels <= 0 || g->cache <= 0 || g->cache > 64) return BSCNAV_EINVAL;
+  if (g->dim <= 0 || g->dim % 128 != 0 || g->dim > 2048) return BSCNAV_EINVAL;
+  if (g->levels != 1 && g->levels != g->maxh - g->minh) return BSCNAV_EINVAL;
+  if (g->maxh - g->minh > (1 << (32 - kSrcBits))) return BSCNAV_EINVAL;
+  if ((long long)g->gs * g->gs * g->levels >= (1ll << 31)) return BSCNAV_EINVAL;
+  if (g->max_slots <= 0) return BSCNAV_EINVAL;
+  return BSCNAV_OK;
+}
+
+struct FuseScratch {
+  uint4* rec;
+  int* tile_count;
+  int* tile_off;
+  int* hdr;
+};
+static int64_t scratch_layout(long long total, FuseScratch* s, char* base) {
+  const long long n_tiles = (total + kTile - 1) / kTile;
+  int64_t off = 0;
+  if (s) s->rec = reinterpret_cast<uint4*>(base + off);
+  off += align_up(total * 16, 256);
+  if (s) s->tile_count = reinterpret_cast<int*>(base + off);
+  off += align_up(n_tiles * 4, 256);
+  if (s) s->tile_off = reinterpret_cast<int*>(base + off);
+  off += align_up(n_tiles * 4, 256);
+  if (s) s->hdr = reinterpret_cast<int*>(base + off);
+  off += 256;
+  return off;
+}
+
+// shared tail of fuse / merge: slots, winners, rows
+static int run_store_update(const bscnav_geom_t* g, const bscnav_store_t* st, const FuseScratch& s, long long total,
+                            const float* tokens, cudaStream_t stream) {
+  const int n_tiles = (int)((total + kTile - 1) / kTile);
+  const int n_blocks = (int)((total + kThreads - 1) / kThreads);
+  BSC_LAUNCH(k_count_new, n_tiles, kThreads, 0, stream, s.rec, total, st->occupied_ids, st->first_touch, s.tile_count);
+  BSC_LAUNCH(k_scan_tiles, 1, kThreads, 0, stream, s.tile_count, s.tile_off, n_tiles, s.hdr, st->counters, g->max_slots);
+  BSC_LAUNCH(k_assign_slots, n_tiles, kThreads, 0, stream, s.rec, total, st->occupied_ids, st->first_touch, s.tile_off,
+             s.hdr, st->slot_cell);
+  BSC_LAUNCH(k_select, n_blocks, kThreads, 0, stream, s.rec, total, st->occupied_ids, st->first_touch,
+             reinterpret_cast<unsigned long long*>(st->slot_keys), g->cache);
+  BSC_LAUNCH(k_commit, n_blocks, kThreads, 0, stream, s.rec, total, st->occupied_ids,
+             reinterpret_cast<const unsigned long long*>(st->slot_keys), reinterpret_cast<unsigned long long*>(st->row_key),
+             st->tok_h, st->norm2, st->feat, tokens, g->cache, g->dim);
+  return BSCNAV_OK;
+}
+
+}  // namespace bscnav
+
+using namespace bscnav;
+
+extern "C" {
+
+int bscnav_abi_version(void) { return 1; }
+const char* bscnav_last_error(void) { return g_last_error; }
+int64_t bscnav_launch_count(void) { return g_launches.load(); }
+
+int bscnav_store_reset(const bscnav_geom_t* g, const bscnav_store_t* st, void* stream_) {
+  if (int e = check_geom(g)) return e;
+  if (!st || !st->occupied_ids || !st->first_touch || !st->slot_keys || !st->row_key || !st->counters) return BSCNAV_EINVAL;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const long long cells = (long long)g->gs * g->gs * g->levels;
+  const long long rows = (long long)g->max_slots * g->cache;
+  const int grid = num_sms() * 8;
+  BSC_LAUNCH(k_fill_u32, grid, 256, 0, stream, reinterpret_cast<uint32_t*>(st->occupied_ids), cells, 0xFFFFFFFFu);
+  BSC_LAUNCH(k_fill_u32, grid, 256, 0, stream, st->first_touch, cells, kNoTouch);
+  BSC_LAUNCH(k_fill_u64, grid, 256, 0, stream, reinterpret_cast<unsigned long long*>(st->slot_keys), rows, BSCNAV_KEY_EMPTY);
+  BSC_LAUNCH(k_fill_u64, grid, 256, 0, stream, reinterpret_cast<unsigned long long*>(st->row_key), rows, BSCNAV_KEY_EMPTY);
+  BSC_CUDA(cudaMemsetAsync(st->counters, 0, 8 * sizeof(int32_t), stream));
+  return BSCNAV_OK;
+}
+
+int64_t bscnav_fuse_scratch_bytes(int32_t n_frames, int32_t n_points) {
+  if (n_frames <= 0 || n_points <= 0) return BSCNAV_EINVAL;
+  return scratch_layout((long long)n_frames * n_points, nullptr, nullptr);
+}
+
+int bscnav_fuse_frames(const bscnav_geom_t* g, const bscnav_store_t* st, const float* depth, const double* poses,
+                       const uint32_t* ord_base, const int32_t* sample_idx, int32_t n_frames, int32_t n_points,
+                       const float* tokens, void* scratch, int64_t scratch_bytes, void* records_out, void* stream_) {
+  if (int e = check_geom(g)) return e;
+  if (!st || !depth || !poses || !ord_base || !tokens || !scratch) return BSCNAV_EINVAL;
+  if (n_frames <= 0 || n_points <= 0) return BSCNAV_EINVAL;
+  if (!sample_idx && n_points != g->height * g->width) return BSCNAV_EINVAL;
+  const long long total = (long long)n_frames * n_points;
+  if (total >= (1ll << 31)) return BSCNAV_EINVAL;
+  if ((long long)n_frames * g->n_patch_h * g->n_patch_w > (1ll << kSrcBits)) return BSCNAV_EINVAL;
+  FuseScratch s;
+  if (scratch_layout(total, &s, static_cast<char*>(scratch)) > scratch_bytes) return BSCNAV_EINVAL;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int n_blocks = (int)((total + kThreads - 1) / kThreads);
+  BSC_LAUNCH(k_index_points, n_blocks, kThreads, 0, stream, *g, depth, poses, ord_base, sample_idx, n_points, total, s.rec,
+             st->occupied_ids, st->first_touch);
+  if (records_out) BSC_CUDA(cudaMemcpyAsync(records_out, s.rec, total * 16, cudaMemcpyDeviceToDevice, stream));
+  return run_store_update(g, st, s, total, tokens, stream);
+}
+
+int bscnav_merge_delta(const bscnav_geom_t* g, const bscnav_store_t* st, const int32_t* d_cell, const uint64_t* d_key,
+                       const int32_t* d_h, const float* d_feat, int32_t n, void* scratch, int64_t scratch_bytes,
+                       void* stream_) {
+  if (int e = check_geom(g)) return e;
+  if (!st || !d_cell || !d_key || !d_h || !d_feat || !scratch || n < 0) return BSCNAV_EINVAL;
+  if (n == 0) return BSCNAV_OK;
+  if (n > (1 << kSrcBits)) return BSCNAV_EINVAL;
+  FuseScratch s;
+  if (scratch_layout(n, &s, static_cast<char*>(scratch)) > scratch_bytes) return BSCNAV_EINVAL;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  BSC_LAUNCH(k_delta_records, (n + kThreads - 1) / kThreads, kThreads, 0, stream, d_cell,
+             reinterpret_cast<const unsigned long long*>(d_key), d_h, n, s.rec, st->occupied_ids, st->first_touch);
+  return run_store_update(g, st, s, n, d_feat, stream);
+}
+
+int64_t bscnav_export_scratch_bytes(const bscnav_geom_t* g) {
+  if (check_geom(g)) return BSCNAV_EINVAL;
+  const long long max_rows = (long long)g->max_slots * g->cache;
+  return 2 * align_up(((max_rows + kTile - 1) / kTile) * 4, 256);
+}
+
+int bscnav_export_delta(const bscnav_geom_t* g, const bscnav_store_t* st, uint32_t ord_lo, uint32_t ord_hi,
+                        int32_t* d_cell, uint64_t* d_key, int32_t* d_h, float* d_feat, int32_t max_out,
+                        int32_t* out_n, void* scratch, int64_t scratch_bytes, void* stream_) {
+  if (int e = check_geom(g)) return e;
+  if (!st || !d_cell || !d_key || !d_h || !d_feat || !out_n || !scratch || max_out <= 0) return BSCNAV_EINVAL;
+  if (bscnav_export_scratch_bytes(g) > scratch_bytes) return BSCNAV_EINVAL;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const long long max_rows = (long long)g->max_slots * g->cache;
+  const int n_tiles = (int)((max_rows + kTile - 1) / kTile);
+  int* tile_count = static_cast<int*>(scratch);
+  int* tile_off = reinterpret_cast<int*>(static_cast<char*>(scratch) + align_up((long long)n_tiles * 4, 256));
+  const unsigned long long* rk = reinterpret_cast<const unsigned long long*>(st->row_key);
+  BSC_LAUNCH(k_export_count, n_tiles, kThreads, 0, stream, rk, st->counters, g->cache, ord_lo, ord_hi, tile_count);
+  BSC_LAUNCH(k_export_scan, 1, kThreads, 0, stream, tile_count, tile_off, n_tiles, out_n, max_out);
+  BSC_LAUNCH(k_export_write, n_tiles, kThreads, 0, stream, rk, st->counters, st->slot_cell, st->tok_h, st->feat, g->cache,
+             g->dim, ord_lo, ord_hi, tile_off, d_cell, reinterpret_cast<unsigned long long*>(d_key), d_h, d_feat, max_out);
+  return BSCNAV_OK;
+}
+
+int64_t bscnav_query_scratch_bytes(const bscnav_geom_t* g, int32_t n_query, int32_t k) {
+  if (check_geom(g) || n_query <= 0 || k <= 0 || k > 1024) return BSCNAV_EINVAL;
+  // level-0 keys: kQ * max_slots; then ping-pong candidate buffers
+  const long long lvl0 = (long long)kQ * g->max_slots;
+  const long long chunks = (g->max_slots + kChunk - 1) / kChunk;
+  const long long cand = (long long)kQ * chunks * k;
+  return align_up(lvl0 * 8, 256) + 2 * align_up(cand * 8, 256) + 256;
+}
+
+int bscnav_query_topk(const bscnav_geom_t* g, const bscnav_store_t* st, const float* q, int32_t n_query, int32_t k,
+                      const bscnav_filter_t* filter, void* scratch, int64_t scratch_bytes, float* out_sim,
+                      int32_t* out_pos, int32_t* out_count, void* stream_) {
+  if (int e = check_geom(g)) return e;
+  if (!st || !q || !scratch || !out_sim || !out_pos || !out_count || n_query <= 0 || k <= 0 || k > 1024) return BSCNAV_EINVAL;
+  if (bscnav_query_scratch_bytes(g, n_query, k) > scratch_bytes) return BSCNAV_EINVAL;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  bscnav_filter_t flt;
+  if (filter) flt = *filter; else { flt.radius2 = -1; flt.cur[0] = flt.cur[1] = flt.cur[2] = 0; flt.floor_min = 1; flt.floor_max = 0; flt.reserved = 0; }
+  const long long lvl0 = (long long)kQ * g->max_slots;
+  const long long chunks0 = (g->max_slots + kChunk - 1) / kChunk;
+  const long long cand = (long long)kQ * chunks0 * k;
+  char* base = static_cast<char*>(scratch);
+  unsigned long long* keys0 = reinterpret_cast<unsigned long long*>(base);
+  unsigned long long* bufA = reinterpret_cast<unsigned long long*>(base + align_up(lvl0 * 8, 256));
+  unsigned long long* bufB = reinterpret_cast<unsigned long long*>(base + align_up(lvl0 * 8, 256) + align_up(cand * 8, 256));
+  const int D = g->dim;
+  const int grid = num_sms() * 4;
+  for (int q0 = 0; q0 < n_query; q0 += kQ) {
+    const int nq = (n_query - q0) < kQ ? (n_query - q0) : kQ;
+    const size_t smem = (size_t)nq * D * sizeof(float);
+#define BSC_QUERY_CASE(NV)                                                                                            \
+  case NV: {                                                                                                          \
+    if (smem > 48 * 1024)                                                                                             \
+      BSC_CUDA(cudaFuncSetAttribute(k_query_slots<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    BSC_LAUNCH(k_query_slots<NV>, grid, kThreads, smem, stream, *g, st->feat, st->norm2,                             \
+               reinterpret_cast<const unsigned long long*>(st->row_key), st->slot_cell, st->tok_h, st->counters, q,  \
+               q0, nq, flt, keys0, (long long)g->max_slots);                                                         \
+  } break;
+    switch (D / 128) {
+      BSC_QUERY_CASE(1) BSC_QUERY_CASE(2) BSC_QUERY_CASE(3) BSC_QUERY_CASE(4) BSC_QUERY_CASE(5) BSC_QUERY_CASE(6)
+      BSC_QUERY_CASE(7) BSC_QUERY_CASE(8) BSC_QUERY_CASE(10) BSC_QUERY_CASE(12) BSC_QUERY_CASE(16)
+      default: return BSCNAV_EINVAL;
+    }
+#undef BSC_QUERY_CASE
+    // level 0: n is the device-side slot count, but the grid covers the capacity
+    long long n_chunks = chunks0;
+    BSC_LAUNCH(k_topk_chunks, dim3((unsigned)n_chunks, (unsigned)nq), 1024, 0, stream, keys0, (long long)g->max_slots,
+               st->counters, 0, bufA, n_chunks * k, k);
+    unsigned long long* in = bufA;
+    unsigned long long* out = bufB;
+    long long n_in = n_chunks * k, in_stride = n_chunks * k;
+    while (n_in > k) {
+      n_chunks = (n_in + kChunk - 1) / kChunk;
+      BSC_LAUNCH(k_topk_chunks, dim3((unsigned)n_chunks, (unsigned)nq), 1024, 0, stream, in, in_stride, nullptr, (int)n_in,
+                 out, n_chunks * k, k);
+      in_stride = n_chunks * k;
+      n_in = n_chunks * k;
+      unsigned long long* t = in; in = out; out = t;
+      if (n_chunks == 1) break;
+    }
+    BSC_LAUNCH(k_topk_decode, nq, kThreads, 0, stream, *g, in, in_stride, k, st->occupied_ids,
+               reinterpret_cast<const unsigned long long*>(st->row_key), st->tok_h, st->feat, st->norm2, q, q0,
+               out_sim + (long long)q0 * k, out_pos + (long long)q0 * k * 3, out_count + q0);
+  }
+  return BSCNAV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,212 @@
+// ViT engine: owns nothing but TMA descriptors; weights and workspace are caller-owned device buffers.
+// Replaces dinov2.forward_features (memory_2.py:591-592, 732-742).  Weight blob layout (see vit.py:pack_weights):
+//   half blob : patch_w [D, k_pad] | per layer { qkv_w [3D, D] (q rows pre-scaled by 1/sqrt(dh)), proj_w [D, D] (LayerScale folded),
+//               fc1_w [M, D], fc2_w [D, M] (LayerScale folded) }
+//   float blob: patch_b [D] | cls_pos [D] | reg [n_reg, D] | pos [Np, D] | ln_pre_w, ln_pre_b [D] (if ln_pre) |
+//               per layer { ln1_w, ln1_b [D], qkv_b [3D], proj_b [D], ln2_w, ln2_b [D], fc1_b [M], fc2_b [D] } | ln_post_w, ln_post_b [D]
+#include "gemm_tcgen05.cuh"
+#include "vit_kernels.cuh"
+
+namespace bscnav {
+
+struct LayerOff {
+  long long qkv_w, proj_w, fc1_w, fc2_w;                                   // half blob (elements)
+  long long ln1_w, ln1_b, qkv_b, proj_b, ln2_w, ln2_b, fc1_b, fc2_b;       // float blob (elements)
+};
+
+struct VitLayout {
+  long long patch_w = 0, half_total = 0;
+  long long patch_b = 0, cls_pos = 0, reg = 0, pos = 0, ln_pre_w = 0, ln_pre_b = 0, ln_post_w = 0, ln_post_b = 0, float_total = 0;
+  LayerOff layer[64];
+};
+
+static int vit_layout(const bscnav_vit_cfg_t* c, VitLayout* L) {
+  if (!c || c->depth <= 0 || c->depth > 64 || c->dim % 128 || c->mlp % 128 || c->heads <= 0 || c->dim != c->heads * 64) return BSCNAV_EINVAL;
+  if (c->image % c->patch || c->patch_k_pad % 64 || c->patch_k_pad < 3 * c->patch * c->patch) return BSCNAV_EINVAL;
+  const long long D = c->dim, M = c->mlp, Np = (long long)(c->image / c->patch) * (c->image / c->patch);
+  long long h = 0, f = 0;
+  L->patch_w = h; h += D * c->patch_k_pad;
+  L->patch_b = f; f += D;
+  L->cls_pos = f; f += D;
+  L->reg = f; f += (long long)c->n_reg * D;
+  L->pos = f; f += Np * D;
+  if (c->ln_pre) { L->ln_pre_w = f; f += D; L->ln_pre_b = f; f += D; }
+  for (int i = 0; i < c->depth; ++i) {
+    LayerOff& o = L->layer[i];
+    o.qkv_w = h; h += 3 * D * D;
+    o.proj_w = h; h += D * D;
+    o.fc1_w = h; h += M * D;
+    o.fc2_w = h; h += D * M;
+    o.ln1_w = f; f += D; o.ln1_b = f; f += D;
+    o.qkv_b = f; f += 3 * D;
+    o.proj_b = f; f += D;
+    o.ln2_w = f; f += D; o.ln2_b = f; f += D;
+    o.fc1_b = f; f += M;
+    o.fc2_b = f; f += D;
+  }
+  L->ln_post_w = f; f += D;
+  L->ln_post_b = f; f += D;
+  L->half_total = h;
+  L->float_total = f;
+  return BSCNAV_OK;
+}
+
+struct Workspace {
+  __half* a0;    // [B*Np, k_pad]  patch rows
+  float* x;      // [B*T, D]       residual stream
+  __half* y;     // [B*T, D]       LayerNorm output / attention output
+  __half* qkv;   // [B*T, 3D]
+  __half* ao;    // [B*T, D]
+  __half* hmid;  // [B*T, M]
+  long long total;
+};
+static void workspace_layout(const bscnav_vit_cfg_t* c, int max_batch, Workspace* w, char* base) {
+  const long long D = c->dim, M = c->mlp, G = c->image / c->patch, Np = G * G, T = 1 + c->n_reg + Np, B = max_batch;
+  long long off = 0;
+  auto take = [&](long long bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes, 1024); return p; };
+  w->a0 = reinterpret_cast<__half*>(take(B * Np * c->patch_k_pad * 2));
+  w->x = reinterpret_cast<float*>(take(B * T * D * 4));
+  w->y = reinterpret_cast<__half*>(take(B * T * D * 2));
+  w->qkv = reinterpret_cast<__half*>(take(B * T * 3 * D * 2));
+  w->ao = reinterpret_cast<__half*>(take(B * T * D * 2));
+  w->hmid = reinterpret_cast<__half*>(take(B * T * M * 2));
+  w->total = off;
+}
+
+struct VitEngine {
+  bscnav_vit_cfg_t cfg;
+  VitLayout L;
+  Workspace ws;
+  const __half* wh;
+  const float* wf;
+  int max_batch, Np, T;
+  CUtensorMap map_a0, map_y, map_ao, map_h;          // activation operands
+  CUtensorMap map_patch_w;
+  CUtensorMap map_qkv[64], map_proj[64], map_fc1[64], map_fc2[64];
+  bool a0_cleared = false;
+};
+
+static int vit_run(VitEngine* e, int batch, float* out_tokens, cudaStream_t stream) {
+  const bscnav_vit_cfg_t& c = e->cfg;
+  const int D = c.dim, M = c.mlp, T = e->T, Np = e->Np;
+  const int rows = batch * T;
+  const float* wf = e->wf;
+  // patch embedding + position embedding, written straight into the residual stream at the patch rows
+  GemmEpilogue ep{};
+  ep.out = e->ws.x; ep.bias = wf + e->L.patch_b; ep.table = wf + e->L.pos; ep.ld_out = D; ep.mode = kOutPatchEmbed;
+  ep.np = Np; ep.tokens = T; ep.row_off = 1 + c.n_reg;
+  if (int r = gemm_f16_launch(&e->map_a0, &e->map_patch_w, batch * Np, D, c.patch_k_pad, ep, stream)) return r;
+  if (int r = fill_prefix_tokens(e->ws.x, wf + e->L.cls_pos, wf + e->L.reg, batch, T, c.n_reg, D, stream)) return r;
+  if (c.ln_pre)
+    if (int r = layernorm_inplace(e->ws.x, wf + e->L.ln_pre_w, wf + e->L.ln_pre_b, c.ln_eps, rows, D, stream)) return r;
+  for (int i = 0; i < c.depth; ++i) {
+    const LayerOff& o = e->L.layer[i];
+    if (int r = layernorm_half(e->ws.x, wf + o.ln1_w, wf + o.ln1_b, c.ln_eps, rows, D, e->ws.y, stream)) return r;
+    GemmEpilogue e1{};
+    e1.out = e->ws.qkv; e1.bias = wf + o.qkv_b; e1.ld_out = 3 * D; e1.mode = kOutHalf;
+    if (int r = gemm_f16_launch(&e->map_y, &e->map_qkv[i], rows, 3 * D, D, e1, stream)) return r;
+    if (int r = attention_f16(e->ws.qkv, e->ws.ao, batch, T, c.heads, stream)) return r;
+    GemmEpilogue e2{};
+    e2.out = e->ws.x; e2.bias = wf + o.proj_b; e2.ld_out = D; e2.mode = kOutResidual;
+    if (int r = gemm_f16_launch(&e->map_ao, &e->map_proj[i], rows, D, D, e2, stream)) return r;
+    if (int r = layernorm_half(e->ws.x, wf + o.ln2_w, wf + o.ln2_b, c.ln_eps, rows, D, e->ws.y, stream)) return r;
+    GemmEpilogue e3{};
+    e3.out = e->ws.hmid; e3.bias = wf + o.fc1_b; e3.ld_out = M; e3.mode = kOutHalfAct; e3.act = c.act;
+    if (int r = gemm_f16_launch(&e->map_y, &e->map_fc1[i], rows, M, D, e3, stream)) return r;
+    GemmEpilogue e4{};
+    e4.out = e->ws.x; e4.bias = wf + o.fc2_b; e4.ld_out = D; e4.mode = kOutResidual;
+    if (int r = gemm_f16_launch(&e->map_h, &e->map_fc2[i], rows, D, M, e4, stream)) return r;
+  }
+  return layernorm_patch_tokens(e->ws.x, wf + e->L.ln_post_w, wf + e->L.ln_post_b, c.ln_eps, batch, T, 1 + c.n_reg, D,
+                                out_tokens, stream);
+}
+
+}  // namespace bscnav
+
+using namespace bscnav;
+
+extern "C" {
+
+int64_t bscnav_vit_half_elems(const bscnav_vit_cfg_t* c) {
+  VitLayout L;
+  if (vit_layout(c, &L)) return BSCNAV_EINVAL;
+  return L.half_total;
+}
+int64_t bscnav_vit_float_elems(const bscnav_vit_cfg_t* c) {
+  VitLayout L;
+  if (vit_layout(c, &L)) return BSCNAV_EINVAL;
+  return L.float_total;
+}
+int64_t bscnav_vit_workspace_bytes(const bscnav_vit_cfg_t* c, int32_t max_batch) {
+  VitLayout L;
+  if (vit_layout(c, &L) || max_batch <= 0) return BSCNAV_EINVAL;
+  Workspace w;
+  workspace_layout(c, max_batch, &w, nullptr);
+  return w.total;
+}
+
+int bscnav_vit_create(const bscnav_vit_cfg_t* c, const void* w_half, const float* w_float, void* workspace,
+                      int64_t workspace_bytes, int32_t max_batch, void** out_engine) {
+  if (!c || !w_half || !w_float || !workspace || !out_engine || max_batch <= 0) return BSCNAV_EINVAL;
+  VitEngine* e = new VitEngine();
+  e->cfg = *c;
+  if (int r = vit_layout(c, &e->L)) { delete e; return r; }
+  workspace_layout(c, max_batch, &e->ws, static_cast<char*>(workspace));
+  if (e->ws.total > workspace_bytes) { delete e; return BSCNAV_EINVAL; }
+  e->wh = static_cast<const __half*>(w_half);
+  e->wf = w_float;
+  e->max_batch = max_batch;
+  const int G = c->image / c->patch;
+  e->Np = G * G;
+  e->T = 1 + c->n_reg + e->Np;
+  const long long D = c->dim, M = c->mlp, rows = (long long)max_batch * e->T;
+  int r = 0;
+  r = r ? r : make_operand_map(&e->map_a0, e->ws.a0, (long long)max_batch * e->Np, c->patch_k_pad, 128);
+  r = r ? r : make_operand_map(&e->map_y, e->ws.y, rows, D, 128);
+  r = r ? r : make_operand_map(&e->map_ao, e->ws.ao, rows, D, 128);
+  r = r ? r : make_operand_map(&e->map_h, e->ws.hmid, rows, M, 128);
+  r = r ? r : make_operand_map(&e->map_patch_w, e->wh + e->L.patch_w, D, c->patch_k_pad, gemm_block_n((int)D));
+  for (int i = 0; i < c->depth && !r; ++i) {
+    const LayerOff& o = e->L.layer[i];
+    r = r ? r : make_operand_map(&e->map_qkv[i], e->wh + o.qkv_w, 3 * D, D, gemm_block_n((int)(3 * D)));
+    r = r ? r : make_operand_map(&e->map_proj[i], e->wh + o.proj_w, D, D, gemm_block_n((int)D));
+    r = r ? r : make_operand_map(&e->map_fc1[i], e->wh + o.fc1_w, M, D, gemm_block_n((int)M));
+    r = r ? r : make_operand_map(&e->map_fc2[i], e->wh + o.fc2_w, D, M, gemm_block_n((int)D));
+  }
+  if (r) { delete e; return r; }
+  *out_engine = e;
+  return BSCNAV_OK;
+}
+
+void bscnav_vit_destroy(void* engine) { delete static_cast<VitEngine*>(engine); }
+
+static int clear_a0_once(VitEngine* e, cudaStream_t stream) {
+  // the K padding columns of the patch rows are never written by im2col: zero them once
+  if (!e->a0_cleared) {
+    BSC_CUDA(cudaMemsetAsync(e->ws.a0, 0, (size_t)e->max_batch * e->Np * e->cfg.patch_k_pad * 2, stream));
+    e->a0_cleared = true;
+  }
+  return BSCNAV_OK;
+}
+
+int bscnav_vit_forward_frames(void* engine, const uint8_t* rgb, int32_t batch, int32_t height, int32_t width,
+                              int32_t channels, float* out_tokens, float* out_pre, void* stream_) {
+  VitEngine* e = static_cast<VitEngine*>(engine);
+  if (!e || !rgb || !out_tokens || batch <= 0 || batch > e->max_batch) return BSCNAV_EINVAL;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int r = clear_a0_once(e, stream)) return r;
+  if (int r = preprocess_frames(rgb, batch, height, width, channels, e->cfg.image, e->cfg.patch, e->cfg.patch_k_pad, e->ws.a0,
+                                out_pre, stream)) return r;
+  return vit_run(e, batch, out_tokens, stream);
+}
+
+int bscnav_vit_forward_images(void* engine, const float* images, int32_t batch, float* out_tokens, void* stream_) {
+  VitEngine* e = static_cast<VitEngine*>(engine);
+  if (!e || !images || !out_tokens || batch <= 0 || batch > e->max_batch) return BSCNAV_EINVAL;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int r = clear_a0_once(e, stream)) return r;
+  if (int r = im2col_images(images, batch, e->cfg.image, e->cfg.patch, e->cfg.patch_k_pad, e->ws.a0, stream)) return r;
+  return vit_run(e, batch, out_tokens, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,391 @@
+// ViT support kernels (sm_100a): fused pre-processing + im2col, LayerNorm, attention, token assembly,
+// Gaussian query pooling.  The dense contractions live in gemm_tcgen05.cu.
+#include "vit_kernels.cuh"
+
+namespace bscnav {
+
+// ---------------------------------------------------------------------------------------------------------
+// Pre-processing fused with im2col (memory_2.py:71-74,733-735): uint8 HWC frame -> /255 -> antialiased bilinear
+// resize (ATen upsample_bilinear2d_aa: triangle filter, support = max(scale,1), weights normalised, horizontal
+// pass then vertical) -> (x-mean)/std -> fp16 patch rows [frame*Np + patch, c*P*P + ky*P + kx].
+static constexpr int kMaxTaps = 34;
+
+__device__ __forceinline__ int aa_taps(int i, float scale, int in_size, float* w, int* start) {
+  const float support = scale >= 1.f ? scale : 1.f;
+  const float invscale = scale >= 1.f ? 1.f / scale : 1.f;
+  const float center = scale * ((float)i + 0.5f);
+  int lo = (int)(center - support + 0.5f);
+  if (lo < 0) lo = 0;
+  int hi = (int)(center + support + 0.5f);
+  if (hi > in_size) hi = in_size;
+  int n = hi - lo;
+  if (n > kMaxTaps) n = kMaxTaps;
+  float total = 0.f;
+  for (int j = 0; j < n; ++j) {
+    float x = ((float)(j + lo) - center + 0.5f) * invscale;
+    x = fabsf(x);
+    const float v = x < 1.f ? 1.f - x : 0.f;
+    w[j] = v;
+    total += v;
+  }
+  if (total != 0.f)
+    for (int j = 0; j < n; ++j) w[j] /= total;
+  *start = lo;
+  return n;
+}
+
+__global__ void __launch_bounds__(256)
+k_preprocess_frames(const uint8_t* __restrict__ rgb, int batch, int H, int W, int ch, int S, int P, int k_pad,
+                    __half* __restrict__ a0, float* __restrict__ out_pre) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)batch * S * S;
+  if (idx >= total) return;
+  const int ox = (int)(idx % S);
+  const int oy = (int)((idx / S) % S);
+  const int b = (int)(idx / ((long long)S * S));
+  float wx[kMaxTaps], wy[kMaxTaps];
+  int x0, y0;
+  const int nx = aa_taps(ox, (float)W / (float)S, W, wx, &x0);
+  const int ny = aa_taps(oy, (float)H / (float)S, H, wy, &y0);
+  float acc[3] = {0.f, 0.f, 0.f};
+  const uint8_t* frame = rgb + (long long)b * H * W * ch;
+  for (int jy = 0; jy < ny; ++jy) {
+    const uint8_t* rowp = frame + ((long long)(y0 + jy) * W + x0) * ch;
+    float r[3] = {0.f, 0.f, 0.f};
+    for (int jx = 0; jx < nx; ++jx) {
+      const float w = wx[jx];
+      r[0] += w * ((float)rowp[jx * ch + 0] / 255.f);
+      r[1] += w * ((float)rowp[jx * ch + 1] / 255.f);
+      r[2] += w * ((float)rowp[jx * ch + 2] / 255.f);
+    }
+    acc[0] += wy[jy] * r[0]; acc[1] += wy[jy] * r[1]; acc[2] += wy[jy] * r[2];
+  }
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+  const int G = S / P;
+  const int py = oy / P, ky = oy - py * P, px = ox / P, kx = ox - px * P;
+  const long long rowi = (long long)b * G * G + py * G + px;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = (acc[c] - mean[c]) / stdv[c];
+    if (out_pre) out_pre[((long long)(b * 3 + c) * S + oy) * S + ox] = v;
+    a0[rowi * k_pad + c * P * P + ky * P + kx] = __float2half_rn(v);
+  }
+}
+
+// already-normalised float images [B,3,S,S] -> fp16 patch rows (query path, memory_2.py:577-580)
+__global__ void __launch_bounds__(256)
+k_im2col_images(const float* __restrict__ img, int batch, int S, int P, int k_pad, __half* __restrict__ a0) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)batch * 3 * S * S;
+  if (idx >= total) return;
+  const int ox = (int)(idx % S);
+  const int oy = (int)((idx / S) % S);
+  const int c = (int)((idx / ((long long)S * S)) % 3);
+  const int b = (int)(idx / ((long long)3 * S * S));
+  const int G = S / P;
+  const int py = oy / P, ky = oy - py * P, px = ox / P, kx = ox - px * P;
+  a0[((long long)b * G * G + py * G + px) * k_pad + c * P * P + ky * P + kx] = __float2half_rn(img[idx]);
+}
+
+// cls (+pos[0]) and register tokens of every frame
+__global__ void k_fill_prefix_tokens(float* __restrict__ x, const float* __restrict__ cls_pos, const float* __restrict__ reg,
+                                     int batch, int tokens, int n_reg, int D) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)batch * (1 + n_reg) * D;
+  if (idx >= total) return;
+  const int c = (int)(idx % D);
+  const int t = (int)((idx / D) % (1 + n_reg));
+  const int b = (int)(idx / ((long long)D * (1 + n_reg)));
+  x[((long long)b * tokens + t) * D + c] = t == 0 ? cls_pos[c] : reg[(long long)(t - 1) * D + c];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// LayerNorm over the last dimension, one warp per row, two passes in registers (mean, then centred variance).
+//   MODE 0: fp16 out (GEMM operand)   MODE 1: fp32 in place   MODE 2: fp32 out, patch rows only (drop cls/registers)
+template <int NV, int MODE>
+__global__ void __launch_bounds__(256)
+k_layernorm(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+            long long rows, void* __restrict__ out, int tokens, int skip) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  constexpr int D = NV * 128;
+  long long in_row = row;
+  if (MODE == 2) {
+    const int np = tokens - skip;
+    const long long f = row / np;
+    in_row = f * tokens + skip + (row - f * np);
+  }
+  const float4* xr = reinterpret_cast<const float4*>(x + in_row * D);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = xr[lane + 32 * i];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g = g4[lane + 32 * i], bb = b4[lane + 32 * i];
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * g.x + bb.x;
+    o.y = (v[i].y - mean) * rstd * g.y + bb.y;
+    o.z = (v[i].z - mean) * rstd * g.z + bb.z;
+    o.w = (v[i].w - mean) * rstd * g.w + bb.w;
+    if (MODE == 0) {
+      __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&h0);
+      u.y = *reinterpret_cast<uint32_t*>(&h1);
+      reinterpret_cast<uint2*>(static_cast<__half*>(out) + row * D)[lane + 32 * i] = u;
+    } else {
+      reinterpret_cast<float4*>(static_cast<float*>(out) + row * D)[lane + 32 * i] = o;
+    }
+  }
+}
+
+template <int MODE>
+static int layernorm_dispatch(const float* x, const float* g, const float* b, float eps, long long rows, int D, void* out,
+                              int tokens, int skip, cudaStream_t stream) {
+  const int grid = (int)((rows + 7) / 8);
+#define BSC_LN_CASE(NV) case NV: BSC_LAUNCH((k_layernorm<NV, MODE>), grid, 256, 0, stream, x, g, b, eps, rows, out, tokens, skip); break;
+  switch (D / 128) {
+    BSC_LN_CASE(1) BSC_LN_CASE(2) BSC_LN_CASE(3) BSC_LN_CASE(4) BSC_LN_CASE(5) BSC_LN_CASE(6) BSC_LN_CASE(7) BSC_LN_CASE(8)
+    BSC_LN_CASE(10) BSC_LN_CASE(12) BSC_LN_CASE(16)
+    default: return BSCNAV_EINVAL;
+  }
+#undef BSC_LN_CASE
+  return BSCNAV_OK;
+}
+
+int layernorm_half(const float* x, const float* g, const float* b, float eps, long long rows, int D, __half* out, cudaStream_t s) {
+  if (D % 128) return BSCNAV_EINVAL;
+  return layernorm_dispatch<0>(x, g, b, eps, rows, D, out, 0, 0, s);
+}
+int layernorm_inplace(float* x, const float* g, const float* b, float eps, long long rows, int D, cudaStream_t s) {
+  if (D % 128) return BSCNAV_EINVAL;
+  return layernorm_dispatch<1>(x, g, b, eps, rows, D, x, 0, 0, s);
+}
+int layernorm_patch_tokens(const float* x, const float* g, const float* b, float eps, int batch, int tokens, int skip, int D,
+                           float* out, cudaStream_t s) {
+  if (D % 128) return BSCNAV_EINVAL;
+  return layernorm_dispatch<2>(x, g, b, eps, (long long)batch * (tokens - skip), D, out, tokens, skip, s);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Multi-head self-attention, head dim 64, fp16 operands, fp32 softmax / accumulation.
+// One CTA = 64 queries of one (frame, head); 4 warps x 16 query rows; K and V of the head staged once in shared
+// memory (16-byte chunks XOR-swizzled by row so ldmatrix is conflict-free); flash-style online softmax over
+// 64-key blocks with mma.sync.m16n8k16 -- 4% of the ViT's FLOPs; the GEMMs carry the tcgen05 work.
+static constexpr int kHd = 64;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// byte offset of (row, 16-byte chunk) in a [rows][64] fp16 tile with the chunk index XOR-swizzled by row
+__device__ __forceinline__ uint32_t sw_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+
+__global__ void __launch_bounds__(128)
+k_attention(const __half* __restrict__ qkv, __half* __restrict__ out, int T, int heads, int t_pad) {
+  extern __shared__ __align__(128) uint8_t smem_attn[];
+  uint8_t* sQ = smem_attn;                       // 64 x 128 B
+  uint8_t* sK = sQ + 64 * 128;                   // t_pad x 128 B
+  uint8_t* sV = sK + (size_t)t_pad * 128;        // t_pad x 128 B
+  const int D = heads * kHd;
+  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const __half* base = qkv + (long long)b * T * 3 * D + head * kHd;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 64 * 8; i += 128) {
+    const int r = i >> 3, c = i & 7, t = qt * 64 + r;
+    const uint4 v = t < T ? *reinterpret_cast<const uint4*>(base + (long long)t * 3 * D + c * 8) : zero;
+    *reinterpret_cast<uint4*>(sQ + sw_off(r, c)) = v;
+  }
+  for (int i = tid; i < t_pad * 8; i += 128) {
+    const int r = i >> 3, c = i & 7;
+    uint4 kv = zero, vv = zero;
+    if (r < T) {
+      kv = *reinterpret_cast<const uint4*>(base + (long long)r * 3 * D + D + c * 8);
+      vv = *reinterpret_cast<const uint4*>(base + (long long)r * 3 * D + 2 * D + c * 8);
+    }
+    *reinterpret_cast<uint4*>(sK + sw_off(r, c)) = kv;
+    *reinterpret_cast<uint4*>(sV + sw_off(r, c)) = vv;
+  }
+  __syncthreads();
+  const uint32_t sQa = (uint32_t)__cvta_generic_to_shared(sQ), sKa = (uint32_t)__cvta_generic_to_shared(sK),
+                 sVa = (uint32_t)__cvta_generic_to_shared(sV);
+  // Q fragments: 4 k-steps of 16 along the head dim
+  uint32_t qf[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+    ldsm_x4(sQa + sw_off(warp * 16 + (lane & 15), ks * 2 + (lane >> 4)), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+
+  float o[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // running max / sum of rows (lane/4) and (lane/4)+8
+  const float kLog2e = 1.4426950408889634f;
+
+  for (int kb = 0; kb < t_pad / 64; ++kb) {
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+    // S = Q K^T for 64 keys: B fragments straight from K rows (key-major, head dim contiguous)
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {     // pairs of 8-key tiles
+        uint32_t b0, b1, b2, b3;
+        const int key = kb * 64 + np * 16 + (lane & 7) + ((lane >> 4) << 3);
+        ldsm_x4(sKa + sw_off(key, ks * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
+        mma_16816(s[2 * np], qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], b0, b1);
+        mma_16816(s[2 * np + 1], qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], b2, b3);
+      }
+    }
+    // mask keys >= T, block row maxima
+    float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int key = kb * 64 + i * 8 + 2 * (lane & 3);
+      if (key >= T) { s[i][0] = -INFINITY; s[i][2] = -INFINITY; }
+      if (key + 1 >= T) { s[i][1] = -INFINITY; s[i][3] = -INFINITY; }
+      bm0 = fmaxf(bm0, fmaxf(s[i][0], s[i][1]));
+      bm1 = fmaxf(bm1, fmaxf(s[i][2], s[i][3]));
+    }
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+    const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);      // finite: every block holds at least one valid key
+    const float sc0 = exp2f((m0 - nm0) * kLog2e), sc1 = exp2f((m1 - nm1) * kLog2e);
+    m0 = nm0; m1 = nm1;
+    float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s[i][0] = exp2f((s[i][0] - m0) * kLog2e); s[i][1] = exp2f((s[i][1] - m0) * kLog2e);
+      s[i][2] = exp2f((s[i][2] - m1) * kLog2e); s[i][3] = exp2f((s[i][3] - m1) * kLog2e);
+      ps0 += s[i][0] + s[i][1];
+      ps1 += s[i][2] + s[i][3];
+    }
+    l0 = l0 * sc0 + ps0;
+    l1 = l1 * sc1 + ps1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o[i][0] *= sc0; o[i][1] *= sc0; o[i][2] *= sc1; o[i][3] *= sc1; }
+    // O += P V : P from the S accumulators (fp16), V fragments via transposing ldmatrix
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {       // 16 keys per step
+      const uint32_t a0 = pack_half2(s[2 * ks][0], s[2 * ks][1]), a1 = pack_half2(s[2 * ks][2], s[2 * ks][3]);
+      const uint32_t a2 = pack_half2(s[2 * ks + 1][0], s[2 * ks + 1][1]), a3 = pack_half2(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {     // pairs of 8-wide head-dim tiles
+        uint32_t b0, b1, b2, b3;
+        const int key = kb * 64 + ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+        ldsm_x4_t(sVa + sw_off(key, np * 2 + (lane >> 4)), b0, b1, b2, b3);
+        mma_16816(o[2 * np], a0, a1, a2, a3, b0, b1);
+        mma_16816(o[2 * np + 1], a0, a1, a2, a3, b2, b3);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  const int r0 = qt * 64 + warp * 16 + (lane >> 2), r1 = r0 + 8;
+  __half* ob = out + (long long)b * T * D + head * kHd + 2 * (lane & 3);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (r0 < T) *reinterpret_cast<uint32_t*>(ob + (long long)r0 * D + i * 8) = pack_half2(o[i][0] * i0, o[i][1] * i0);
+    if (r1 < T) *reinterpret_cast<uint32_t*>(ob + (long long)r1 * D + i * 8) = pack_half2(o[i][2] * i1, o[i][3] * i1);
+  }
+}
+
+int attention_f16(const __half* qkv, __half* out, int batch, int T, int heads, cudaStream_t stream) {
+  if (batch <= 0 || T <= 0 || heads <= 0) return BSCNAV_EINVAL;
+  const int t_pad = (T + 63) / 64 * 64;
+  const size_t smem = 64 * 128 + 2 * (size_t)t_pad * 128;
+  if (smem > 200 * 1024) return BSCNAV_EINVAL;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    BSC_CUDA(cudaFuncSetAttribute(k_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  BSC_LAUNCH(k_attention, dim3((unsigned)(t_pad / 64), (unsigned)heads, (unsigned)batch), 128, smem, stream, qkv, out, T, heads, t_pad);
+  return BSCNAV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Gaussian centre-weighted pooling (memory_2.py:596-608): q = mean_b sum_i w_i t[b,i,:], w_i ~ exp(-d_i / (2 (g/2)^2))
+__global__ void k_gaussian_pool(const float* __restrict__ tokens, int batch, int grid, int D, float* __restrict__ out) {
+  extern __shared__ float w[];
+  const int n = grid * grid;
+  const float center = (grid - 1) / 2.f, sigma = (grid / 2.f) * (grid / 2.f);
+  __shared__ float wsum;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float xs = (float)(i % grid), ys = (float)(i / grid);
+    const float d = (xs - center) * (xs - center) + (ys - center) * (ys - center);
+    w[i] = expf(-d / (2.f * sigma));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < n; ++i) s += w[i];
+    wsum = s;
+  }
+  __syncthreads();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  float acc_b = 0.f;
+  for (int b = 0; b < batch; ++b) {
+    float acc = 0.f;
+    for (int i = 0; i < n; ++i) acc += tokens[((long long)b * n + i) * D + c] * (w[i] / wsum);
+    acc_b += acc;
+  }
+  out[c] = acc_b / (float)batch;
+}
+
+int preprocess_frames(const uint8_t* rgb, int batch, int H, int W, int ch, int S, int P, int k_pad, __half* a0, float* out_pre,
+                      cudaStream_t stream) {
+  if (batch <= 0 || H <= 0 || W <= 0 || (ch != 3 && ch != 4) || S % P) return BSCNAV_EINVAL;
+  if ((float)W / S > 16.f || (float)H / S > 16.f) return BSCNAV_EINVAL;   // tap buffer bound
+  const long long total = (long long)batch * S * S;
+  BSC_LAUNCH(k_preprocess_frames, (unsigned)((total + 255) / 256), 256, 0, stream, rgb, batch, H, W, ch, S, P, k_pad, a0, out_pre);
+  return BSCNAV_OK;
+}
+int im2col_images(const float* img, int batch, int S, int P, int k_pad, __half* a0, cudaStream_t stream) {
+  const long long total = (long long)batch * 3 * S * S;
+  BSC_LAUNCH(k_im2col_images, (unsigned)((total + 255) / 256), 256, 0, stream, img, batch, S, P, k_pad, a0);
+  return BSCNAV_OK;
+}
+int fill_prefix_tokens(float* x, const float* cls_pos, const float* reg, int batch, int tokens, int n_reg, int D, cudaStream_t stream) {
+  const long long total = (long long)batch * (1 + n_reg) * D;
+  BSC_LAUNCH(k_fill_prefix_tokens, (unsigned)((total + 255) / 256), 256, 0, stream, x, cls_pos, reg, batch, tokens, n_reg, D);
+  return BSCNAV_OK;
+}
+
+}  // namespace bscnav
+
+using namespace bscnav;
+
+extern "C" int bscnav_gaussian_pool(const float* tokens, int32_t batch, int32_t grid, int32_t dim, float* out, void* stream) {
+  if (!tokens || !out || batch <= 0 || grid <= 0 || grid > 64 || dim <= 0) return BSCNAV_EINVAL;
+  BSC_LAUNCH(k_gaussian_pool, (dim + 255) / 256, 256, grid * grid * sizeof(float), (cudaStream_t)stream, tokens, batch, grid, dim, out);
+  return BSCNAV_OK;
+}

@@ -1,0 +1,17 @@
+// Host-callable launchers of the ViT support kernels (vit_kernels.cu).
+#pragma once
+#include "common.cuh"
+
+namespace bscnav {
+
+int preprocess_frames(const uint8_t* rgb, int batch, int H, int W, int ch, int S, int P, int k_pad, __half* a0, float* out_pre,
+                      cudaStream_t stream);
+int im2col_images(const float* img, int batch, int S, int P, int k_pad, __half* a0, cudaStream_t stream);
+int fill_prefix_tokens(float* x, const float* cls_pos, const float* reg, int batch, int tokens, int n_reg, int D, cudaStream_t stream);
+int layernorm_half(const float* x, const float* g, const float* b, float eps, long long rows, int D, __half* out, cudaStream_t s);
+int layernorm_inplace(float* x, const float* g, const float* b, float eps, long long rows, int D, cudaStream_t s);
+int layernorm_patch_tokens(const float* x, const float* g, const float* b, float eps, int batch, int tokens, int skip, int D,
+                           float* out, cudaStream_t s);
+int attention_f16(const __half* qkv, __half* out, int batch, int T, int heads, cudaStream_t stream);
+
+}  // namespace bscnav

@@ -1,0 +1,213 @@
+"""Device-resident spatial store: the HBM layout behind VoxelTokenMemory and the thin wrappers over the C ABI.
+
+Replaces the reference's host buffers + HDF5 token file (memory_2.py:708-722, 326-358): occupancy index, per-cell
+top-C winner keys, token rows and their norms all live in HBM (layout in include/bscnav_b200.h: bscnav_store_t).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from .geometry import sim_cam_mat, sim_cam_mat_with_fov
+
+
+@dataclass
+class StoreConfig:
+    height: int
+    width: int
+    grid_size: int = 1000
+    cell_size: float = 0.1
+    floor_height: float = -10.0
+    map_height: float = 10.0
+    min_depth: float = 0.1
+    max_depth: float = 10
+    n_patch_h: int = 16
+    n_patch_w: int = 16
+    token_dim: int = 1024
+    cache_size: int = 10           # C (memory_2.py:111)
+    bev: bool = False              # key reduced over h: the north-star "512x512 BEV feature grid"
+    max_slots: int | None = None   # default gs*gs, the reference's capacity (memory_2.py:715-718)
+    calib_mat: np.ndarray | None = None
+
+    def geom(self) -> _lib.Geom:
+        gs, cs = int(self.grid_size), float(self.cell_size)
+        maxh = int(self.map_height / cs)       # memory_2.py:122
+        minh = int(self.floor_height / cs)     # memory_2.py:123
+        k = self.calib_mat if self.calib_mat is not None else sim_cam_mat_with_fov(self.height, self.width, fov=90)
+        k = np.asarray(k, dtype=np.float64)
+        kinv = np.linalg.inv(k)                # utils.py:164
+        kp = sim_cam_mat(self.n_patch_w, self.n_patch_h)   # get_sim_cam_mat(shape[0], shape[1]) of the (W', H', D) token array
+        g = _lib.Geom(height=self.height, width=self.width, gs=gs, minh=minh, maxh=maxh,
+                      levels=1 if self.bev else maxh - minh, n_patch_h=self.n_patch_h, n_patch_w=self.n_patch_w,
+                      cache=int(self.cache_size), dim=int(self.token_dim),
+                      max_slots=int(self.max_slots if self.max_slots is not None else gs * gs), reserved=0,
+                      cs=cs, min_depth=float(self.min_depth), max_depth=float(self.max_depth))
+        g.kinv[:] = kinv.reshape(-1).tolist()
+        g.kimg[:] = k.reshape(-1).tolist()
+        g.kpatch[:] = kp.reshape(-1).tolist()
+        return g
+
+
+class SpatialStore:
+    def __init__(self, cfg: StoreConfig, device="cuda"):
+        self.lib = _lib.lib()
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.g = cfg.geom()
+        g = self.g
+        cells = g.gs * g.gs * g.levels
+        rows = g.max_slots * g.cache
+        dev = self.device
+        self.occupied_ids = torch.empty(cells, dtype=torch.int32, device=dev)
+        self.first_touch = torch.empty(cells, dtype=torch.int32, device=dev)
+        self.slot_cell = torch.empty(g.max_slots, dtype=torch.int32, device=dev)
+        self.slot_keys = torch.empty(rows, dtype=torch.int64, device=dev)
+        self.row_key = torch.empty(rows, dtype=torch.int64, device=dev)
+        self.tok_h = torch.empty(rows, dtype=torch.int32, device=dev)
+        self.norm2 = torch.empty(rows, dtype=torch.float32, device=dev)
+        self.feat = torch.empty(rows, g.dim, dtype=torch.float32, device=dev)
+        self.counters = torch.zeros(8, dtype=torch.int32, device=dev)
+        self.st = _lib.Store(*[C.c_void_p(t.data_ptr()) for t in (self.occupied_ids, self.first_touch, self.slot_cell,
+                                                                   self.slot_keys, self.row_key, self.tok_h, self.norm2,
+                                                                   self.feat, self.counters)])
+        self._scratch = None
+        self._qscratch = None
+        self.next_ordinal = 0
+        self.reset()
+
+    # ------------------------------------------------------------------ build
+    def reset(self):
+        _lib.check(self.lib.bscnav_store_reset(C.byref(self.g), C.byref(self.st), _lib.stream_ptr()), "store_reset")
+        self.next_ordinal = 0
+
+    def _scratch_for(self, nbytes: int) -> torch.Tensor:
+        if self._scratch is None or self._scratch.numel() < nbytes:
+            self._scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._scratch
+
+    def fuse(self, depth: torch.Tensor, poses, tokens: torch.Tensor, sample_idx: torch.Tensor | None = None,
+             ord_base=None, want_records: bool = False):
+        """Fuse a batch: depth (B,H,W) f32 device, poses (B,4,4) float64 (host array or device tensor),
+        tokens (B, n_patch, D) f32 device; sample_idx (B, n_points) int32 device or None for dense raster order."""
+        g = self.g
+        B = depth.shape[0]
+        assert depth.dtype == torch.float32 and depth.is_cuda and depth.is_contiguous() and depth.shape[1:] == (g.height, g.width)
+        assert tokens.dtype == torch.float32 and tokens.is_contiguous() and tokens.shape == (B, g.n_patch_h * g.n_patch_w, g.dim)
+        n_points = g.height * g.width if sample_idx is None else sample_idx.shape[1]
+        if not torch.is_tensor(poses):
+            poses = torch.from_numpy(np.ascontiguousarray(np.asarray(poses, dtype=np.float64).reshape(B, 16))).to(self.device, non_blocking=True)
+        assert poses.dtype == torch.float64 and poses.numel() == B * 16
+        if ord_base is None:
+            if self.next_ordinal + B * n_points >= 2 ** 32:
+                raise _lib.BscnavError("ordinal range exceeded (2^32 points per store)")
+            ord_base = self.next_ordinal + np.arange(B, dtype=np.int64) * n_points
+            self.next_ordinal += B * n_points
+        ob = torch.from_numpy(np.asarray(ord_base, dtype=np.int64).astype(np.uint32).view(np.int32)).to(self.device, non_blocking=True)
+        nbytes = _lib.check(self.lib.bscnav_fuse_scratch_bytes(B, n_points), "fuse_scratch_bytes")
+        scratch = self._scratch_for(nbytes)
+        rec = torch.empty(B * n_points, 4, dtype=torch.int32, device=self.device) if want_records else None
+        if sample_idx is not None:
+            assert sample_idx.dtype == torch.int32 and sample_idx.is_contiguous()
+        _lib.check(self.lib.bscnav_fuse_frames(C.byref(g), C.byref(self.st), _lib.ptr(depth), _lib.ptr(poses), _lib.ptr(ob),
+                                               _lib.ptr(sample_idx), B, n_points, _lib.ptr(tokens), _lib.ptr(scratch), nbytes,
+                                               _lib.ptr(rec), _lib.stream_ptr()), "fuse_frames")
+        return rec
+
+    def count(self) -> int:
+        """Slots in use (max_id, memory_2.py:894); synchronises.  Raises if a batch overflowed the slot capacity."""
+        c = self.counters[:2].tolist()
+        if c[1]:
+            raise _lib.BscnavError(f"slot capacity {self.g.max_slots} exceeded (reference: IndexError at memory_2.py:891)")
+        return int(c[0])
+
+    # ------------------------------------------------------------------ query
+    def query(self, q: torch.Tensor, k: int = 100, region_radius=np.inf, curr_grid=None, floor_range=None):
+        """q (Q, D) f32 device -> (sims (Q,k) f32, positions (Q,k,3) i32, counts (Q,) i32), device tensors."""
+        g = self.g
+        q = q.to(self.device, torch.float32).contiguous()
+        Q = q.shape[0]
+        assert q.shape[1] == g.dim
+        flt = _lib.Filter(radius2=-1, floor_min=1, floor_max=0, reserved=0)
+        if region_radius != np.inf:
+            flt.radius2 = int(np.floor(float(region_radius) ** 2))   # d2 integer: d2 <= r^2  <=>  d2 <= floor(r^2)
+            flt.cur[:] = [int(v) for v in curr_grid]
+        if floor_range is not None:
+            flt.floor_min, flt.floor_max = int(floor_range[0]), int(floor_range[1])
+        nbytes = _lib.check(self.lib.bscnav_query_scratch_bytes(C.byref(g), Q, k), "query_scratch_bytes")
+        if self._qscratch is None or self._qscratch.numel() < nbytes:
+            self._qscratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        sims = torch.empty(Q, k, dtype=torch.float32, device=self.device)
+        pos = torch.empty(Q, k, 3, dtype=torch.int32, device=self.device)
+        cnt = torch.empty(Q, dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.bscnav_query_topk(C.byref(g), C.byref(self.st), _lib.ptr(q), Q, k, C.byref(flt),
+                                              _lib.ptr(self._qscratch), nbytes, _lib.ptr(sims), _lib.ptr(pos), _lib.ptr(cnt),
+                                              _lib.stream_ptr()), "query_topk")
+        return sims, pos, cnt
+
+    # ------------------------------------------------------------------ multi-GPU deltas
+    def export_delta(self, ord_lo: int, ord_hi: int, max_out: int):
+        g = self.g
+        dev = self.device
+        d_cell = torch.full((max_out,), -1, dtype=torch.int32, device=dev)
+        d_key = torch.empty(max_out, dtype=torch.int64, device=dev)
+        d_h = torch.empty(max_out, dtype=torch.int32, device=dev)
+        d_feat = torch.empty(max_out, g.dim, dtype=torch.float32, device=dev)
+        n = torch.zeros(1, dtype=torch.int32, device=dev)
+        nbytes = _lib.check(self.lib.bscnav_export_scratch_bytes(C.byref(g)), "export_scratch_bytes")
+        scratch = self._scratch_for(nbytes)
+        _lib.check(self.lib.bscnav_export_delta(C.byref(g), C.byref(self.st), ord_lo, ord_hi, _lib.ptr(d_cell), _lib.ptr(d_key),
+                                                _lib.ptr(d_h), _lib.ptr(d_feat), max_out, _lib.ptr(n), _lib.ptr(scratch), nbytes,
+                                                _lib.stream_ptr()), "export_delta")
+        return d_cell, d_key, d_h, d_feat, n
+
+    def merge_delta(self, d_cell, d_key, d_h, d_feat):
+        n = d_cell.numel()
+        chunk = 1 << 20
+        for s in range(0, n, chunk):
+            e = min(n, s + chunk)
+            nbytes = _lib.check(self.lib.bscnav_fuse_scratch_bytes(1, e - s), "fuse_scratch_bytes")
+            scratch = self._scratch_for(nbytes)
+            _lib.check(self.lib.bscnav_merge_delta(C.byref(self.g), C.byref(self.st), _lib.ptr(d_cell[s:e]), _lib.ptr(d_key[s:e]),
+                                                   _lib.ptr(d_h[s:e]), _lib.ptr(d_feat[s:e]), e - s, _lib.ptr(scratch), nbytes,
+                                                   _lib.stream_ptr()), "merge_delta")
+
+    # ------------------------------------------------------------------ host views (tests, I/O)
+    def positions(self) -> np.ndarray:
+        """(max_id, 3) int32 [row, col, h-minh] in slot order (grid_rgb_pos, memory_2.py:893).  BEV keys: h of the best token."""
+        n = self.count()
+        g = self.g
+        cell = self.slot_cell[:n].cpu().numpy().astype(np.int64)
+        if g.levels == 1:
+            h = self.tok_h.view(-1, g.cache)[:n, 0].cpu().numpy()
+            rc = cell
+        else:
+            h = cell % g.levels
+            rc = cell // g.levels
+        return np.stack([rc // g.gs, rc % g.gs, h], axis=1).astype(np.int32)
+
+    def snapshot(self) -> dict:
+        """Host copy of the kept tokens: {(row,col[,h]): [(r2 f32, ordinal, h, feature row)] best first}."""
+        n = self.count()
+        g = self.g
+        C_ = g.cache
+        keys = self.row_key.view(-1, C_)[:n].cpu().numpy().view(np.uint64)
+        hs = self.tok_h.view(-1, C_)[:n].cpu().numpy()
+        feat = self.feat.view(-1, C_, g.dim)[:n].cpu().numpy()
+        pos = self.positions()
+        out = {}
+        for s in range(n):
+            items = []
+            for j in range(C_):
+                k = int(keys[s, j])
+                if k == _lib.KEY_EMPTY:
+                    continue
+                r2 = np.array([k >> 32], dtype=np.uint32).view(np.float32)[0]
+                items.append((r2, k & 0xFFFFFFFF, int(hs[s, j]), feat[s, j]))
+            items.sort(key=lambda t: (t[0], t[1]))
+            key = (int(pos[s, 0]), int(pos[s, 1])) if g.levels == 1 else (int(pos[s, 0]), int(pos[s, 1]), int(pos[s, 2]))
+            out[key] = items
+        return out

@@ -1,0 +1,148 @@
+"""ViT feature extractor engine (host side): weight packing and the `forward_features` plug-point.
+
+The object returned by `ViTEngine(...)` can be passed as `preload_dino` to VoxelTokenMemory exactly like the
+torch.hub DINOv2 module the reference passes (create_memory_for_dataset.py:58-70, memory_2.py:43-46): it exposes
+`forward_features(x) -> {'x_norm_patchtokens': (B, n_patch, D)}`.  All arithmetic runs in libbscnav_b200.so
+(tcgen05 GEMMs, fp16 operands / fp32 accumulation, fp32 residual stream, LayerNorm and softmax).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from .vit_config import ViTConfig
+
+
+def _cfg_struct(cfg: ViTConfig) -> _lib.VitCfg:
+    k_pad = (cfg.patch_k + 63) // 64 * 64
+    return _lib.VitCfg(image=cfg.image, patch=cfg.patch, dim=cfg.dim, depth=cfg.depth, heads=cfg.heads, mlp=cfg.mlp,
+                       n_reg=cfg.n_reg, act=0 if cfg.act == "gelu" else 1, ln_pre=1 if cfg.ln_pre else 0,
+                       patch_k_pad=k_pad, ln_eps=cfg.ln_eps, reserved=0)
+
+
+def pack_weights(cfg: ViTConfig, w: dict):
+    """fp32 weight dict (vit_config.random_weights layout) -> (half blob, float blob), CPU tensors.
+
+    Folded on the host (exact in real arithmetic): 1/sqrt(head_dim) into the q rows of qkv (a power of two for
+    head_dim 64, so also exact in fp16), LayerScale gamma into proj / fc2 weights and biases, cls + pos[0].
+    Layout must match csrc/vit_engine.cu:vit_layout.
+    """
+    D, M = cfg.dim, cfg.mlp
+    dh = D // cfg.heads
+    if dh != 64:
+        raise ValueError("engine supports head_dim 64")
+    k_pad = (cfg.patch_k + 63) // 64 * 64
+    half, flt = [], []
+    pw = torch.zeros(D, k_pad)
+    pw[:, : cfg.patch_k] = w["patch_w"]
+    half.append(pw)
+    flt += [w["patch_b"] if cfg.patch_bias else torch.zeros(D), w["cls"] + w["pos"][0]]
+    if cfg.n_reg:
+        flt.append(w["reg"].reshape(-1))
+    flt.append(w["pos"][1:].reshape(-1))
+    if cfg.ln_pre:
+        flt += [w["ln_pre_w"], w["ln_pre_b"]]
+    qs = 1.0 / math.sqrt(dh)
+    for i in range(cfg.depth):
+        p = f"l{i}."
+        qkv_w, qkv_b = w[p + "qkv_w"].clone(), w[p + "qkv_b"].clone()
+        qkv_w[:D] *= qs
+        qkv_b[:D] *= qs
+        proj_w, proj_b, fc2_w, fc2_b = w[p + "proj_w"], w[p + "proj_b"], w[p + "fc2_w"], w[p + "fc2_b"]
+        if cfg.layerscale:
+            proj_w, proj_b = proj_w * w[p + "ls1"][:, None], proj_b * w[p + "ls1"]
+            fc2_w, fc2_b = fc2_w * w[p + "ls2"][:, None], fc2_b * w[p + "ls2"]
+        half += [qkv_w, proj_w, w[p + "fc1_w"], fc2_w]
+        flt += [w[p + "ln1_w"], w[p + "ln1_b"], qkv_b, proj_b, w[p + "ln2_w"], w[p + "ln2_b"], w[p + "fc1_b"], fc2_b]
+    flt += [w["ln_post_w"], w["ln_post_b"]]
+    hb = torch.cat([t.reshape(-1).float() for t in half]).to(torch.float16)
+    fb = torch.cat([t.reshape(-1).float() for t in flt]).contiguous()
+    return hb, fb
+
+
+class ViTEngine:
+    """Device-resident ViT: packed weights + workspace + TMA descriptors, one instance per GPU."""
+
+    def __init__(self, cfg: ViTConfig, weights: dict, max_batch: int = 64, device="cuda"):
+        self.lib = _lib.lib()
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.max_batch = int(max_batch)
+        self._c = _cfg_struct(cfg)
+        hb, fb = pack_weights(cfg, weights)
+        if hb.numel() != self.lib.bscnav_vit_half_elems(C.byref(self._c)) or fb.numel() != self.lib.bscnav_vit_float_elems(C.byref(self._c)):
+            raise _lib.BscnavError("weight blob layout mismatch between vit.py and vit_engine.cu")
+        self.w_half = hb.to(self.device)
+        self.w_float = fb.to(self.device)
+        nbytes = _lib.check(self.lib.bscnav_vit_workspace_bytes(C.byref(self._c), self.max_batch), "vit_workspace_bytes")
+        self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bscnav_vit_create(C.byref(self._c), _lib.ptr(self.w_half), _lib.ptr(self.w_float),
+                                                  _lib.ptr(self.workspace), nbytes, self.max_batch, C.byref(h)), "vit_create")
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self.lib.bscnav_vit_destroy(h)
+
+    # -- frames path: uint8 HWC (3 or 4 channels) -> patch tokens (B, n_patch, D) fp32, optionally the pre-processed image
+    def forward_frames(self, rgb_u8: torch.Tensor, out: torch.Tensor | None = None, return_pre: bool = False):
+        assert rgb_u8.dtype == torch.uint8 and rgb_u8.is_cuda and rgb_u8.dim() == 4 and rgb_u8.is_contiguous()
+        B, H, W, ch = rgb_u8.shape
+        if out is None:
+            out = torch.empty(B, self.cfg.n_patch, self.cfg.dim, dtype=torch.float32, device=self.device)
+        pre = torch.empty(B, 3, self.cfg.image, self.cfg.image, dtype=torch.float32, device=self.device) if return_pre else None
+        for b0 in range(0, B, self.max_batch):
+            nb = min(self.max_batch, B - b0)
+            _lib.check(self.lib.bscnav_vit_forward_frames(self._h, _lib.ptr(rgb_u8[b0:]), nb, H, W, ch, _lib.ptr(out[b0:]),
+                                                          _lib.ptr(pre[b0:]) if return_pre else None, _lib.stream_ptr()),
+                       "vit_forward_frames")
+        return (out, pre) if return_pre else out
+
+    # -- the reference's plug-point: normalised float images (B,3,S,S) on the device
+    @torch.no_grad()
+    def forward_features(self, x: torch.Tensor) -> dict:
+        x = x.to(self.device, torch.float32).contiguous()
+        B = x.shape[0]
+        assert x.shape[1:] == (3, self.cfg.image, self.cfg.image), x.shape
+        out = torch.empty(B, self.cfg.n_patch, self.cfg.dim, dtype=torch.float32, device=self.device)
+        for b0 in range(0, B, self.max_batch):
+            nb = min(self.max_batch, B - b0)
+            _lib.check(self.lib.bscnav_vit_forward_images(self._h, _lib.ptr(x[b0:]), nb, _lib.ptr(out[b0:]), _lib.stream_ptr()),
+                       "vit_forward_images")
+        return {"x_norm_patchtokens": out}
+
+    def to(self, *_a, **_k):     # callers do `.to('cuda')` on the hub module (create_memory_for_dataset.py:58)
+        return self
+
+    def eval(self):
+        return self
+
+
+def gaussian_pool(tokens: torch.Tensor) -> torch.Tensor:
+    """Query embedding (memory_2.py:592-608): (B, g*g, D) device tokens -> (1, D)."""
+    B, n, D = tokens.shape
+    g = int(math.isqrt(n))
+    out = torch.empty(1, D, dtype=torch.float32, device=tokens.device)
+    _lib.check(_lib.lib().bscnav_gaussian_pool(_lib.ptr(tokens.contiguous()), B, g, D, _lib.ptr(out), _lib.stream_ptr()),
+               "gaussian_pool")
+    return out
+
+
+def gemm_f16(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, out_mode: int = 0, act: int = 0,
+             out: torch.Tensor | None = None) -> torch.Tensor:
+    """out = a @ w.T (+bias): fp16 operands, fp32 accumulation on tcgen05 (tests / micro-benchmarks)."""
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float16 if out_mode in (0, 1) else torch.float32, device=a.device)
+        if out_mode == 2:
+            out.zero_()
+    _lib.check(_lib.lib().bscnav_gemm_f16(_lib.ptr(a), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(out), M, N, K, out_mode, act,
+                                          _lib.stream_ptr()), "gemm_f16")
+    return out

@@ -1,0 +1,178 @@
+/* bscnav_b200 -- C ABI of the B200-native spatial-memory build + query path.
+ *
+ * The reference (Heathcliff-saku/BSC-Nav) has no FFI layer: its boundary is the Python class
+ * VoxelTokenMemory (memory_2.py:38).  These entry points are what a binding for that class's hot path
+ * would bind; each cites the reference lines it replaces.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions: every pointer is a DEVICE pointer unless named host_*; `stream` is a cudaStream_t passed as
+ * void*; calls enqueue work on that stream and return without synchronising (unless stated); the return
+ * value is 0 on success or a negative BSCNAV_E* code; nothing throws; re-entrant per stream.
+ * The library never allocates device memory: the caller owns every buffer (sizes given by *_bytes helpers).
+ */
+#ifndef BSCNAV_B200_H
+#define BSCNAV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSCNAV_OK            0
+#define BSCNAV_EINVAL       -1   /* bad argument (null pointer, size out of range, unsupported shape) */
+#define BSCNAV_ECAPACITY    -2   /* slot capacity / ordinal range exceeded                            */
+#define BSCNAV_ECUDA        -3   /* a CUDA runtime/driver call failed (see bscnav_last_error)         */
+#define BSCNAV_EUNSUPPORTED -4   /* device is not sm_100                                              */
+
+#define BSCNAV_KEY_EMPTY 0xFFFFFFFFFFFFFFFFull
+
+int bscnav_abi_version(void);
+const char* bscnav_last_error(void);           /* host string describing the last BSCNAV_ECUDA on this thread */
+
+/* ------------------------------------------------------------------------------------------------------
+ * Geometry of one memory (ctor state, memory_2.py:78-123; utils.py:144-150,181-186).
+ * All matrices row-major float64, computed on the host exactly as the reference does. */
+typedef struct {
+  int32_t height, width;          /* frame size (args.height/width)                                   */
+  int32_t gs;                     /* grid_size                                                         */
+  int32_t minh, maxh;             /* int(floor_height/cs), int(map_height/cs)   memory_2.py:122-123    */
+  int32_t levels;                 /* maxh-minh (voxel keys) or 1 (BEV keys: key reduced over h)        */
+  int32_t n_patch_h, n_patch_w;   /* token grid of the feature extractor (16x16 for /14 at 224)       */
+  int32_t cache;                  /* C: tokens kept per cell (cache_size, memory_2.py:111)             */
+  int32_t dim;                    /* D: token dimension (token_dim, memory_2.py:107), multiple of 128  */
+  int32_t max_slots;              /* slot capacity (reference: gs*gs, memory_2.py:715-718)             */
+  int32_t reserved;
+  double  cs;                     /* cell_size                                                         */
+  double  min_depth, max_depth;   /* strict bounds (utils.py:174-176)                                  */
+  double  kinv[9];                /* inv(calib_mat)                    utils.py:164                    */
+  double  kimg[9];                /* calib_mat (image intrinsics)      memory_2.py:102                 */
+  double  kpatch[9];              /* get_sim_cam_mat(n_patch)          memory_2.py:857                 */
+} bscnav_geom_t;
+
+/* Device buffers of one memory ("store").  Sizes in elements, with cells = gs*gs*levels, S = max_slots, C = cache:
+ *   occupied_ids int32[cells]   cell -> slot, -1 = empty            (occupied_ids, memory_2.py:716)
+ *   first_touch  uint32[cells]  scratch, must be 0xFFFFFFFF between calls
+ *   slot_cell    int32[S]       slot -> linear cell                 (grid_rgb_pos, memory_2.py:715)
+ *   slot_keys    uint64[S*C]    per slot the C best keys ascending; key = float32 bits of r^2 << 32 | ordinal
+ *   row_key      uint64[S*C]    key of the token held by physical row slot*C+j (unordered within a slot)
+ *   tok_h        int32[S*C]     h-minh of the point that produced the row (the position reported in BEV mode)
+ *   norm2        float[S*C]     squared L2 norm of the row
+ *   feat         float[S*C*D]   token rows                          (feat.h5df 'features', memory_2.py:335-354)
+ *   counters     int32[8]       [0] = number of slots in use (max_id, memory_2.py:894), [1] = capacity-overflow flag
+ */
+typedef struct {
+  int32_t*  occupied_ids;
+  uint32_t* first_touch;
+  int32_t*  slot_cell;
+  uint64_t* slot_keys;
+  uint64_t* row_key;
+  int32_t*  tok_h;
+  float*    norm2;
+  float*    feat;
+  int32_t*  counters;
+} bscnav_store_t;
+
+/* Reset a store to empty (replaces _init_cache, memory_2.py:708-722). */
+int bscnav_store_reset(const bscnav_geom_t* g, const bscnav_store_t* st, void* stream);
+
+/* Scratch needed by bscnav_fuse_frames for a batch of n_frames x n_points points. */
+int64_t bscnav_fuse_scratch_bytes(int32_t n_frames, int32_t n_points);
+
+/* Fuse a batch of frames into the store: depth unprojection, pose transform, voxel index, patch projection,
+ * deterministic slot assignment and top-C winner selection, feature-row commit.
+ * Replaces the per-point loop of obs2voxeltoken (memory_2.py:859-894) + update_memory_dist_base (:326-358).
+ *   depth       float[n_frames*H*W]
+ *   poses       double[n_frames*16]      pc_transform = tf @ base_transform @ base2cam_tf (memory_2.py:860)
+ *   ord_base    uint32[n_frames]         ordinal of the frame's first visited point (frame-major, visiting order)
+ *   sample_idx  int32[n_frames*n_points] visited pixel indices in visiting order (memory_2.py:746-749), or NULL
+ *                                        for dense raster order (then n_points must equal H*W)
+ *   tokens      float[n_frames*n_patch*D] patch tokens of each frame  (x_norm_patchtokens, memory_2.py:738-741)
+ *   records_out optional uint4[n_frames*n_points] copy-out of the per-point records {cell | -1, patch | h<<16,
+ *               ordinal, float32 bits of r^2} (parity tests), may be NULL
+ */
+int bscnav_fuse_frames(const bscnav_geom_t* g, const bscnav_store_t* st, const float* depth, const double* poses,
+                       const uint32_t* ord_base, const int32_t* sample_idx, int32_t n_frames, int32_t n_points,
+                       const float* tokens, void* scratch, int64_t scratch_bytes, void* records_out, void* stream);
+
+/* Candidate filter of voxel_localized (memory_2.py:624-640). radius2 < 0 disables the sphere test;
+ * floor_min > floor_max disables the floor test. */
+typedef struct {
+  int64_t radius2;                 /* region_radius^2 in cells^2 (compared as integers) */
+  int32_t cur[3];                  /* curr_grid (row, col, h-minh)                       */
+  int32_t floor_min, floor_max;    /* load_single_floor range, inclusive                 */
+  int32_t reserved;
+} bscnav_filter_t;
+
+int64_t bscnav_query_scratch_bytes(const bscnav_geom_t* g, int32_t n_query, int32_t k);
+
+/* Cosine similarity of each query against every stored token, per-cell max, top-K (memory_2.py:642-671).
+ *   q         float[n_query*D]
+ *   out_sim   float[n_query*k]   descending; unused tail = -inf
+ *   out_pos   int32[n_query*k*3] (row, col, h-minh); unused tail = -1
+ *   out_count int32[n_query]     number of valid results (<= k);  k <= 1024
+ * Ties are ordered by ascending (row, col, h). */
+int bscnav_query_topk(const bscnav_geom_t* g, const bscnav_store_t* st, const float* q, int32_t n_query, int32_t k,
+                      const bscnav_filter_t* filter, void* scratch, int64_t scratch_bytes,
+                      float* out_sim, int32_t* out_pos, int32_t* out_count, void* stream);
+
+/* Merge compacted deltas (e.g. all-gathered from other ranks) into the store under the same winner rule.
+ *   d_cell int32[n], d_key uint64[n], d_h int32[n], d_feat float[n*D]; entries with d_cell < 0 are skipped.
+ * Slot numbering of cells first seen through a merge follows delta order. */
+int bscnav_merge_delta(const bscnav_geom_t* g, const bscnav_store_t* st, const int32_t* d_cell, const uint64_t* d_key,
+                       const int32_t* d_h, const float* d_feat, int32_t n, void* scratch, int64_t scratch_bytes,
+                       void* stream);
+
+/* Export the rows whose key ordinal lies in [ord_lo, ord_hi) as a compact delta (for the all-gather merge).
+ * out_n (device int32) receives the count; at most max_out rows are written. */
+int64_t bscnav_export_scratch_bytes(const bscnav_geom_t* g);
+int bscnav_export_delta(const bscnav_geom_t* g, const bscnav_store_t* st, uint32_t ord_lo, uint32_t ord_hi,
+                        int32_t* d_cell, uint64_t* d_key, int32_t* d_h, float* d_feat, int32_t max_out,
+                        int32_t* out_n, void* scratch, int64_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * ViT feature extractor (replaces dinov2.forward_features, memory_2.py:591-592,732-742). */
+typedef struct {
+  int32_t image, patch;           /* 224, 14                                           */
+  int32_t dim, depth, heads, mlp; /* 1024, 24, 16, 4096                                */
+  int32_t n_reg;                  /* register tokens after cls (DINOv2-reg: 4)         */
+  int32_t act;                    /* 0 = GELU(erf), 1 = QuickGELU                      */
+  int32_t ln_pre;                 /* 1 = CLIP pre-LayerNorm                            */
+  int32_t patch_k_pad;            /* 3*patch*patch rounded up to a multiple of 64      */
+  float   ln_eps;
+  int32_t reserved;
+} bscnav_vit_cfg_t;
+
+/* Element counts of the two packed weight blobs (layout documented in DESIGN.md / vit.py:pack_weights). */
+int64_t bscnav_vit_half_elems(const bscnav_vit_cfg_t* c);
+int64_t bscnav_vit_float_elems(const bscnav_vit_cfg_t* c);
+int64_t bscnav_vit_workspace_bytes(const bscnav_vit_cfg_t* c, int32_t max_batch);
+
+/* Create an engine bound to caller-owned weight blobs and workspace (TMA descriptors are encoded here). */
+int bscnav_vit_create(const bscnav_vit_cfg_t* c, const void* w_half, const float* w_float, void* workspace,
+                      int64_t workspace_bytes, int32_t max_batch, void** out_engine);
+void bscnav_vit_destroy(void* engine);
+
+/* Frames path (_get_patch_token, memory_2.py:732-742): uint8 HWC frames (channels = 3 or 4, alpha ignored)
+ * -> /255 -> antialiased bilinear resize to image x image -> ImageNet normalise -> ViT -> patch tokens.
+ *   out_tokens float[batch*n_patch*dim];  out_pre optional float[batch*3*image*image] (pre-processed image) */
+int bscnav_vit_forward_frames(void* engine, const uint8_t* rgb, int32_t batch, int32_t height, int32_t width,
+                              int32_t channels, float* out_tokens, float* out_pre, void* stream);
+
+/* Query-image path (voxel_localized, memory_2.py:577-592): already normalised float[batch*3*image*image]. */
+int bscnav_vit_forward_images(void* engine, const float* images, int32_t batch, float* out_tokens, void* stream);
+
+/* Gaussian centre-weighted pooling of query tokens (memory_2.py:596-608): float[batch*n_patch*dim] -> float[dim]. */
+int bscnav_gaussian_pool(const float* tokens, int32_t batch, int32_t grid, int32_t dim, float* out, void* stream);
+
+/* Stand-alone GEMM entry (tests/bench): C[M,N] = A[M,K] * W[N,K]^T + bias, fp16 operands, fp32 accumulate on
+ * tcgen05; out_mode 0: fp16 out, 1: fp16 out with activation `act`, 2: fp32 out += (residual accumulate). */
+int bscnav_gemm_f16(const void* a, const void* w, const float* bias, void* out, int32_t m, int32_t n, int32_t k,
+                    int32_t out_mode, int32_t act, void* stream);
+
+/* Number of kernels launched by this library since load (bench.py's gpu_launches). */
+int64_t bscnav_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSCNAV_B200_H */

@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE ONLY -- CPU (numpy) restatement of the reference's spatial-memory hot path.
 
-This is the oracle the CUDA path is checked against.  It is pinned (tests/test_oracle_vs_reference.py, and the
+This is the oracle the CUDA path is checked against.  It is pinned (tests/test_oracle_golden.py, and the
 fixtures under tests/golden/ produced by oracle/make_golden.py) against the reference's own functions executed
 unmodified through oracle/ref_harness.py.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference legs may import it; the product package never does.
@@ -158,7 +158,7 @@ class MemoryParams:
         self.base2cam_tf = np.eye(4)                    # memory_2.py:90-92
         self.base2cam_tf[:3, :3] = np.array([self.base2cam_rot]).reshape((3, 3))
         self.base2cam_tf[1, 3] = self.sensor_height
-        self.patch_intr = get_sim_cam_mat(self.n_patch_h, self.n_patch_w)  # memory_2.py:857
+        self.patch_intr = get_sim_cam_mat(self.n_patch_w, self.n_patch_h)  # memory_2.py:857: get_sim_cam_mat(shape[0], shape[1]) of the (W', H', D) array
 
 
 def pose_chain(p: MemoryParams, pose, inv_init_base_tf=None):
@@ -205,7 +205,7 @@ def fuse_records(p: MemoryParams, depth: np.ndarray, pc_transform: np.ndarray, p
     qp = p.patch_intr @ pc
     ppx = _trunc(qp[0] / qp[2] - 0.5)
     ppy = _trunc(qp[1] / qp[2] - 0.5)
-    patch_ok = ~((ppx < 0) | (ppy < 0) | (ppx >= p.n_patch_w) | (ppy >= p.n_patch_h))  # :878 (shape[1]=W', shape[0]=H')
+    patch_ok = ~((ppx < 0) | (ppy < 0) | (ppx >= p.n_patch_h) | (ppy >= p.n_patch_w))  # :878 (token array is (W', H', D))
     r2 = (np.square(pc[0]) + np.square(pc[1])) + np.square(pc[2])   # np.sum(np.square(p_local)), 3 terms left to right
     keep = in_range & patch_ok
     out = dict(pix=pix[keep], row=row[keep], col=col[keep], h=(h - p.minh)[keep], ppx=ppx[keep], ppy=ppy[keep],

@@ -1,0 +1,89 @@
+"""GPU parity of the ViT engine pieces (tcgen05 GEMM, LayerNorm, attention, pre-processing) and of the whole
+forward against the torch-fp32 oracle (oracle/vit_ref.py).  Tolerance: 1e-3 relative, per token (L2), as
+BASELINE.json's north_star states for feature vectors."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vit_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return ((a - b).norm(dim=-1) / b.norm(dim=-1)).max().item()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 256, 128), (1000, 1024, 1024), (257 * 3, 3072, 1024), (515, 4096, 1024),
+                                   (200, 1024, 4096), (4112, 2304, 768)])
+def test_gemm_modes(pkg, M, N, K):
+    g = torch.Generator("cuda").manual_seed(M + N + K)
+    a = (torch.randn(M, K, device="cuda", generator=g)).half()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = a.float() @ w.float().t() + bias
+    out = pkg.gemm_f16(a, w, bias, out_mode=0)
+    torch.testing.assert_close(out.float(), ref, rtol=2e-3, atol=2e-3)
+    out = pkg.gemm_f16(a, w, bias, out_mode=1, act=0)
+    torch.testing.assert_close(out.float(), torch.nn.functional.gelu(ref), rtol=2e-3, atol=2e-3)
+    out = pkg.gemm_f16(a, w, bias, out_mode=1, act=1)
+    torch.testing.assert_close(out.float(), ref * torch.sigmoid(1.702 * ref), rtol=2e-3, atol=2e-3)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    out = pkg.gemm_f16(a, w, bias, out_mode=2, out=res.clone())
+    torch.testing.assert_close(out, res + ref, rtol=1e-4, atol=1e-4)
+    out = pkg.gemm_f16(a, w, None, out_mode=4, out=torch.empty(M, N, device="cuda"))
+    torch.testing.assert_close(out, ref - bias, rtol=1e-4, atol=1e-4)
+
+
+def test_gemm_repeatable(pkg):
+    g = torch.Generator("cuda").manual_seed(0)
+    a = torch.randn(2056, 1024, device="cuda", generator=g).half()
+    w = (torch.randn(4096, 1024, device="cuda", generator=g) * 0.05).half()
+    o1 = pkg.gemm_f16(a, w)
+    for _ in range(3):
+        assert torch.equal(o1, pkg.gemm_f16(a, w))
+
+
+@pytest.mark.parametrize("hw", [(480, 640), (680, 680), (128, 128), (96, 128)])
+@pytest.mark.parametrize("ch", [3, 4])
+def test_preprocess_matches_torch(pkg, hw, ch):
+    cfg = pkg.tiny(pkg.CLIP_L14)
+    eng = pkg.ViTEngine(cfg, pkg.random_weights(cfg, 0), max_batch=2)
+    rgb = torch.randint(0, 256, (2, hw[0], hw[1], ch), dtype=torch.uint8, generator=torch.Generator().manual_seed(1))
+    _, pre = eng.forward_frames(rgb.cuda(), return_pre=True)
+    ref = vit_ref.preprocess_frame(rgb[..., :3])
+    torch.testing.assert_close(pre.cpu(), ref, rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("base", ["clip-vit-l14", "dinov2-vitl14-reg"])
+def test_tiny_vit_matches_oracle(pkg, base):
+    cfg = pkg.tiny(pkg.CONFIGS[base], dim=128, depth=2, heads=2, mlp=256)
+    w = pkg.random_weights(cfg, seed=3, perturb=True)
+    eng = pkg.ViTEngine(cfg, w, max_batch=3)
+    x = torch.randn(5, 3, 224, 224, generator=torch.Generator().manual_seed(2))
+    got = eng.forward_features(x.cuda())["x_norm_patchtokens"].cpu()
+    ref = vit_ref.vit_forward(x, w, cfg)
+    assert got.shape == ref.shape == (5, 256, 128)
+    assert _rel(got, ref) < 1e-3
+
+
+@pytest.mark.parametrize("base", ["clip-vit-l14", "dinov2-vitl14-reg", "clip-vit-b32"])
+def test_full_vit_matches_oracle(pkg, base):
+    cfg = pkg.CONFIGS[base]
+    w = pkg.random_weights(cfg, seed=0)
+    eng = pkg.ViTEngine(cfg, w, max_batch=4)
+    rgb = torch.randint(0, 256, (3, 480, 640, 4), dtype=torch.uint8, generator=torch.Generator().manual_seed(5))
+    got = eng.forward_frames(rgb.cuda()).cpu()
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    ref = vit_ref.vit_forward(vit_ref.preprocess_frame(rgb[..., :3]), w, cfg)
+    rel = _rel(got, ref)
+    print(base, "max per-token relative L2 error", rel)
+    assert rel < 1e-3
+
+
+def test_gaussian_pool(pkg):
+    t = torch.randn(3, 256, 1024, generator=torch.Generator().manual_seed(0))
+    got = pkg.gaussian_pool(t.cuda()).cpu()
+    torch.testing.assert_close(got, vit_ref.gaussian_pool(t), rtol=1e-5, atol=1e-6)

@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""Headline benchmark: RGB-D frames/s fused into a 512x512 feature grid (640x480 frames, ViT-L/14), BASELINE.json.
+
+A step = one batch of synthetic frames through the whole build path:
+    uint8 frames -> pre-process -> ViT-L/14 (tcgen05 GEMMs) -> patch tokens -> unproject + pose + cell index
+    -> winner selection -> token-row commit into the grid store.
+`value`  : inputs resident in HBM, kernels only (CUDA events, max over ranks).
+`e2e`    : the same metric through the reference-facing API (VoxelTokenMemory.fuse_frames) with pinned HOST buffers,
+           host->device copies and a device->host read of the result inside the timed region.
+`--impl reference` times the reference's CPU algorithm (oracle port: torch-fp32 ViT on all host threads + the
+per-point Python loop of obs2voxeltoken) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+H, W, GS, D = 480, 640, 512, 1024
+METRIC = "RGB-D frames/sec into 512² feature grid (640×480, ViT-L/14) at 1/2/4/8 B200"
+WORKLOAD = ("BASELINE configs[1]: HM3D single scene, synthetic 640x480 RGB-D frames (box room, poses on a circle), "
+            "CLIP ViT-L/14 seeded random weights, 512x512 BEV grid, C=1, dense sampling (rate=1)")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops_sustained", 1386.8), d.get("hbm_gbs", 6445.3), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.sm_max = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:   # noqa: BLE001
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10, "applications_clocks": 0x2}
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:   # noqa: BLE001
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        self.stop_flag = True
+        if self.is_alive():
+            self.join(timeout=1)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+# ---------------------------------------------------------------------------------------------- reference arm / cpu baseline
+_CPU_W = {}
+
+
+def cpu_reference_rate(n_frames: int, sample_points: int, threads: int):
+    """The reference's CPU algorithm on `n_frames` frames: fp32 ViT forward on `threads` host threads (its per-frame,
+    batch-1 call pattern, memory_2.py:732-742) + the literal per-point loop of obs2voxeltoken (memory_2.py:863-903) over
+    the first `sample_points` valid points, scaled to the frame's valid points.  Returns (frames/s, detail)."""
+    from oracle import memory_port as mp
+    from oracle import vit_ref
+    vc = importlib.import_module("bsc-nav_b200.vit_config")
+    torch.set_num_threads(threads)
+    cfg = vc.CLIP_L14
+    if "w" not in _CPU_W:
+        _CPU_W["w"] = vc.random_weights(cfg, seed=0)
+    w = _CPU_W["w"]
+    p = mp.MemoryParams(height=H, width=W, grid_size=GS, token_dim=D, cache_size=1, bev=True)
+    om = mp.OracleMemory(p)
+    inv0 = None
+    t_vit = t_loop = 0.0
+    for f in range(n_frames):
+        rgb, depth, pose = mp.synthetic_frame(f, H, W)
+        t0 = time.perf_counter()
+        x = vit_ref.preprocess_frame(torch.from_numpy(rgb[None, :, :, :3]))
+        tok = vit_ref.vit_forward(x, w, cfg)[0].reshape(16, 16, D).numpy()
+        t1 = time.perf_counter()
+        T, inv0 = mp.pose_chain(p, pose, inv0)
+        visited = mp.fuse_frame_loop(p, rgb, depth, T, tok, om, max_points=sample_points)
+        t2 = time.perf_counter()
+        n_valid = int(((depth > p.min_depth) & (depth < p.max_depth)).sum())
+        t_vit += t1 - t0
+        t_loop += (t2 - t1) * (n_valid / max(visited, 1))
+    per_frame = (t_vit + t_loop) / n_frames
+    detail = (f"{n_frames} frame(s) of the workload: fp32 ViT-L/14 forward on {threads} threads ({t_vit / n_frames:.2f} s/frame) + "
+              f"per-point loop over the first {sample_points} of ~{H * W} points, scaled ({t_loop / n_frames:.1f} s/frame)")
+    return 1.0 / per_frame, detail
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    # warm-up + K steps; each step is one frame on a bounded point sample
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, detail = cpu_reference_rate(1, args.ref_points, threads)
+        if i >= args.warmup:
+            vals.append(v)
+        if i >= args.warmup and len(vals) >= 3 and time.time() - T_START > 240:
+            break
+    value = float(np.mean(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": len(vals),
+            "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (ViT) / f64 (geometry)", "data": "synthetic", "config": {"workload": WORKLOAD},
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port", "sample": detail},
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ge = importlib.import_module("__graft_entry__")
+    blib = importlib.import_module("bsc-nav_b200._lib")
+    if not os.path.exists(blib.LIB_PATH):
+        if local == 0:
+            ge.build()
+        if world > 1:
+            dist.barrier()
+    pkg = importlib.import_module("bsc-nav_b200")
+    synth = importlib.import_module("bsc-nav_b200.synth")
+    lib = blib.lib()
+    B, K, Wm = args.batch, args.steps, args.warmup
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # engine + memory (the reference-facing object)
+    cfg = pkg.CLIP_L14
+    eng = pkg.ViTEngine(cfg, pkg.random_weights(cfg, seed=0), max_batch=B, device=dev)
+    margs = synth.Args(height=H, width=W, grid_size=GS, depth_sample_rate=1)
+    mem = pkg.VoxelTokenMemory(margs, preload_dino=eng, need_diffusion=False, cache_size=1, bev=True, max_batch=B)
+    # synthetic pool: each rank owns a scene (weak scaling); P frames cycled, P*2.46 MB > L2
+    P = args.pool_batches * B
+    rgb_h = torch.empty(P, H, W, 4, dtype=torch.uint8, pin_memory=True)
+    dep_h = torch.empty(P, H, W, dtype=torch.float32, pin_memory=True)
+    poses = np.empty((P, 7))
+    for f in range(P):
+        r, d, po = synth.synthetic_frame(f, H, W, n_frames=1000, seed_base=100000 * rank)
+        rgb_h[f] = torch.from_numpy(r)
+        dep_h[f] = torch.from_numpy(d)
+        poses[f] = po
+    rgb_d, dep_d = rgb_h.to(dev), dep_h.to(dev)
+    tokens = torch.empty(B, cfg.n_patch, cfg.dim, dtype=torch.float32, device=dev)
+    chain = pkg.PoseChain(margs.base_forward_axis, margs.base_left_axis, margs.base_up_axis, margs.base2cam_rot, margs.sensor_height)
+    tfs = np.stack([chain(p) for p in poses]).reshape(P, 16)
+    tfs_d = torch.from_numpy(tfs).to(dev)
+    store = mem.store
+    npts = H * W
+
+    def step_device(s):
+        b0 = (s % args.pool_batches) * B
+        eng.forward_frames(rgb_d[b0:b0 + B], out=tokens)
+        ob = (np.arange(B, dtype=np.int64) + (s * B)) * npts % (2 ** 32 - npts * B)
+        store.fuse(dep_d[b0:b0 + B], tfs_d[b0:b0 + B], tokens, ord_base=ob)
+
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for s in range(n):
+            fn(s)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms
+
+    # ---- value: kernels only, inputs in HBM
+    for s in range(Wm):
+        step_device(s)
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = lib.bscnav_launch_count()
+    ms = timed(step_device, K)
+    launches = lib.bscnav_launch_count() - l0
+    clocks = sampler.result()
+    value = world * B * K / (ms / 1e3)
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM), CUDA events around every launch of two more steps
+    eng.profile(True)
+    for s in range(2):
+        step_device(s)
+    torch.cuda.synchronize()
+    prof = eng.profile_read()
+    eng.profile(False)
+    peak_tf, peak_gbs, peak_src = peaks()
+    g_ms, g_flops, g_n = prof["gemm"]
+    achieved = g_flops / (g_ms / 1e3) / 1e12
+    step_ms_prof = sum(v[0] for v in prof.values()) / 2
+    roofline = {"bound": "tensor", "kernel": "k_gemm_f16 (tcgen05, fp16 x fp16 -> fp32)", "achieved": achieved, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                "launches_per_step": g_n // 2, "share_of_step": (g_ms / 2) / (ms / K),
+                "breakdown_ms_per_step": {k: v[0] / 2 for k, v in prof.items()},
+                "attention_tflops": prof["attention"][1] / (prof["attention"][0] / 1e3) / 1e12 if prof["attention"][0] else None}
+
+    # ---- e2e: public API, pinned host buffers, H2D inside the timed region, D2H read of the slot count every step
+    mem._clear_memory()
+
+    def step_e2e(s):
+        b0 = (s % args.pool_batches) * B
+        mem.fuse_frames(rgb_h[b0:b0 + B], dep_h[b0:b0 + B], poses[b0:b0 + B])
+        _ = mem.max_id
+
+    for s in range(Wm):
+        step_e2e(s)
+    ms_e2e = timed(step_e2e, K)
+    e2e = {"value": world * B * K / (ms_e2e / 1e3), "unit": "frames/s",
+           "h2d_bytes_per_step": B * (H * W * 4 + H * W * 4 + 16 * 8 + 4), "d2h_bytes_per_step": 8,
+           "api": "VoxelTokenMemory.fuse_frames + max_id"}
+
+    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 operands / f32 accumulate (ViT), f64 (cell index), f32 (tokens)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_frames_per_gpu": B, "frames_per_step": world * B,
+                       "l2": f"inputs larger than L2: {B * 2 * H * W * 4 / 1e6:.0f} MB of frames per step, pool of {P} frames",
+                       "sharding": "one scene per rank, no data-path collective" if world > 1 else "single GPU"},
+            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "vit_tflops": cfg.flops_per_frame() * B * K / (ms / 1e3) / 1e12}
+    if world == 1:
+        v, detail = cpu_reference_rate(1, args.ref_points, os.cpu_count() or 1)
+        line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": detail}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+T_START = time.time()
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="frames per step per GPU")
+    ap.add_argument("--pool-batches", type=int, default=3, help="distinct batches of synthetic frames cycled through")
+    ap.add_argument("--ref-points", type=int, default=20000, help="points of each frame the CPU reference loop visits")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -66,6 +66,8 @@ _SIGS = {
     "bscnav_vit_workspace_bytes": (C.c_int64, [C.POINTER(VitCfg), C.c_int32]),
     "bscnav_vit_create": (C.c_int, [C.POINTER(VitCfg), _P, _P, _P, C.c_int64, C.c_int32, C.POINTER(_P)]),
     "bscnav_vit_destroy": (None, [_P]),
+    "bscnav_vit_profile": (C.c_int, [_P, C.c_int32]),
+    "bscnav_vit_profile_read": (C.c_int, [_P, _P, _P, _P]),
     "bscnav_vit_forward_frames": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
     "bscnav_vit_forward_images": (C.c_int, [_P, _P, C.c_int32, _P, _P]),
     "bscnav_gaussian_pool": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),

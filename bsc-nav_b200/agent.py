@@ -1,0 +1,93 @@
+"""Retrieval slice of the agent: the calls that enter the spatial memory.
+
+GESObjectNavRobot.working_memory_retrival / weighted_cluster_centers / _grid2loc / _loc2grid (BSCAgent.py:454-497,
+587-664; twin in objnav_benchmark.py:440-495) and LocalizeAgent (agent_localize.py:11-37).  LLM prompt expansion,
+CLIP view verification and motion execution are out-of-scope collaborators: `prompt_expander` is injectable.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+
+class GESObjectNavRobot:
+    def __init__(self, memory, habitat_benchmark_env=None, prompt_expander=None):
+        self.memory = memory
+        self.benchmark_env = habitat_benchmark_env          # may be None (agent_localize.py:12-13)
+        self.prompt_expander = prompt_expander              # stands in for imagenary_helper(client, text) (LLMAgent.py:70)
+
+    # -- BSCAgent.py:454-477
+    def _agent_position(self):
+        env = self.benchmark_env
+        sim = getattr(env, "sim", None) or getattr(env, "sims", None)      # both spellings exist
+        return sim.agents[0].get_state().position
+
+    def _grid2loc(self, grid_id):
+        row, col, _height = grid_id[0], grid_id[1], grid_id[2]
+        initial_x, _initial_z, initial_y = self.memory.Env.original_state.position
+        actual_y = initial_y + (row - self.memory.gs // 2) * self.memory.cs
+        actual_x = initial_x + (col - self.memory.gs // 2) * self.memory.cs
+        actual_z = self._agent_position()[1] + 0.2
+        return np.array([actual_x, actual_z, actual_y])
+
+    def _loc2grid(self, loc):
+        x, z, y = loc
+        initial_x, _initial_z, initial_y = self.memory.Env.original_state.position
+        row = int((y - initial_y) / self.memory.cs + self.memory.gs // 2)
+        col = int((x - initial_x) / self.memory.cs + self.memory.gs // 2)
+        h = int(z / self.memory.cs) - self.memory.minh
+        return np.array([row, col, h])
+
+    # -- BSCAgent.py:479-497
+    def weighted_cluster_centers(self, top_k_positions, top_k_similarity, eps=10, min_samples=5):
+        from sklearn.cluster import DBSCAN
+        labels = DBSCAN(eps=eps, min_samples=min_samples).fit_predict(top_k_positions)
+        cluster_info = []
+        for lbl in [l for l in set(labels) if l != -1]:
+            m = labels == lbl
+            cluster_info.append((np.mean(top_k_similarity[m]),
+                                 np.average(top_k_positions[m], axis=0, weights=top_k_similarity[m]), np.sum(m)))
+        cluster_info.sort(key=lambda x: x[0], reverse=True)
+        return np.array([c[1] for c in cluster_info]), labels, [c[2] for c in cluster_info]
+
+    # -- BSCAgent.py:587-664
+    def working_memory_retrival(self, prompts, vis_aug=False, text_aug=True, region_radius=np.inf, curr_grid=None):
+        if curr_grid is None and region_radius != np.inf:
+            curr_grid = self._loc2grid(self._agent_position())
+        if isinstance(prompts, (str, list)):
+            text = prompts if isinstance(prompts, str) else " ".join(prompts)
+            if text_aug and self.prompt_expander is not None:
+                text = self.prompt_expander(text)
+            _best, top_pos, top_sim = self.memory.voxel_localized(text, region_radius=region_radius, curr_grid=curr_grid)
+        else:
+            _best, top_pos, top_sim = self.memory.voxel_localized(prompts, region_radius=region_radius, curr_grid=curr_grid)
+        centers, _, _ = self.weighted_cluster_centers(top_pos, top_sim)
+        if isinstance(prompts, str):
+            name = prompts[:64]
+            os.makedirs(self.memory.memory_save_path, exist_ok=True)
+            np.save(self.memory.memory_save_path + f"/best_pos_topK_{name}.npy", np.array(top_pos))
+            np.save(self.memory.memory_save_path + f"/best_pos_centers_{name}.npy", np.array(centers))
+        return np.array([centers])
+
+
+class LocalizeAgent(GESObjectNavRobot):
+    """agent_localize.py:11-37."""
+
+    def __init__(self, memory, habitat_benchmark_env=None, prompt_expander=None, save_dir="localize_results"):
+        super().__init__(memory, habitat_benchmark_env, prompt_expander)
+        self.save_dir = save_dir
+        os.makedirs(self.save_dir, exist_ok=True)
+
+    def LocalizeTextPrompt(self, text_prompt):
+        text = self.prompt_expander(text_prompt) if self.prompt_expander else text_prompt
+        _best, top_pos, top_sim = self.memory.voxel_localized(text)
+        centers, _, _ = self.weighted_cluster_centers(top_pos, top_sim)
+        np.save(f"{self.save_dir}/best_pos_topK_text_prompt.npy", np.array(top_pos))
+        return centers
+
+    def LocalizeImagePrompt(self, img):
+        _best, top_pos, top_sim = self.memory.voxel_localized(img)
+        centers, _, _ = self.weighted_cluster_centers(top_pos, top_sim)
+        np.save(f"{self.save_dir}/best_pos_topK_img_input.npy", np.array(top_pos))
+        return centers

@@ -4,6 +4,7 @@
 //               fc1_w [M, D], fc2_w [D, M] (LayerScale folded) }
 //   float blob: patch_b [D] | cls_pos [D] | reg [n_reg, D] | pos [Np, D] | ln_pre_w, ln_pre_b [D] (if ln_pre) |
 //               per layer { ln1_w, ln1_b [D], qkv_b [3D], proj_b [D], ln2_w, ln2_b [D], fc1_b [M], fc2_b [D] } | ln_post_w, ln_post_b [D]
+#include <vector>
 #include "gemm_tcgen05.cuh"
 #include "vit_kernels.cuh"
 
@@ -84,6 +85,25 @@ struct VitEngine {
   CUtensorMap map_patch_w;
   CUtensorMap map_qkv[64], map_proj[64], map_fc1[64], map_fc2[64];
   bool a0_cleared = false;
+  // optional per-kernel timing (bench.py's roofline leg): CUDA events around every launch on the caller's stream
+  bool profile = false;
+  struct Span { int cat; double work; cudaEvent_t e0, e1; };
+  std::vector<Span> spans;
+};
+
+enum ProfCat : int { kCatGemm = 0, kCatAttention = 1, kCatLayerNorm = 2, kCatPre = 3, kCatCount = 4 };
+
+struct ProfScope {
+  VitEngine* e; cudaStream_t s; size_t idx;
+  ProfScope(VitEngine* e_, cudaStream_t s_, int cat, double work) : e(e_), s(s_), idx(0) {
+    if (!e->profile) return;
+    VitEngine::Span sp{cat, work, nullptr, nullptr};
+    cudaEventCreate(&sp.e0); cudaEventCreate(&sp.e1);
+    cudaEventRecord(sp.e0, s);
+    e->spans.push_back(sp);
+    idx = e->spans.size();
+  }
+  ~ProfScope() { if (idx) cudaEventRecord(e->spans[idx - 1].e1, s); }
 };
 
 static int vit_run(VitEngine* e, int batch, float* out_tokens, cudaStream_t stream) {
@@ -95,27 +115,35 @@ static int vit_run(VitEngine* e, int batch, float* out_tokens, cudaStream_t stre
   GemmEpilogue ep{};
   ep.out = e->ws.x; ep.bias = wf + e->L.patch_b; ep.table = wf + e->L.pos; ep.ld_out = D; ep.mode = kOutPatchEmbed;
   ep.np = Np; ep.tokens = T; ep.row_off = 1 + c.n_reg;
-  if (int r = gemm_f16_launch(&e->map_a0, &e->map_patch_w, batch * Np, D, c.patch_k_pad, ep, stream)) return r;
+  { ProfScope ps(e, stream, kCatGemm, 2.0 * batch * Np * (double)D * c.patch_k_pad);
+    if (int r = gemm_f16_launch(&e->map_a0, &e->map_patch_w, batch * Np, D, c.patch_k_pad, ep, stream)) return r; }
   if (int r = fill_prefix_tokens(e->ws.x, wf + e->L.cls_pos, wf + e->L.reg, batch, T, c.n_reg, D, stream)) return r;
   if (c.ln_pre)
     if (int r = layernorm_inplace(e->ws.x, wf + e->L.ln_pre_w, wf + e->L.ln_pre_b, c.ln_eps, rows, D, stream)) return r;
   for (int i = 0; i < c.depth; ++i) {
     const LayerOff& o = e->L.layer[i];
-    if (int r = layernorm_half(e->ws.x, wf + o.ln1_w, wf + o.ln1_b, c.ln_eps, rows, D, e->ws.y, stream)) return r;
+    { ProfScope ps(e, stream, kCatLayerNorm, (double)rows * D * 6);
+      if (int r = layernorm_half(e->ws.x, wf + o.ln1_w, wf + o.ln1_b, c.ln_eps, rows, D, e->ws.y, stream)) return r; }
     GemmEpilogue e1{};
     e1.out = e->ws.qkv; e1.bias = wf + o.qkv_b; e1.ld_out = 3 * D; e1.mode = kOutHalf;
-    if (int r = gemm_f16_launch(&e->map_y, &e->map_qkv[i], rows, 3 * D, D, e1, stream)) return r;
-    if (int r = attention_f16(e->ws.qkv, e->ws.ao, batch, T, c.heads, stream)) return r;
+    { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * 3.0 * D * D);
+      if (int r = gemm_f16_launch(&e->map_y, &e->map_qkv[i], rows, 3 * D, D, e1, stream)) return r; }
+    { ProfScope ps(e, stream, kCatAttention, 4.0 * batch * (double)T * T * D);
+      if (int r = attention_f16(e->ws.qkv, e->ws.ao, batch, T, c.heads, stream)) return r; }
     GemmEpilogue e2{};
     e2.out = e->ws.x; e2.bias = wf + o.proj_b; e2.ld_out = D; e2.mode = kOutResidual;
-    if (int r = gemm_f16_launch(&e->map_ao, &e->map_proj[i], rows, D, D, e2, stream)) return r;
-    if (int r = layernorm_half(e->ws.x, wf + o.ln2_w, wf + o.ln2_b, c.ln_eps, rows, D, e->ws.y, stream)) return r;
+    { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * (double)D * D);
+      if (int r = gemm_f16_launch(&e->map_ao, &e->map_proj[i], rows, D, D, e2, stream)) return r; }
+    { ProfScope ps(e, stream, kCatLayerNorm, (double)rows * D * 6);
+      if (int r = layernorm_half(e->ws.x, wf + o.ln2_w, wf + o.ln2_b, c.ln_eps, rows, D, e->ws.y, stream)) return r; }
     GemmEpilogue e3{};
     e3.out = e->ws.hmid; e3.bias = wf + o.fc1_b; e3.ld_out = M; e3.mode = kOutHalfAct; e3.act = c.act;
-    if (int r = gemm_f16_launch(&e->map_y, &e->map_fc1[i], rows, M, D, e3, stream)) return r;
+    { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * (double)M * D);
+      if (int r = gemm_f16_launch(&e->map_y, &e->map_fc1[i], rows, M, D, e3, stream)) return r; }
     GemmEpilogue e4{};
     e4.out = e->ws.x; e4.bias = wf + o.fc2_b; e4.ld_out = D; e4.mode = kOutResidual;
-    if (int r = gemm_f16_launch(&e->map_h, &e->map_fc2[i], rows, D, M, e4, stream)) return r;
+    { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * (double)M * D);
+      if (int r = gemm_f16_launch(&e->map_h, &e->map_fc2[i], rows, D, M, e4, stream)) return r; }
   }
   return layernorm_patch_tokens(e->ws.x, wf + e->L.ln_post_w, wf + e->L.ln_post_b, c.ln_eps, batch, T, 1 + c.n_reg, D,
                                 out_tokens, stream);
@@ -180,6 +208,28 @@ int bscnav_vit_create(const bscnav_vit_cfg_t* c, const void* w_half, const float
 
 void bscnav_vit_destroy(void* engine) { delete static_cast<VitEngine*>(engine); }
 
+int bscnav_vit_profile(void* engine, int32_t enable) {
+  VitEngine* e = static_cast<VitEngine*>(engine);
+  if (!e) return BSCNAV_EINVAL;
+  e->profile = enable != 0;
+  return BSCNAV_OK;
+}
+
+int bscnav_vit_profile_read(void* engine, double* out_ms, double* out_work, int32_t* out_launches) {
+  VitEngine* e = static_cast<VitEngine*>(engine);
+  if (!e || !out_ms || !out_work || !out_launches) return BSCNAV_EINVAL;
+  for (int i = 0; i < kCatCount; ++i) { out_ms[i] = 0; out_work[i] = 0; out_launches[i] = 0; }
+  for (auto& sp : e->spans) {
+    BSC_CUDA(cudaEventSynchronize(sp.e1));
+    float ms = 0.f;
+    BSC_CUDA(cudaEventElapsedTime(&ms, sp.e0, sp.e1));
+    out_ms[sp.cat] += ms; out_work[sp.cat] += sp.work; out_launches[sp.cat] += 1;
+    cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1);
+  }
+  e->spans.clear();
+  return BSCNAV_OK;
+}
+
 static int clear_a0_once(VitEngine* e, cudaStream_t stream) {
   // the K padding columns of the patch rows are never written by im2col: zero them once
   if (!e->a0_cleared) {
@@ -195,8 +245,9 @@ int bscnav_vit_forward_frames(void* engine, const uint8_t* rgb, int32_t batch, i
   if (!e || !rgb || !out_tokens || batch <= 0 || batch > e->max_batch) return BSCNAV_EINVAL;
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int r = clear_a0_once(e, stream)) return r;
-  if (int r = preprocess_frames(rgb, batch, height, width, channels, e->cfg.image, e->cfg.patch, e->cfg.patch_k_pad, e->ws.a0,
-                                out_pre, stream)) return r;
+  { ProfScope ps(e, stream, kCatPre, (double)batch * height * width * channels);
+    if (int r = preprocess_frames(rgb, batch, height, width, channels, e->cfg.image, e->cfg.patch, e->cfg.patch_k_pad, e->ws.a0,
+                                  out_pre, stream)) return r; }
   return vit_run(e, batch, out_tokens, stream);
 }
 

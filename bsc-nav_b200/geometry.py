@@ -53,6 +53,20 @@ class PoseChain:
     def reset(self):
         self.inv_init_base_tf = []
 
+    def batch(self, poses) -> np.ndarray:
+        """(B,7) poses -> (B,4,4) pc_transforms; same operations as __call__, stacked (one SciPy / matmul call per step)."""
+        poses = np.asarray(poses, dtype=np.float64).reshape(-1, 7)
+        if len(self.inv_init_base_tf) == 0:
+            self(poses[0])
+        bt = self.base_transform
+        tf = np.tile(np.eye(4), (len(poses), 1, 1))
+        tf[:, :3, 3] = poses[:, :3]
+        tf[:, :3, :3] = R.from_quat(poses[:, 3:]).as_matrix()
+        base_pose = bt @ tf @ np.linalg.inv(bt)
+        tfs = self.inv_init_base_tf @ base_pose
+        self.tf = tfs[-1]
+        return tfs @ bt @ self.base2cam_tf
+
     def __call__(self, pose) -> np.ndarray:
         bt = self.base_transform
         if len(self.inv_init_base_tf) == 0:

@@ -1,0 +1,314 @@
+"""VoxelTokenMemory -- drop-in for the reference's memory class (memory_2.py:38) on top of the CUDA path.
+
+Same constructor, methods, attributes and return types as the reference for the spatial-memory hot path
+(SURVEY.md section 8b); the simulator (`Env`), YOLO long-term memory and diffusion "imagination" are injected
+collaborators, not part of this package.  Differences that are part of the contract:
+  * tokens are committed on the device as frames are fused; `update_memory_dist_base()` is therefore a no-op flush;
+  * the store keeps per cell the `cache_size` tokens with the smallest float32 r^2 (deterministic) where the
+    reference evicts at random once a cell holds 10 tokens (memory_2.py:352);
+  * `fuse_frames` is the batched entry point (many frames per call); `obs2voxeltoken` is the single-frame form.
+"""
+from __future__ import annotations
+
+import gc
+import json
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from .geometry import PoseChain, sim_cam_mat_with_fov
+from .store import SpatialStore, StoreConfig
+from .vit import ViTEngine, gaussian_pool
+
+
+class _NullEnv:
+    """Stand-in when no simulator is injected (query-only use, synthetic builds)."""
+    sims = None
+    agent = None
+    plnner = None
+
+    class _State:
+        position = np.zeros(3)
+    original_state = _State()
+
+    def reset(self, *a, **k):
+        return None
+
+
+class VoxelTokenMemory:
+    def __init__(self, args, memory_path=None, init_state=None, build_map=False, preload_dino=None, preload_yolo=None,
+                 need_diffusion=True, env=None, cache_size=10, bev=False, max_slots=None, max_batch=64):
+        self.args = args
+        self.device = "cuda"                                   # memory_2.py:41
+        if preload_dino is None:
+            raise _lib.BscnavError(
+                "preload_dino is required: pass a bscnav ViTEngine (or any module with forward_features); there is no "
+                "network here for torch.hub.load('facebookresearch/dinov2', ...) (memory_2.py:43)")
+        self.dinov2 = preload_dino
+        self.yolow = preload_yolo                               # long-term memory detector: out of scope, kept for callers
+        if memory_path:
+            self.memory_save_path = memory_path
+        else:
+            self.memory_save_path = os.path.join(getattr(args, "memory_path", "."), getattr(args, "scene_name", "scene"))
+        self.Env = env if env is not None else _NullEnv()
+
+        self.patch_h = self.patch_w = getattr(getattr(preload_dino, "cfg", None), "patch", 14)   # memory_2.py:80-81
+        self.n_patch_w = args.query_width // self.patch_w
+        self.n_patch_h = args.query_height // self.patch_h
+        self._chain = PoseChain(args.base_forward_axis, args.base_left_axis, args.base_up_axis, args.base2cam_rot,
+                                args.sensor_height)
+        self.base_transform = self._chain.base_transform
+        self.base2cam_tf = self._chain.base2cam_tf
+        self.cs = args.cell_size
+        self.gs = int(args.grid_size)
+        self.depth_sample_rate = args.depth_sample_rate
+        self.calib_mat = sim_cam_mat_with_fov(args.height, args.width, fov=90)      # memory_2.py:102
+        self.min_depth = args.min_depth
+        self.max_depth = args.max_depth
+        self.token_dim = getattr(getattr(preload_dino, "cfg", None), "dim", 1024)  # memory_2.py:107
+        self.cache_size = cache_size                                                # memory_2.py:111
+        self.camera_height = args.sensor_height
+        self.floor_height = args.floor_height
+        self.map_height = args.map_height
+        self.maxh = int(self.map_height / self.cs)
+        self.minh = int(self.floor_height / self.cs)
+        self.bev = bool(bev)
+        self._max_slots = max_slots
+        self._max_batch = max_batch
+        self.long_memory_dict = []
+        self.base_height = []
+        self.floor_min_height = None
+        self.floor_max_height = None
+        self._store = None
+        self._init_cache()
+        self._pinned = {}
+
+    # ------------------------------------------------------------------ state
+    def _init_cache(self):
+        """Replaces memory_2.py:708-722: all buffers live in HBM (SpatialStore)."""
+        a = self.args
+        cfg = StoreConfig(height=a.height, width=a.width, grid_size=self.gs, cell_size=self.cs,
+                          floor_height=self.floor_height, map_height=self.map_height, min_depth=self.min_depth,
+                          max_depth=self.max_depth, n_patch_h=self.n_patch_h, n_patch_w=self.n_patch_w,
+                          token_dim=self.token_dim, cache_size=self.cache_size, bev=self.bev, max_slots=self._max_slots,
+                          calib_mat=self.calib_mat)
+        if self._store is not None and self._store.cfg == cfg:
+            self._store.reset()
+        else:
+            self._store = None
+            gc.collect()
+            torch.cuda.empty_cache()
+            self._store = SpatialStore(cfg, device=self.device)
+        self._chain.reset()
+        self.iter_id = 0
+
+    def _clear_memory(self):
+        """memory_2.py:147-164."""
+        self._store.reset()
+        self._chain.reset()
+
+    @property
+    def inv_init_base_tf(self):
+        return self._chain.inv_init_base_tf
+
+    @property
+    def max_id(self) -> int:
+        return self._store.count()
+
+    @property
+    def grid_rgb_pos(self) -> np.ndarray:
+        return self._store.positions()
+
+    @property
+    def store(self) -> SpatialStore:
+        return self._store
+
+    # ------------------------------------------------------------------ build
+    def _get_patch_token(self, img: np.ndarray) -> torch.Tensor:
+        """memory_2.py:732-742: (H,W,3|4) uint8 -> (n_patch_w, n_patch_h, D) device tokens."""
+        t = torch.from_numpy(np.ascontiguousarray(img)).to(self.device).unsqueeze(0)
+        return self._tokens_of(t)[0].reshape(self.n_patch_w, self.n_patch_h, -1)
+
+    def _tokens_of(self, rgb_dev: torch.Tensor) -> torch.Tensor:
+        if isinstance(self.dinov2, ViTEngine):
+            return self.dinov2.forward_frames(rgb_dev)
+        # any other module with the reference's plug-point signature: pre-process as the reference does
+        x = rgb_dev[..., :3].permute(0, 3, 1, 2).float() / 255
+        x = torch.nn.functional.interpolate(x, size=(self.args.query_height, self.args.query_width), mode="bilinear",
+                                            align_corners=False, antialias=True)
+        mean = torch.tensor([0.485, 0.456, 0.406], device=x.device).view(1, 3, 1, 1)
+        std = torch.tensor([0.229, 0.224, 0.225], device=x.device).view(1, 3, 1, 1)
+        with torch.no_grad():
+            return self.dinov2.forward_features((x - mean) / std)["x_norm_patchtokens"].float().contiguous()
+
+    def _sample_indices(self, n_frames: int):
+        """memory_2.py:746-749: a fresh permutation per frame, every depth_sample_rate-th entry.  rate == 1 keeps raster order."""
+        if self.depth_sample_rate == 1:
+            return None
+        n = self.args.height * self.args.width
+        idx = []
+        for _ in range(n_frames):
+            perm = np.arange(n)
+            np.random.shuffle(perm)
+            idx.append(perm[:: self.depth_sample_rate])
+        return torch.from_numpy(np.stack(idx).astype(np.int32)).to(self.device)
+
+    def _staging(self, name, shape, dtype):
+        buf = self._pinned.get(name)
+        if buf is None or buf.shape != tuple(shape) or buf.dtype != dtype:
+            buf = torch.empty(shape, dtype=dtype, pin_memory=True)
+            self._pinned[name] = buf
+        return buf
+
+    def fuse_frames(self, rgb, depth, poses, sample_idx=None):
+        """Batched build step: rgb (B,H,W,3|4) uint8, depth (B,H,W) float32, poses (B,7) -- host arrays (copied through
+        pinned staging buffers) or device tensors.  Everything after the copy runs on the device, no host sync."""
+        poses = np.asarray(poses, dtype=np.float64).reshape(-1, 7)
+        tfs = self._chain.batch(poses)
+        if not torch.is_tensor(rgb):
+            rgb = np.asarray(rgb)
+            st = self._staging("rgb", rgb.shape, torch.uint8)
+            st.numpy()[...] = rgb
+            rgb = st.to(self.device, non_blocking=True)
+        if not torch.is_tensor(depth):
+            depth = np.asarray(depth, dtype=np.float32)
+            st = self._staging("depth", depth.shape, torch.float32)
+            st.numpy()[...] = depth
+            depth = st.to(self.device, non_blocking=True)
+        rgb = rgb.to(self.device, non_blocking=True).contiguous()          # pinned host tensors copy asynchronously
+        depth = depth.to(self.device, non_blocking=True).contiguous()
+        if sample_idx is None:
+            sample_idx = self._sample_indices(rgb.shape[0])
+        tokens = self._tokens_of(rgb)
+        self._store.fuse(depth, tfs, tokens, sample_idx=sample_idx)
+        self.tf = self._chain.tf
+
+    def obs2voxeltoken(self, obs, pose):
+        """memory_2.py:842-903, one frame."""
+        rgb = np.asarray(obs["rgb"])
+        depth = np.asarray(obs["depth"], dtype=np.float32)
+        self.fuse_frames(rgb[None], depth[None], np.asarray(pose)[None])
+
+    def long_memory(self, obs):
+        """YOLO-World long-term memory (memory_2.py:905-1025): detector is an out-of-scope collaborator."""
+        return None
+
+    def update_memory_dist_base(self):
+        """memory_2.py:326-358: the reference flushes its 50 000-row host buffer to HDF5 here.  Tokens are already in the
+        device store; this only surfaces a pending capacity error."""
+        self._store.count()
+
+    def initial_memory(self):
+        """memory_2.py:298-309: never overwrite an existing directory."""
+        count = 1
+        while os.path.exists(self.memory_save_path):
+            self.memory_save_path = self.memory_save_path.split("_")[0]
+            self.memory_save_path = f"{self.memory_save_path}_{count}"
+            count += 1
+        os.makedirs(self.memory_save_path)
+        self.feat_path = self.memory_save_path + "/feat.h5df"
+
+    # ------------------------------------------------------------------ query
+    def imaginary(self, text_prompts, vis=False):
+        raise NotImplementedError("text -> image generation (SD3.5, memory_2.py:258-276) is an injected collaborator: "
+                                  "assign memory.imaginary = callable returning an object with .images")
+
+    def _query_vector(self, prompt) -> torch.Tensor:
+        if torch.is_tensor(prompt) or isinstance(prompt, np.ndarray):           # direct query-vector injection
+            return torch.as_tensor(prompt, dtype=torch.float32).reshape(-1, self.token_dim).to(self.device)
+        from torchvision import transforms
+        tf = transforms.Compose([                                               # memory_2.py:66-70 (host, PIL)
+            transforms.Resize((self.args.query_height, self.args.query_width)),
+            transforms.ToTensor(),
+            transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225]),
+        ])
+        if isinstance(prompt, str):
+            gen = self.imaginary(prompt)
+            imgs = [gen.images[i] for i in range(self.args.imagenary_num)]
+        else:
+            imgs = [prompt]
+        x = torch.stack([tf(im) for im in imgs]).to(self.device)                # memory_2.py:577-580
+        with torch.no_grad():
+            tokens = self.dinov2.forward_features(x)["x_norm_patchtokens"].float().contiguous()
+        return gaussian_pool(tokens)                                            # memory_2.py:592-608
+
+    def voxel_localized(self, prompt, K=100, batch_size=300, region_radius=np.inf, curr_grid=None):
+        """memory_2.py:563-671.  Returns (best (1,3), top-K positions (K',3) int64, top-K similarities (K',) float64).
+        `batch_size` is accepted and ignored (the reference overwrites it at :593)."""
+        q = self._query_vector(prompt)
+        floor = None
+        if getattr(self.args, "load_single_floor", False) and self.floor_min_height is not None:
+            floor = (self.floor_min_height, self.floor_max_height)
+        sims, pos, cnt = self._store.query(q[:1], k=K, region_radius=region_radius, curr_grid=curr_grid, floor_range=floor)
+        n = int(cnt[0])
+        top_pos = pos[0, :n].cpu().numpy().astype(np.int64)
+        top_sim = sims[0, :n].cpu().numpy().astype(np.float64)
+        return top_pos[0:1].copy(), top_pos, top_sim
+
+    def voxel_localized_batch(self, queries, K=100, region_radius=np.inf, curr_grid=None):
+        """Batched form: queries (Q, D) -> device tensors (sims (Q,K), positions (Q,K,3), counts (Q,))."""
+        return self._store.query(self._query_vector(queries), k=K, region_radius=region_radius, curr_grid=curr_grid)
+
+    def long_memory_filter(self):
+        """memory_2.py:686-704."""
+        if getattr(self.args, "load_single_floor", False) and self.floor_min_height is not None:
+            return [o for o in self.long_memory_dict if self.floor_min_height <= o["loc"][2] <= self.floor_max_height]
+        return self.long_memory_dict
+
+    # ------------------------------------------------------------------ exploration drivers (simulator injected)
+    def excute(self, obs, actions):
+        """memory_2.py:1086-1101 without the cv2 preview."""
+        for action in actions:
+            if action != "stop":
+                obs = self.Env.sims.step(action)
+                st = self.Env.agent.get_state()
+                pos, rot = st.position, st.rotation
+                pose = np.array([pos[0], pos[1], pos[2], rot.x, rot.y, rot.z, rot.w])
+                self.obs2voxeltoken(obs, pose)
+                self.long_memory(obs)
+        return obs
+
+    def exploring_create_memory(self):
+        """memory_2.py:1104-1145: random navigable sub-goals, look-around, save."""
+        self.initial_memory()
+        obs = self.Env.sims.get_sensor_observations(0)
+        self.init_height = self.Env.agent.get_state().position[1]
+        pf = self.Env.plnner.pathfinder
+        for _ in range(self.args.random_move_num):
+            subgoal = pf.get_random_navigable_point()
+            island_begin = pf.get_island(self.Env.agent.get_state().position)
+            while (not pf.is_navigable(subgoal)) or (pf.get_island(subgoal) != island_begin):
+                subgoal = pf.get_random_navigable_point()
+            try:
+                path, _goal = self.Env.move2point(subgoal)
+                obs = self.excute(obs, path)
+                self.base_height.append(self.Env.agent.get_state().position[1])
+                obs = self.excute(obs, ["turn_left"] * int(360 / self.args.turn_left))
+            except Exception as e:   # noqa: BLE001  (the reference swallows motion failures the same way, :1126-1128)
+                print(f"move failed: {e}")
+                continue
+        self.update_memory_dist_base()
+        self.save_memory()
+
+    def create_memory(self):
+        raise NotImplementedError("keyboard-driven exploration (memory_2.py:1027-1083) needs an interactive simulator window")
+
+    # ------------------------------------------------------------------ persistence (npy set of memory_2.py:1136-1145)
+    def save_memory(self, path=None):
+        from . import io
+        io.save_memory(self, path or self.memory_save_path)
+
+    def load_memory(self, init_state=None, build_map=False):
+        """memory_2.py:166-256."""
+        from . import io
+        self._clear_memory()
+        if hasattr(self.Env, "reset"):
+            self.Env.reset(self.args, init_state=init_state, build_map=build_map)
+        self.memory_save_path = self.args.load_memory_path
+        if not build_map:
+            io.load_memory(self, self.memory_save_path)
+
+
+Memory = VoxelTokenMemory   # the name BASELINE.json's north_star uses

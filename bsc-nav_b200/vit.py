@@ -117,6 +117,15 @@ class ViTEngine:
                        "vit_forward_images")
         return {"x_norm_patchtokens": out}
 
+    def profile(self, enable: bool):
+        _lib.check(self.lib.bscnav_vit_profile(self._h, 1 if enable else 0), "vit_profile")
+
+    def profile_read(self) -> dict:
+        """{category: (ms, work, launches)} for 'gemm' (FLOPs), 'attention' (FLOPs), 'layernorm' (bytes), 'preprocess' (bytes)."""
+        ms, work, n = (C.c_double * 4)(), (C.c_double * 4)(), (C.c_int32 * 4)()
+        _lib.check(self.lib.bscnav_vit_profile_read(self._h, ms, work, n), "vit_profile_read")
+        return {k: (ms[i], work[i], n[i]) for i, k in enumerate(("gemm", "attention", "layernorm", "preprocess"))}
+
     def to(self, *_a, **_k):     # callers do `.to('cuda')` on the hub module (create_memory_for_dataset.py:58)
         return self
 

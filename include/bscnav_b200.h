@@ -152,6 +152,13 @@ int bscnav_vit_create(const bscnav_vit_cfg_t* c, const void* w_half, const float
                       int64_t workspace_bytes, int32_t max_batch, void** out_engine);
 void bscnav_vit_destroy(void* engine);
 
+/* Optional per-kernel timing for the roofline report: when enabled, every launch of the next forward calls is
+ * bracketed by CUDA events on the caller's stream.  profile_read synchronises on them and returns, per category
+ * {0: tcgen05 GEMM, 1: attention, 2: LayerNorm, 3: pre-processing}, summed milliseconds, algorithmic work
+ * (FLOPs for 0-1, bytes for 2-3) and launch counts (arrays of 4), then clears the record. */
+int bscnav_vit_profile(void* engine, int32_t enable);
+int bscnav_vit_profile_read(void* engine, double* out_ms, double* out_work, int32_t* out_launches);
+
 /* Frames path (_get_patch_token, memory_2.py:732-742): uint8 HWC frames (channels = 3 or 4, alpha ignored)
  * -> /255 -> antialiased bilinear resize to image x image -> ImageNet normalise -> ViT -> patch tokens.
  *   out_tokens float[batch*n_patch*dim];  out_pre optional float[batch*3*image*image] (pre-processed image) */

@@ -6,7 +6,10 @@ namespace bscnav {
 static constexpr int BM = 128;           // UMMA M (cta_group::1)
 static constexpr int BK = 64;            // one 128-byte swizzle atom of fp16 along K
 static constexpr int UK = 16;            // UMMA K for 16-bit operands
-static constexpr int kGemmThreads = 192;
+static constexpr int kEpiWarps = 8;
+static constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
+static constexpr int kTmaWarp = kEpiWarps;          // the scheduler favours the highest warp id: the single-thread
+static constexpr int kMmaWarp = kEpiWarps + 1;      // MMA issuer must never wait behind ALU-bound epilogue warps
 
 template <int BN> struct Cfg {
   static constexpr int kStages = BN == 256 ? 4 : 6;
@@ -14,7 +17,8 @@ template <int BN> struct Cfg {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarBytes = 256;
-  static constexpr int kSmem = kStages * kStageBytes + kBarBytes + 1024;   // + slack for 1024-byte alignment
+  static constexpr int kStagingBytes = kEpiWarps * 4096;                    // per epilogue warp: 32 rows x 128 B (TMA store box)
+  static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;   // + slack for 1024-byte alignment
   static constexpr int kTmemCols = 2 * BN;                                  // two accumulator stages
 };
 
@@ -44,6 +48,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -89,17 +108,17 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int n) {
 
 __device__ __forceinline__ float act_fn(float v, int act) {
   if (act == 0) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));   // GELU (erf)
-  return v / (1.0f + expf(-1.702f * v));                                          // QuickGELU
+  return __fdividef(v, 1.0f + __expf(-1.702f * v));                               // QuickGELU (|rel err| ~1e-6 << fp16 ulp)
 }
 
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M, int N, int K,
-           const GemmEpilogue epi) {
+k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+           const __grid_constant__ CUtensorMap map_out, int M, int N, int K, const GemmEpilogue epi) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* bars = smem + C::kStages * C::kStageBytes;
+  uint8_t* bars = smem + C::kStages * C::kStageBytes + C::kStagingBytes;
   const uint32_t full_bar = smem_u32(bars);                       // kStages x 8 B
   const uint32_t empty_bar = full_bar + 8 * C::kStages;           // kStages x 8 B
   const uint32_t tfull_bar = empty_bar + 8 * C::kStages;          // 2 x 8 B
@@ -113,12 +132,12 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, 32 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -127,7 +146,7 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
   tcgen05_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-  if (warp == 0) {
+  if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
@@ -145,7 +164,7 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(BN);
@@ -177,14 +196,21 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     }
   } else {
     // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global
-    const int quarter = warp & 3;                        // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
+    // 8 warps: TMEM lane quarter = warp % 4 (hardware restriction), column half = warp / 4.
+    // Output tiles leave through shared memory: each warp stages 32 rows x 128 B in the TMA 128-byte-swizzle layout
+    // (conflict-free 16-byte st.shared), then one lane issues a bulk tensor store -- or, for the fp32 residual stream,
+    // a bulk tensor reduce-add performed at L2 (one contributor per element per launch: deterministic).
+    const int quarter = warp & 3;
+    const int half = warp >> 2;
+    constexpr int kCols = BN / 2;                        // columns handled by one warp
+    const uint32_t stg = smem_base + C::kStages * C::kStageBytes + warp * 4096;
+    const bool via_tma = epi.mode == kOutHalf || epi.mode == kOutHalfAct || epi.mode == kOutResidual;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
-      mbar_wait(tfull_bar + 8 * acc, acc_phase);
-      tcgen05_fence_after();
-      const int m = m_blk * BM + quarter * 32 + lane;
+      const int m0 = m_blk * BM + quarter * 32;
+      const int m = m0 + lane;
       const bool in_m = m < M;
       long long out_row = m;
       const float* table_row = nullptr;
@@ -193,60 +219,92 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         out_row = (long long)f * epi.tokens + epi.row_off + p;
         table_row = epi.table + (long long)p * N;
       }
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
-        tmem_ld_wait();
-        const int n0 = n_blk * BN + c * 32;
-        if (in_m) {
-          float v[32];
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      tcgen05_fence_after();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (epi.bias ? __ldg(epi.bias + n0 + j) : 0.f);
-          if (epi.mode == kOutHalf || epi.mode == kOutHalfAct) {
+      for (int c = 0; c < kCols / 32; ++c) {
+        uint32_t r[32];
+        const int col = half * kCols + c * 32;
+        const int n0 = n_blk * BN + col;
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col), r);
+        float4 bq[8];
+        if (epi.bias) {                                   // in flight together with the TMEM load
+          const float4* b4 = reinterpret_cast<const float4*>(epi.bias + n0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bq[j] = __ldg(b4 + j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[4 * j] = __uint_as_float(r[4 * j]) + bq[j].x; v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bq[j].y;
+          v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bq[j].z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bq[j].w;
+        }
+        if (via_tma) {
+          const uint32_t row_base = stg + lane * 128;
+          const int sw = lane & 7;
+          if (epi.mode == kOutResidual) {
+            // fp32: one chunk = one full 128-byte row per lane
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              sts128(row_base + ((j ^ sw) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                     __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { tma_reduce_add_2d(&map_out, stg, n0, m0); bulk_commit(); }
+          } else {
             if (epi.mode == kOutHalfAct) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = act_fn(v[j], epi.act);
             }
-            uint4* dst = reinterpret_cast<uint4*>(static_cast<__half*>(epi.out) + out_row * epi.ld_out + n0);
+            // fp16: two chunks fill the 64-column (128-byte) box
+            if ((c & 1) == 0) {
+              if (lane == 0) bulk_wait_read0();
+              __syncwarp();
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               __half2 h0 = __floats2half2_rn(v[8 * j + 0], v[8 * j + 1]), h1 = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
               __half2 h2 = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]), h3 = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
-              uint4 u;
-              u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-              u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-              dst[j] = u;
+              sts128(row_base + ((((c & 1) * 4 + j) ^ sw) << 4), *reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                     *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
             }
-          } else {
-            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(epi.out) + out_row * epi.ld_out + n0);
-            if (epi.mode == kOutResidual) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 o = dst[j];
-                o.x += v[4 * j]; o.y += v[4 * j + 1]; o.z += v[4 * j + 2]; o.w += v[4 * j + 3];
-                dst[j] = o;
-              }
-            } else {
-              if (epi.mode == kOutPatchEmbed) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += __ldg(table_row + n0 + j);
-              }
-#pragma unroll
-              for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if ((c & 1) == 1) {
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) { tma_store_2d(&map_out, stg, n0 - 32, m0); bulk_commit(); }
             }
           }
+        } else if (in_m) {
+          float* dstf = static_cast<float*>(epi.out) + out_row * epi.ld_out + n0;
+          if (epi.mode == kOutPatchEmbed) {
+            const float4* t4 = reinterpret_cast<const float4*>(table_row + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 t = __ldg(t4 + j);
+              v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+            }
+          }
+          float4* dst = reinterpret_cast<float4*>(dstf);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
       }
       tcgen05_fence_before();
       mbar_arrive(tempty_bar + 8 * acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) bulk_wait_all();                      // outstanding bulk stores read shared memory: finish before exit
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::kTmemCols) : "memory");
   }
@@ -284,7 +342,24 @@ int make_operand_map(CUtensorMap* map, const void* ptr, long long rows, long lon
   return BSCNAV_OK;
 }
 
-int gemm_block_n(int N) { return (N % 256 == 0 && N >= 2048) ? 256 : 128; }
+// output tensor [rows, N] -> map with a 32-row x 128-byte box (64 fp16 or 32 fp32 columns), 128-byte swizzle
+int make_store_map(CUtensorMap* map, const void* ptr, long long rows, long long N, bool is_float) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { snprintf(g_last_error, sizeof(g_last_error), "cuTensorMapEncodeTiled entry point not found"); return BSCNAV_ECUDA; }
+  const int esz = is_float ? 4 : 2;
+  if (!ptr || rows <= 0 || N <= 0 || (N * esz) % 128 != 0 || (reinterpret_cast<uintptr_t>(ptr) & 127)) return BSCNAV_EINVAL;
+  cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)N * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, is_float ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(g_last_error, sizeof(g_last_error), "cuTensorMapEncodeTiled(store) failed: %d", (int)r); return BSCNAV_ECUDA; }
+  return BSCNAV_OK;
+}
+
+int gemm_block_n(int N) { return N % 256 == 0 ? 256 : 128; }
 
 static int sm_count() {
   static int n = 0;
@@ -298,8 +373,8 @@ static int sm_count() {
 }
 
 template <int BN>
-static int launch_bn(const CUtensorMap* map_a, const CUtensorMap* map_w, int M, int N, int K, const GemmEpilogue& epi,
-                     cudaStream_t stream) {
+static int launch_bn(const CUtensorMap* map_a, const CUtensorMap* map_w, const CUtensorMap* map_out, int M, int N, int K,
+                     const GemmEpilogue& epi, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     BSC_CUDA(cudaFuncSetAttribute(k_gemm_f16<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem));
@@ -307,15 +382,18 @@ static int launch_bn(const CUtensorMap* map_a, const CUtensorMap* map_w, int M, 
   }
   const int tiles = ((M + BM - 1) / BM) * (N / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  BSC_LAUNCH(k_gemm_f16<BN>, grid, kGemmThreads, Cfg<BN>::kSmem, stream, *map_a, *map_w, M, N, K, epi);
+  BSC_LAUNCH(k_gemm_f16<BN>, grid, kGemmThreads, Cfg<BN>::kSmem, stream, *map_a, *map_w, *map_out, M, N, K, epi);
   return BSCNAV_OK;
 }
 
-int gemm_f16_launch(const CUtensorMap* map_a, const CUtensorMap* map_w, int M, int N, int K, const GemmEpilogue& epi,
-                    cudaStream_t stream) {
+int gemm_f16_launch(const CUtensorMap* map_a, const CUtensorMap* map_w, const CUtensorMap* map_out, int M, int N, int K,
+                    const GemmEpilogue& epi, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0 || N % 128 != 0 || K % BK != 0 || !epi.out) return BSCNAV_EINVAL;
-  if (gemm_block_n(N) == 256) return launch_bn<256>(map_a, map_w, M, N, K, epi, stream);
-  return launch_bn<128>(map_a, map_w, M, N, K, epi, stream);
+  const bool via_tma = epi.mode == kOutHalf || epi.mode == kOutHalfAct || epi.mode == kOutResidual;
+  if (via_tma && !map_out) return BSCNAV_EINVAL;
+  if (!map_out) map_out = map_a;       // unused by the direct-store epilogues
+  if (gemm_block_n(N) == 256) return launch_bn<256>(map_a, map_w, map_out, M, N, K, epi, stream);
+  return launch_bn<128>(map_a, map_w, map_out, M, N, K, epi, stream);
 }
 
 }  // namespace bscnav
@@ -326,10 +404,13 @@ extern "C" int bscnav_gemm_f16(const void* a, const void* w, const float* bias, 
                                int32_t out_mode, int32_t act, void* stream) {
   if (!a || !w || !out || m <= 0 || n <= 0 || k <= 0 || n % 128 != 0 || k % 64 != 0) return BSCNAV_EINVAL;
   if (out_mode != kOutHalf && out_mode != kOutHalfAct && out_mode != kOutResidual && out_mode != kOutFloat) return BSCNAV_EINVAL;
-  CUtensorMap ma, mw;
+  CUtensorMap ma, mw, mo;
   if (int e = make_operand_map(&ma, a, m, k, BM)) return e;
   if (int e = make_operand_map(&mw, w, n, k, gemm_block_n(n))) return e;
+  const bool via_tma = out_mode != kOutFloat;
+  if (via_tma)
+    if (int e = make_store_map(&mo, out, m, n, out_mode == kOutResidual)) return e;
   GemmEpilogue epi{};
   epi.out = out; epi.bias = bias; epi.table = nullptr; epi.ld_out = n; epi.mode = out_mode; epi.act = act;
-  return gemm_f16_launch(&ma, &mw, m, n, k, epi, (cudaStream_t)stream);
+  return gemm_f16_launch(&ma, &mw, via_tma ? &mo : nullptr, m, n, k, epi, (cudaStream_t)stream);
 }

@@ -2,10 +2,12 @@
 //   out[M,N] (+)= A[M,K] * W[N,K]^T (+ bias, activation / residual / row-remap epilogues)
 // A and W are K-major fp16; accumulation is fp32 in TMEM.
 //
-//   warp 0      TMA producer   cp.async.bulk.tensor (128B swizzle) -> smem ring, mbarrier complete_tx
-//   warp 1      MMA issuer     one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (UMMA 128 x BN x 16),
+//   warp 8      TMA producer   cp.async.bulk.tensor (128B swizzle) -> smem ring, mbarrier complete_tx
+//   warp 9      MMA issuer     one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (UMMA 128 x BN x 16),
 //                              tcgen05.commit releases smem stages and publishes the TMEM accumulator
-//   warps 2..5  epilogue       tcgen05.ld (32 lanes x 32 columns per warp-instruction) -> registers -> global
+//   warps 0..7  epilogue       tcgen05.ld (32 lanes x 32 columns per warp-instruction) -> registers -> swizzled smem
+//                              -> cp.async.bulk.tensor store (fp16) / cp.reduce.async.bulk.tensor add.f32 (residual)
+//   warp 8      TMA producer,  warp 9  MMA issuer (see below)
 // Two TMEM accumulator stages (2 x BN columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 #pragma once
 #include <cuda.h>
@@ -31,12 +33,14 @@ struct GemmEpilogue {
   int np, tokens, row_off;  // kOutPatchEmbed: out row = (m / np) * tokens + row_off + m % np
 };
 
-int gemm_f16_launch(const CUtensorMap* map_a, const CUtensorMap* map_w, int M, int N, int K, const GemmEpilogue& epi,
-                    cudaStream_t stream);
+// map_out: store map of the output tensor (make_store_map) for the fp16 / residual epilogues; null for the others
+int gemm_f16_launch(const CUtensorMap* map_a, const CUtensorMap* map_w, const CUtensorMap* map_out, int M, int N, int K,
+                    const GemmEpilogue& epi, cudaStream_t stream);
+int make_store_map(CUtensorMap* map, const void* ptr, long long rows, long long N, bool is_float);
 
 // 2-D K-major fp16 operand [rows, K] -> tensor map with box {64, box_rows}, 128-byte swizzle
 int make_operand_map(CUtensorMap* map, const void* ptr, long long rows, long long K, int box_rows);
 
-int gemm_block_n(int N);   // 256 when N % 256 == 0 and the tile count fills the machine, else 128
+int gemm_block_n(int N);   // 256 when N % 256 == 0 (BN=128 is shared-memory-bandwidth bound at cta_group::1), else 128
 
 }  // namespace bscnav

@@ -83,6 +83,7 @@ struct VitEngine {
   int max_batch, Np, T;
   CUtensorMap map_a0, map_y, map_ao, map_h;          // activation operands
   CUtensorMap map_patch_w;
+  CUtensorMap out_qkv, out_h, out_x;                 // store maps of the GEMM outputs
   CUtensorMap map_qkv[64], map_proj[64], map_fc1[64], map_fc2[64];
   bool a0_cleared = false;
   // optional per-kernel timing (bench.py's roofline leg): CUDA events around every launch on the caller's stream
@@ -116,7 +117,7 @@ static int vit_run(VitEngine* e, int batch, float* out_tokens, cudaStream_t stre
   ep.out = e->ws.x; ep.bias = wf + e->L.patch_b; ep.table = wf + e->L.pos; ep.ld_out = D; ep.mode = kOutPatchEmbed;
   ep.np = Np; ep.tokens = T; ep.row_off = 1 + c.n_reg;
   { ProfScope ps(e, stream, kCatGemm, 2.0 * batch * Np * (double)D * c.patch_k_pad);
-    if (int r = gemm_f16_launch(&e->map_a0, &e->map_patch_w, batch * Np, D, c.patch_k_pad, ep, stream)) return r; }
+    if (int r = gemm_f16_launch(&e->map_a0, &e->map_patch_w, nullptr, batch * Np, D, c.patch_k_pad, ep, stream)) return r; }
   if (int r = fill_prefix_tokens(e->ws.x, wf + e->L.cls_pos, wf + e->L.reg, batch, T, c.n_reg, D, stream)) return r;
   if (c.ln_pre)
     if (int r = layernorm_inplace(e->ws.x, wf + e->L.ln_pre_w, wf + e->L.ln_pre_b, c.ln_eps, rows, D, stream)) return r;
@@ -127,23 +128,23 @@ static int vit_run(VitEngine* e, int batch, float* out_tokens, cudaStream_t stre
     GemmEpilogue e1{};
     e1.out = e->ws.qkv; e1.bias = wf + o.qkv_b; e1.ld_out = 3 * D; e1.mode = kOutHalf;
     { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * 3.0 * D * D);
-      if (int r = gemm_f16_launch(&e->map_y, &e->map_qkv[i], rows, 3 * D, D, e1, stream)) return r; }
+      if (int r = gemm_f16_launch(&e->map_y, &e->map_qkv[i], &e->out_qkv, rows, 3 * D, D, e1, stream)) return r; }
     { ProfScope ps(e, stream, kCatAttention, 4.0 * batch * (double)T * T * D);
       if (int r = attention_f16(e->ws.qkv, e->ws.ao, batch, T, c.heads, stream)) return r; }
     GemmEpilogue e2{};
     e2.out = e->ws.x; e2.bias = wf + o.proj_b; e2.ld_out = D; e2.mode = kOutResidual;
     { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * (double)D * D);
-      if (int r = gemm_f16_launch(&e->map_ao, &e->map_proj[i], rows, D, D, e2, stream)) return r; }
+      if (int r = gemm_f16_launch(&e->map_ao, &e->map_proj[i], &e->out_x, rows, D, D, e2, stream)) return r; }
     { ProfScope ps(e, stream, kCatLayerNorm, (double)rows * D * 6);
       if (int r = layernorm_half(e->ws.x, wf + o.ln2_w, wf + o.ln2_b, c.ln_eps, rows, D, e->ws.y, stream)) return r; }
     GemmEpilogue e3{};
     e3.out = e->ws.hmid; e3.bias = wf + o.fc1_b; e3.ld_out = M; e3.mode = kOutHalfAct; e3.act = c.act;
     { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * (double)M * D);
-      if (int r = gemm_f16_launch(&e->map_y, &e->map_fc1[i], rows, M, D, e3, stream)) return r; }
+      if (int r = gemm_f16_launch(&e->map_y, &e->map_fc1[i], &e->out_h, rows, M, D, e3, stream)) return r; }
     GemmEpilogue e4{};
     e4.out = e->ws.x; e4.bias = wf + o.fc2_b; e4.ld_out = D; e4.mode = kOutResidual;
     { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * (double)M * D);
-      if (int r = gemm_f16_launch(&e->map_h, &e->map_fc2[i], rows, D, M, e4, stream)) return r; }
+      if (int r = gemm_f16_launch(&e->map_h, &e->map_fc2[i], &e->out_x, rows, D, M, e4, stream)) return r; }
   }
   return layernorm_patch_tokens(e->ws.x, wf + e->L.ln_post_w, wf + e->L.ln_post_b, c.ln_eps, batch, T, 1 + c.n_reg, D,
                                 out_tokens, stream);
@@ -193,6 +194,9 @@ int bscnav_vit_create(const bscnav_vit_cfg_t* c, const void* w_half, const float
   r = r ? r : make_operand_map(&e->map_y, e->ws.y, rows, D, 128);
   r = r ? r : make_operand_map(&e->map_ao, e->ws.ao, rows, D, 128);
   r = r ? r : make_operand_map(&e->map_h, e->ws.hmid, rows, M, 128);
+  r = r ? r : make_store_map(&e->out_qkv, e->ws.qkv, rows, 3 * D, false);
+  r = r ? r : make_store_map(&e->out_h, e->ws.hmid, rows, M, false);
+  r = r ? r : make_store_map(&e->out_x, e->ws.x, rows, D, true);
   r = r ? r : make_operand_map(&e->map_patch_w, e->wh + e->L.patch_w, D, c->patch_k_pad, gemm_block_n((int)D));
   for (int i = 0; i < c->depth && !r; ++i) {
     const LayerOff& o = e->L.layer[i];

@@ -184,9 +184,9 @@ int layernorm_patch_tokens(const float* x, const float* g, const float* b, float
 
 // ---------------------------------------------------------------------------------------------------------
 // Multi-head self-attention, head dim 64, fp16 operands, fp32 softmax / accumulation.
-// One CTA = 64 queries of one (frame, head); 4 warps x 16 query rows; K and V of the head staged once in shared
-// memory (16-byte chunks XOR-swizzled by row so ldmatrix is conflict-free); flash-style online softmax over
-// 64-key blocks with mma.sync.m16n8k16 -- 4% of the ViT's FLOPs; the GEMMs carry the tcgen05 work.
+// One CTA = 128 queries of one (frame, head); 8 warps x 16 query rows; K/V stream through shared memory in 64-key
+// blocks, double-buffered with cp.async (16-byte chunks XOR-swizzled by row so ldmatrix is conflict-free);
+// flash-style online softmax with mma.sync.m16n8k16 -- 4% of the ViT's FLOPs; the GEMMs carry the tcgen05 work.
 static constexpr int kHd = 64;
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -206,109 +206,140 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 // byte offset of (row, 16-byte chunk) in a [rows][64] fp16 tile with the chunk index XOR-swizzled by row
 __device__ __forceinline__ uint32_t sw_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
 
-__global__ void __launch_bounds__(128)
-k_attention(const __half* __restrict__ qkv, __half* __restrict__ out, int T, int heads, int t_pad) {
+// 16-byte async copy global -> shared; src_bytes == 0 zero-fills (rows past the sequence end)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+static constexpr int kAttnQ = 128;          // queries per CTA (8 warps x 16 rows)
+static constexpr int kAttnThreads = 256;
+static constexpr int kAttnSmem = kAttnQ * 128 + 2 * 2 * 64 * 128;   // Q tile + double-buffered K and V blocks of 64 keys
+
+__global__ void __launch_bounds__(kAttnThreads)
+k_attention(const __half* __restrict__ qkv, __half* __restrict__ out, int T, int heads) {
   extern __shared__ __align__(128) uint8_t smem_attn[];
-  uint8_t* sQ = smem_attn;                       // 64 x 128 B
-  uint8_t* sK = sQ + 64 * 128;                   // t_pad x 128 B
-  uint8_t* sV = sK + (size_t)t_pad * 128;        // t_pad x 128 B
   const int D = heads * kHd;
   const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const __half* base = qkv + (long long)b * T * 3 * D + head * kHd;
-  const uint4 zero = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < 64 * 8; i += 128) {
-    const int r = i >> 3, c = i & 7, t = qt * 64 + r;
-    const uint4 v = t < T ? *reinterpret_cast<const uint4*>(base + (long long)t * 3 * D + c * 8) : zero;
-    *reinterpret_cast<uint4*>(sQ + sw_off(r, c)) = v;
-  }
-  for (int i = tid; i < t_pad * 8; i += 128) {
-    const int r = i >> 3, c = i & 7;
-    uint4 kv = zero, vv = zero;
-    if (r < T) {
-      kv = *reinterpret_cast<const uint4*>(base + (long long)r * 3 * D + D + c * 8);
-      vv = *reinterpret_cast<const uint4*>(base + (long long)r * 3 * D + 2 * D + c * 8);
-    }
-    *reinterpret_cast<uint4*>(sK + sw_off(r, c)) = kv;
-    *reinterpret_cast<uint4*>(sV + sw_off(r, c)) = vv;
-  }
-  __syncthreads();
-  const uint32_t sQa = (uint32_t)__cvta_generic_to_shared(sQ), sKa = (uint32_t)__cvta_generic_to_shared(sK),
-                 sVa = (uint32_t)__cvta_generic_to_shared(sV);
-  // Q fragments: 4 k-steps of 16 along the head dim
-  uint32_t qf[4][4];
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks)
-    ldsm_x4(sQa + sw_off(warp * 16 + (lane & 15), ks * 2 + (lane >> 4)), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+  const uint32_t sQa = (uint32_t)__cvta_generic_to_shared(smem_attn);
+  const uint32_t sKV = sQa + kAttnQ * 128;       // buffer i: K at sKV + i*16384, V at sKV + i*16384 + 8192
+  const int n_kb = (T + 63) / 64;
 
+  // stage Q (once) and K/V block 0
+  for (int i = tid; i < kAttnQ * 8; i += kAttnThreads) {
+    const int r = i >> 3, c = i & 7, t = qt * kAttnQ + r;
+    cp_async16(sQa + sw_off(r, c), base + (long long)(t < T ? t : 0) * 3 * D + c * 8, t < T ? 16 : 0);
+  }
+  auto load_kv = [&](int kb, int buf) {
+    for (int i = tid; i < 64 * 8; i += kAttnThreads) {
+      const int r = i >> 3, c = i & 7, t = kb * 64 + r;
+      const __half* src = base + (long long)(t < T ? t : 0) * 3 * D + c * 8;
+      const int nb = t < T ? 16 : 0;
+      cp_async16(sKV + buf * 16384 + sw_off(r, c), src + D, nb);
+      cp_async16(sKV + buf * 16384 + 8192 + sw_off(r, c), src + 2 * D, nb);
+    }
+  };
+  load_kv(0, 0);
+  cp_async_commit();
+
+  const bool active = qt * kAttnQ + warp * 16 < T;     // warps whose 16 query rows are all past the end skip the math
+  uint32_t qf[4][4];
   float o[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // running max / sum of rows (lane/4) and (lane/4)+8
   const float kLog2e = 1.4426950408889634f;
 
-  for (int kb = 0; kb < t_pad / 64; ++kb) {
-    float s[8][4];
+  for (int kb = 0; kb < n_kb; ++kb) {
+    const int buf = kb & 1;
+    if (kb + 1 < n_kb) {
+      load_kv(kb + 1, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (active) {
+      if (kb == 0) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
-    // S = Q K^T for 64 keys: B fragments straight from K rows (key-major, head dim contiguous)
+        for (int ks = 0; ks < 4; ++ks)
+          ldsm_x4(sQa + sw_off(warp * 16 + (lane & 15), ks * 2 + (lane >> 4)), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+      }
+      const uint32_t sKa = sKV + buf * 16384, sVa = sKa + 8192;
+      float s[8][4];
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
+      for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+      // S = Q K^T for 64 keys: B fragments straight from K rows (key-major, head dim contiguous)
 #pragma unroll
-      for (int np = 0; np < 4; ++np) {     // pairs of 8-key tiles
-        uint32_t b0, b1, b2, b3;
-        const int key = kb * 64 + np * 16 + (lane & 7) + ((lane >> 4) << 3);
-        ldsm_x4(sKa + sw_off(key, ks * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
-        mma_16816(s[2 * np], qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], b0, b1);
-        mma_16816(s[2 * np + 1], qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], b2, b3);
+      for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {     // pairs of 8-key tiles
+          uint32_t b0, b1, b2, b3;
+          const int key = np * 16 + (lane & 7) + ((lane >> 4) << 3);
+          ldsm_x4(sKa + sw_off(key, ks * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
+          mma_16816(s[2 * np], qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], b0, b1);
+          mma_16816(s[2 * np + 1], qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], b2, b3);
+        }
+      }
+      // mask keys >= T (last block only), block row maxima
+      float bm0 = -INFINITY, bm1 = -INFINITY;
+      if (kb == n_kb - 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int key = kb * 64 + i * 8 + 2 * (lane & 3);
+          if (key >= T) { s[i][0] = -INFINITY; s[i][2] = -INFINITY; }
+          if (key + 1 >= T) { s[i][1] = -INFINITY; s[i][3] = -INFINITY; }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        bm0 = fmaxf(bm0, fmaxf(s[i][0], s[i][1]));
+        bm1 = fmaxf(bm1, fmaxf(s[i][2], s[i][3]));
+      }
+      bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+      bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+      const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);      // finite: every block holds at least one valid key
+      const float sc0 = exp2f((m0 - nm0) * kLog2e), sc1 = exp2f((m1 - nm1) * kLog2e);
+      m0 = nm0; m1 = nm1;
+      const float mo0 = m0 * kLog2e, mo1 = m1 * kLog2e;
+      float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i][0] = exp2f(fmaf(s[i][0], kLog2e, -mo0)); s[i][1] = exp2f(fmaf(s[i][1], kLog2e, -mo0));
+        s[i][2] = exp2f(fmaf(s[i][2], kLog2e, -mo1)); s[i][3] = exp2f(fmaf(s[i][3], kLog2e, -mo1));
+        ps0 += s[i][0] + s[i][1];
+        ps1 += s[i][2] + s[i][3];
+      }
+      l0 = l0 * sc0 + ps0;
+      l1 = l1 * sc1 + ps1;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { o[i][0] *= sc0; o[i][1] *= sc0; o[i][2] *= sc1; o[i][3] *= sc1; }
+      // O += P V : P from the S accumulators (fp16), V fragments via transposing ldmatrix
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {       // 16 keys per step
+        const uint32_t a0 = pack_half2(s[2 * ks][0], s[2 * ks][1]), a1 = pack_half2(s[2 * ks][2], s[2 * ks][3]);
+        const uint32_t a2 = pack_half2(s[2 * ks + 1][0], s[2 * ks + 1][1]), a3 = pack_half2(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {     // pairs of 8-wide head-dim tiles
+          uint32_t b0, b1, b2, b3;
+          const int key = ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+          ldsm_x4_t(sVa + sw_off(key, np * 2 + (lane >> 4)), b0, b1, b2, b3);
+          mma_16816(o[2 * np], a0, a1, a2, a3, b0, b1);
+          mma_16816(o[2 * np + 1], a0, a1, a2, a3, b2, b3);
+        }
       }
     }
-    // mask keys >= T, block row maxima
-    float bm0 = -INFINITY, bm1 = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int key = kb * 64 + i * 8 + 2 * (lane & 3);
-      if (key >= T) { s[i][0] = -INFINITY; s[i][2] = -INFINITY; }
-      if (key + 1 >= T) { s[i][1] = -INFINITY; s[i][3] = -INFINITY; }
-      bm0 = fmaxf(bm0, fmaxf(s[i][0], s[i][1]));
-      bm1 = fmaxf(bm1, fmaxf(s[i][2], s[i][3]));
-    }
-    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
-    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
-    const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);      // finite: every block holds at least one valid key
-    const float sc0 = exp2f((m0 - nm0) * kLog2e), sc1 = exp2f((m1 - nm1) * kLog2e);
-    m0 = nm0; m1 = nm1;
-    float ps0 = 0.f, ps1 = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      s[i][0] = exp2f((s[i][0] - m0) * kLog2e); s[i][1] = exp2f((s[i][1] - m0) * kLog2e);
-      s[i][2] = exp2f((s[i][2] - m1) * kLog2e); s[i][3] = exp2f((s[i][3] - m1) * kLog2e);
-      ps0 += s[i][0] + s[i][1];
-      ps1 += s[i][2] + s[i][3];
-    }
-    l0 = l0 * sc0 + ps0;
-    l1 = l1 * sc1 + ps1;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { o[i][0] *= sc0; o[i][1] *= sc0; o[i][2] *= sc1; o[i][3] *= sc1; }
-    // O += P V : P from the S accumulators (fp16), V fragments via transposing ldmatrix
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {       // 16 keys per step
-      const uint32_t a0 = pack_half2(s[2 * ks][0], s[2 * ks][1]), a1 = pack_half2(s[2 * ks][2], s[2 * ks][3]);
-      const uint32_t a2 = pack_half2(s[2 * ks + 1][0], s[2 * ks + 1][1]), a3 = pack_half2(s[2 * ks + 1][2], s[2 * ks + 1][3]);
-#pragma unroll
-      for (int np = 0; np < 4; ++np) {     // pairs of 8-wide head-dim tiles
-        uint32_t b0, b1, b2, b3;
-        const int key = kb * 64 + ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
-        ldsm_x4_t(sVa + sw_off(key, np * 2 + (lane >> 4)), b0, b1, b2, b3);
-        mma_16816(o[2 * np], a0, a1, a2, a3, b0, b1);
-        mma_16816(o[2 * np + 1], a0, a1, a2, a3, b2, b3);
-      }
-    }
+    __syncthreads();     // everyone is done with this K/V buffer before the next prefetch overwrites it
   }
+  if (!active) return;
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
   const float i0 = 1.f / l0, i1 = 1.f / l1;
-  const int r0 = qt * 64 + warp * 16 + (lane >> 2), r1 = r0 + 8;
+  const int r0 = qt * kAttnQ + warp * 16 + (lane >> 2), r1 = r0 + 8;
   __half* ob = out + (long long)b * T * D + head * kHd + 2 * (lane & 3);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -319,15 +350,13 @@ k_attention(const __half* __restrict__ qkv, __half* __restrict__ out, int T, int
 
 int attention_f16(const __half* qkv, __half* out, int batch, int T, int heads, cudaStream_t stream) {
   if (batch <= 0 || T <= 0 || heads <= 0) return BSCNAV_EINVAL;
-  const int t_pad = (T + 63) / 64 * 64;
-  const size_t smem = 64 * 128 + 2 * (size_t)t_pad * 128;
-  if (smem > 200 * 1024) return BSCNAV_EINVAL;
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    BSC_CUDA(cudaFuncSetAttribute(k_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
+  static bool attr_set = false;
+  if (!attr_set) {
+    BSC_CUDA(cudaFuncSetAttribute(k_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    attr_set = true;
   }
-  BSC_LAUNCH(k_attention, dim3((unsigned)(t_pad / 64), (unsigned)heads, (unsigned)batch), 128, smem, stream, qkv, out, T, heads, t_pad);
+  BSC_LAUNCH(k_attention, dim3((unsigned)((T + kAttnQ - 1) / kAttnQ), (unsigned)heads, (unsigned)batch), kAttnThreads, kAttnSmem,
+             stream, qkv, out, T, heads);
   return BSCNAV_OK;
 }
 

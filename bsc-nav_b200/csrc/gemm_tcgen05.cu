@@ -106,12 +106,17 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-__device__ __forceinline__ float act_fn(float v, int act) {
-  if (act == 0) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));   // GELU (erf)
-  return __fdividef(v, 1.0f + __expf(-1.702f * v));                               // QuickGELU (|rel err| ~1e-6 << fp16 ulp)
+// activation selected at compile time: evaluating both and selecting cost 35 instructions per element
+template <int ACT> __device__ __forceinline__ float act_fn(float v) {
+  if (ACT == 0) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));   // GELU (erf)
+  // QuickGELU v * sigmoid(1.702 v) = v / (1 + 2^(-1.702 log2(e) v)): two MUFU ops, |rel err| ~1e-6 << fp16 ulp
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -2.4554669595930157f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return v * r;
 }
 
-template <int BN>
+template <int BN, int MODE, int ACT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
            const __grid_constant__ CUtensorMap map_out, int M, int N, int K, const GemmEpilogue epi) {
@@ -200,11 +205,18 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     // Output tiles leave through shared memory: each warp stages 32 rows x 128 B in the TMA 128-byte-swizzle layout
     // (conflict-free 16-byte st.shared), then one lane issues a bulk tensor store -- or, for the fp32 residual stream,
     // a bulk tensor reduce-add performed at L2 (one contributor per element per launch: deterministic).
+    // MODE is a template parameter and the column loop is not unrolled: the epilogue stays small enough for the
+    // instruction cache (an unrolled multi-mode body spent a quarter of its samples in stall_no_inst).
+    constexpr bool kHalfOut = MODE == kOutHalf || MODE == kOutHalfAct;
+    constexpr bool kViaTma = kHalfOut || MODE == kOutResidual;
+    constexpr int kCols = BN / 2;                        // columns handled by one warp
+    constexpr int kIter = kHalfOut ? 64 : 32;            // columns per iteration == one 128-byte TMA box row
+    constexpr int kLd = kIter / 32;                      // TMEM loads in flight per iteration
     const int quarter = warp & 3;
     const int half = warp >> 2;
-    constexpr int kCols = BN / 2;                        // columns handled by one warp
     const uint32_t stg = smem_base + C::kStages * C::kStageBytes + warp * 4096;
-    const bool via_tma = epi.mode == kOutHalf || epi.mode == kOutHalfAct || epi.mode == kOutResidual;
+    const uint32_t row_base = stg + lane * 128;
+    const int sw = lane & 7;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -214,92 +226,92 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       const bool in_m = m < M;
       long long out_row = m;
       const float* table_row = nullptr;
-      if (epi.mode == kOutPatchEmbed && in_m) {
+      if (MODE == kOutPatchEmbed && in_m) {
         const int f = m / epi.np, p = m - f * epi.np;
         out_row = (long long)f * epi.tokens + epi.row_off + p;
         table_row = epi.table + (long long)p * N;
       }
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tcgen05_fence_after();
-#pragma unroll
-      for (int c = 0; c < kCols / 32; ++c) {
-        uint32_t r[32];
-        const int col = half * kCols + c * 32;
+#pragma unroll 1
+      for (int it = 0; it < kCols / kIter; ++it) {
+        const int col = half * kCols + it * kIter;
         const int n0 = n_blk * BN + col;
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col), r);
-        float4 bq[8];
-        if (epi.bias) {                                   // in flight together with the TMEM load
+        uint32_t r[kLd][32];
+#pragma unroll
+        for (int u = 0; u < kLd; ++u)
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col + 32 * u), r[u]);
+        float4 bq[kLd][8];
+        if (epi.bias) {                                   // in flight together with the TMEM loads
           const float4* b4 = reinterpret_cast<const float4*>(epi.bias + n0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) bq[j] = __ldg(b4 + j);
+          for (int j = 0; j < 8 * kLd; ++j) bq[j / 8][j % 8] = __ldg(b4 + j);
         } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) bq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = 0; j < 8 * kLd; ++j) bq[j / 8][j % 8] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          v[4 * j] = __uint_as_float(r[4 * j]) + bq[j].x; v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bq[j].y;
-          v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bq[j].z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bq[j].w;
+        if (it == kCols / kIter - 1) {                    // accumulator fully read: hand the TMEM stage back to the MMA warp
+          tcgen05_fence_before();
+          mbar_arrive(tempty_bar + 8 * acc);
         }
-        if (via_tma) {
-          const uint32_t row_base = stg + lane * 128;
-          const int sw = lane & 7;
-          if (epi.mode == kOutResidual) {
-            // fp32: one chunk = one full 128-byte row per lane
-            if (lane == 0) bulk_wait_read0();
-            __syncwarp();
+        if (kViaTma) {                                    // staging buffer free again? (previous bulk op has read it)
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+        }
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              sts128(row_base + ((j ^ sw) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
-                     __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) { tma_reduce_add_2d(&map_out, stg, n0, m0); bulk_commit(); }
-          } else {
-            if (epi.mode == kOutHalfAct) {
+        for (int u = 0; u < kLd; ++u) {
+          float v[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = act_fn(v[j], epi.act);
-            }
-            // fp16: two chunks fill the 64-column (128-byte) box
-            if ((c & 1) == 0) {
-              if (lane == 0) bulk_wait_read0();
-              __syncwarp();
+          for (int j = 0; j < 8; ++j) {
+            v[4 * j] = __uint_as_float(r[u][4 * j]) + bq[u][j].x; v[4 * j + 1] = __uint_as_float(r[u][4 * j + 1]) + bq[u][j].y;
+            v[4 * j + 2] = __uint_as_float(r[u][4 * j + 2]) + bq[u][j].z; v[4 * j + 3] = __uint_as_float(r[u][4 * j + 3]) + bq[u][j].w;
+          }
+          if (kHalfOut) {
+            if (MODE == kOutHalfAct) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = act_fn<ACT>(v[j]);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               __half2 h0 = __floats2half2_rn(v[8 * j + 0], v[8 * j + 1]), h1 = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
               __half2 h2 = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]), h3 = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
-              sts128(row_base + ((((c & 1) * 4 + j) ^ sw) << 4), *reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+              sts128(row_base + (((u * 4 + j) ^ sw) << 4), *reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
                      *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
             }
-            if ((c & 1) == 1) {
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) { tma_store_2d(&map_out, stg, n0 - 32, m0); bulk_commit(); }
-            }
-          }
-        } else if (in_m) {
-          float* dstf = static_cast<float*>(epi.out) + out_row * epi.ld_out + n0;
-          if (epi.mode == kOutPatchEmbed) {
-            const float4* t4 = reinterpret_cast<const float4*>(table_row + n0);
+          } else if (MODE == kOutResidual) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 t = __ldg(t4 + j);
-              v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
-            }
-          }
-          float4* dst = reinterpret_cast<float4*>(dstf);
+            for (int j = 0; j < 8; ++j)
+              sts128(row_base + ((j ^ sw) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                     __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+          } else if (in_m) {
+            float* dstf = static_cast<float*>(epi.out) + out_row * epi.ld_out + n0 + 32 * u;
+            if (MODE == kOutPatchEmbed) {
+              const float4* t4 = reinterpret_cast<const float4*>(table_row + n0 + 32 * u);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              for (int j = 0; j < 8; ++j) {
+                const float4 t = __ldg(t4 + j);
+                v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+              }
+            }
+            float4* dst = reinterpret_cast<float4*>(dstf);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        }
+        if (kViaTma) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (MODE == kOutResidual) tma_reduce_add_2d(&map_out, stg, n0, m0);
+            else tma_store_2d(&map_out, stg, n0, m0);
+            bulk_commit();
+          }
         }
       }
-      tcgen05_fence_before();
-      mbar_arrive(tempty_bar + 8 * acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (lane == 0) bulk_wait_all();                      // outstanding bulk stores read shared memory: finish before exit
+    if (kViaTma && lane == 0) bulk_wait_all();           // outstanding bulk ops read shared memory: finish before exit
   }
 
   tcgen05_fence_before();
@@ -372,18 +384,33 @@ static int sm_count() {
   return n;
 }
 
-template <int BN>
-static int launch_bn(const CUtensorMap* map_a, const CUtensorMap* map_w, const CUtensorMap* map_out, int M, int N, int K,
-                     const GemmEpilogue& epi, cudaStream_t stream) {
+template <int BN, int MODE, int ACT = 0>
+static int launch_bn_mode(const CUtensorMap* map_a, const CUtensorMap* map_w, const CUtensorMap* map_out, int M, int N, int K,
+                          const GemmEpilogue& epi, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    BSC_CUDA(cudaFuncSetAttribute(k_gemm_f16<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem));
+    BSC_CUDA(cudaFuncSetAttribute((k_gemm_f16<BN, MODE, ACT>), cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem));
     attr_set = true;
   }
   const int tiles = ((M + BM - 1) / BM) * (N / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  BSC_LAUNCH(k_gemm_f16<BN>, grid, kGemmThreads, Cfg<BN>::kSmem, stream, *map_a, *map_w, *map_out, M, N, K, epi);
+  BSC_LAUNCH((k_gemm_f16<BN, MODE, ACT>), grid, kGemmThreads, Cfg<BN>::kSmem, stream, *map_a, *map_w, *map_out, M, N, K, epi);
   return BSCNAV_OK;
+}
+
+template <int BN>
+static int launch_bn(const CUtensorMap* map_a, const CUtensorMap* map_w, const CUtensorMap* map_out, int M, int N, int K,
+                     const GemmEpilogue& epi, cudaStream_t stream) {
+  switch (epi.mode) {
+    case kOutHalf: return launch_bn_mode<BN, kOutHalf>(map_a, map_w, map_out, M, N, K, epi, stream);
+    case kOutHalfAct:
+      if (epi.act == 0) return launch_bn_mode<BN, kOutHalfAct, 0>(map_a, map_w, map_out, M, N, K, epi, stream);
+      return launch_bn_mode<BN, kOutHalfAct, 1>(map_a, map_w, map_out, M, N, K, epi, stream);
+    case kOutResidual: return launch_bn_mode<BN, kOutResidual>(map_a, map_w, map_out, M, N, K, epi, stream);
+    case kOutPatchEmbed: return launch_bn_mode<BN, kOutPatchEmbed>(map_a, map_w, map_out, M, N, K, epi, stream);
+    case kOutFloat: return launch_bn_mode<BN, kOutFloat>(map_a, map_w, map_out, M, N, K, epi, stream);
+    default: return BSCNAV_EINVAL;
+  }
 }
 
 int gemm_f16_launch(const CUtensorMap* map_a, const CUtensorMap* map_w, const CUtensorMap* map_out, int M, int N, int K,

@@ -16,13 +16,13 @@ def timeit(fn, n=10, warm=3):
 
 B = int(os.environ.get("B", 64)); T = 257; M = B * T
 g = torch.Generator("cuda").manual_seed(0)
-for (N, K, mode) in ((3072, 1024, 0), (1024, 1024, 2), (4096, 1024, 1), (1024, 4096, 2), (1024, 640, 4)):
+for (N, K, mode, act) in ((3072, 1024, 0, 0), (1024, 1024, 2, 0), (4096, 1024, 1, 1), (4096, 1024, 1, 0), (1024, 4096, 2, 0), (1024, 640, 4, 0)):
     a = torch.randn(M, K, device="cuda", generator=g).half(); w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).half()
     bias = torch.randn(N, device="cuda")
     out = torch.zeros(M, N, device="cuda", dtype=torch.float16 if mode in (0, 1) else torch.float32)
-    ms = timeit(lambda: vit.gemm_f16(a, w, bias, out_mode=mode, out=out))
+    ms = timeit(lambda: vit.gemm_f16(a, w, bias, out_mode=mode, act=act, out=out))
     ref = timeit(lambda: torch.matmul(a, w.t()))
-    print(f"gemm M={M} N={N} K={K} mode={mode}: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s   (torch.matmul fp16: {ref:.3f} ms {2*M*N*K/ref/1e9:.1f} TF)")
+    print(f"gemm M={M} N={N} K={K} mode={mode} act={act}: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s   (torch.matmul fp16: {ref:.3f} ms {2*M*N*K/ref/1e9:.1f} TF)")
 cfg = pkg.CLIP_L14
 eng = pkg.ViTEngine(cfg, pkg.random_weights(cfg, 0), max_batch=B)
 rgb = torch.randint(0, 256, (B, 480, 640, 4), dtype=torch.uint8, device="cuda")

@@ -184,9 +184,10 @@ int layernorm_patch_tokens(const float* x, const float* g, const float* b, float
 
 // ---------------------------------------------------------------------------------------------------------
 // Multi-head self-attention, head dim 64, fp16 operands, fp32 softmax / accumulation.
-// One CTA = 128 queries of one (frame, head); 8 warps x 16 query rows; K/V stream through shared memory in 64-key
-// blocks, double-buffered with cp.async (16-byte chunks XOR-swizzled by row so ldmatrix is conflict-free);
-// flash-style online softmax with mma.sync.m16n8k16 -- 4% of the ViT's FLOPs; the GEMMs carry the tcgen05 work.
+// One CTA = one (frame, head): K and V are staged once in shared memory with cp.async (16-byte chunks XOR-swizzled
+// by row so ldmatrix is conflict-free) and shared by all query rows; each of the 6 warps owns 16-row query groups
+// and runs a flash-style online softmax over 64-key blocks with mma.sync.m16n8k16, no block-level barriers in the loop.
+// 4% of the ViT's FLOPs; the GEMMs carry the tcgen05 work.
 static constexpr int kHd = 64;
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -196,8 +197,14 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t&
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
 __device__ __forceinline__ void mma_16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  // not volatile: a pure register operation, so the scheduler may interleave it with the (ordered) ldmatrix stream
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float fast_exp2(float x) {      // single MUFU.EX2; inputs are <= 0, flush-to-zero is the wanted limit
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
@@ -213,80 +220,80 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int sr
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-static constexpr int kAttnQ = 128;          // queries per CTA (8 warps x 16 rows)
-static constexpr int kAttnThreads = 256;
-static constexpr int kAttnSmem = kAttnQ * 128 + 2 * 2 * 64 * 128;   // Q tile + double-buffered K and V blocks of 64 keys
+static constexpr int kAttnWarps = 6;        // 257 (261) tokens = 17 row groups of 16 -> 3 rounds of 6 warps, 94% of lanes busy
+static constexpr int kAttnThreads = kAttnWarps * 32;
 
-__global__ void __launch_bounds__(kAttnThreads)
-k_attention(const __half* __restrict__ qkv, __half* __restrict__ out, int T, int heads) {
+__global__ void __launch_bounds__(kAttnThreads, 2)
+k_attention(const __half* __restrict__ qkv, __half* __restrict__ out, int T, int heads, int t_pad) {
   extern __shared__ __align__(128) uint8_t smem_attn[];
   const int D = heads * kHd;
-  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int head = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const __half* base = qkv + (long long)b * T * 3 * D + head * kHd;
-  const uint32_t sQa = (uint32_t)__cvta_generic_to_shared(smem_attn);
-  const uint32_t sKV = sQa + kAttnQ * 128;       // buffer i: K at sKV + i*16384, V at sKV + i*16384 + 8192
-  const int n_kb = (T + 63) / 64;
-
-  // stage Q (once) and K/V block 0
-  for (int i = tid; i < kAttnQ * 8; i += kAttnThreads) {
-    const int r = i >> 3, c = i & 7, t = qt * kAttnQ + r;
-    cp_async16(sQa + sw_off(r, c), base + (long long)(t < T ? t : 0) * 3 * D + c * 8, t < T ? 16 : 0);
+  const uint32_t sKa = (uint32_t)__cvta_generic_to_shared(smem_attn);
+  const uint32_t sVa = sKa + t_pad * 128;
+  // K and V of this (frame, head): staged once, shared by every query row of the head
+  for (int i = tid; i < t_pad * 8; i += kAttnThreads) {
+    const int r = i >> 3, c = i & 7;
+    const __half* src = base + (long long)(r < T ? r : 0) * 3 * D + c * 8;
+    const int nb = r < T ? 16 : 0;
+    cp_async16(sKa + sw_off(r, c), src + D, nb);
+    cp_async16(sVa + sw_off(r, c), src + 2 * D, nb);
   }
-  auto load_kv = [&](int kb, int buf) {
-    for (int i = tid; i < 64 * 8; i += kAttnThreads) {
-      const int r = i >> 3, c = i & 7, t = kb * 64 + r;
-      const __half* src = base + (long long)(t < T ? t : 0) * 3 * D + c * 8;
-      const int nb = t < T ? 16 : 0;
-      cp_async16(sKV + buf * 16384 + sw_off(r, c), src + D, nb);
-      cp_async16(sKV + buf * 16384 + 8192 + sw_off(r, c), src + 2 * D, nb);
-    }
-  };
-  load_kv(0, 0);
   cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
 
-  const bool active = qt * kAttnQ + warp * 16 < T;     // warps whose 16 query rows are all past the end skip the math
-  uint32_t qf[4][4];
-  float o[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
-  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // running max / sum of rows (lane/4) and (lane/4)+8
+  const int n_kb = (T + 63) / 64;
+  const int n_groups = (T + 15) / 16;
   const float kLog2e = 1.4426950408889634f;
-
-  for (int kb = 0; kb < n_kb; ++kb) {
-    const int buf = kb & 1;
-    if (kb + 1 < n_kb) {
-      load_kv(kb + 1, buf ^ 1);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-    if (active) {
-      if (kb == 0) {
+  for (int g = warp; g < n_groups; g += kAttnWarps) {
+    // Q fragments (m16k16 A operand, 4 k-steps) straight from global memory: rows r0 and r0+8 of this group
+    const int r0 = g * 16 + (lane >> 2), r1 = r0 + 8;
+    uint32_t qf[4][4];
+    {
+      const __half* q0 = base + (long long)r0 * 3 * D + 2 * (lane & 3);
+      const __half* q1 = base + (long long)r1 * 3 * D + 2 * (lane & 3);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          ldsm_x4(sQa + sw_off(warp * 16 + (lane & 15), ks * 2 + (lane >> 4)), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+      for (int ks = 0; ks < 4; ++ks) {
+        qf[ks][0] = r0 < T ? *reinterpret_cast<const uint32_t*>(q0 + ks * 16) : 0u;
+        qf[ks][1] = r1 < T ? *reinterpret_cast<const uint32_t*>(q1 + ks * 16) : 0u;
+        qf[ks][2] = r0 < T ? *reinterpret_cast<const uint32_t*>(q0 + ks * 16 + 8) : 0u;
+        qf[ks][3] = r1 < T ? *reinterpret_cast<const uint32_t*>(q1 + ks * 16 + 8) : 0u;
       }
-      const uint32_t sKa = sKV + buf * 16384, sVa = sKa + 8192;
+    }
+    float o[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // running max / sum of rows r0 and r1
+
+    for (int kb = 0; kb < n_kb; ++kb) {
+      // 16-key groups of this block that hold at least one real key (T = 257: the last block has one of four)
+      const int ng = (kb == n_kb - 1) ? (T - kb * 64 + 15) >> 4 : 4;
       float s[8][4];
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
-      // S = Q K^T for 64 keys: B fragments straight from K rows (key-major, head dim contiguous)
+      // S = Q K^T for 64 keys: B fragments straight from K rows (key-major, head dim contiguous).
+      // k-step outermost: the eight 8-key accumulator tiles form eight independent mma chains.
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
+        uint32_t kf[4][4];
 #pragma unroll
         for (int np = 0; np < 4; ++np) {     // pairs of 8-key tiles
-          uint32_t b0, b1, b2, b3;
-          const int key = np * 16 + (lane & 7) + ((lane >> 4) << 3);
-          ldsm_x4(sKa + sw_off(key, ks * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
-          mma_16816(s[2 * np], qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], b0, b1);
-          mma_16816(s[2 * np + 1], qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], b2, b3);
+          if (np < ng) {
+            const int key = kb * 64 + np * 16 + (lane & 7) + ((lane >> 4) << 3);
+            ldsm_x4(sKa + sw_off(key, ks * 2 + ((lane >> 3) & 1)), kf[np][0], kf[np][1], kf[np][2], kf[np][3]);
+          }
+        }
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          if (np < ng) {
+            mma_16816(s[2 * np], qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], kf[np][0], kf[np][1]);
+            mma_16816(s[2 * np + 1], qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], kf[np][2], kf[np][3]);
+          }
         }
       }
       // mask keys >= T (last block only), block row maxima
-      float bm0 = -INFINITY, bm1 = -INFINITY;
       if (kb == n_kb - 1) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -295,6 +302,7 @@ k_attention(const __half* __restrict__ qkv, __half* __restrict__ out, int T, int
           if (key + 1 >= T) { s[i][1] = -INFINITY; s[i][3] = -INFINITY; }
         }
       }
+      float bm0 = -INFINITY, bm1 = -INFINITY;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         bm0 = fmaxf(bm0, fmaxf(s[i][0], s[i][1]));
@@ -303,14 +311,14 @@ k_attention(const __half* __restrict__ qkv, __half* __restrict__ out, int T, int
       bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
       bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
       const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);      // finite: every block holds at least one valid key
-      const float sc0 = exp2f((m0 - nm0) * kLog2e), sc1 = exp2f((m1 - nm1) * kLog2e);
+      const float sc0 = fast_exp2((m0 - nm0) * kLog2e), sc1 = fast_exp2((m1 - nm1) * kLog2e);
       m0 = nm0; m1 = nm1;
       const float mo0 = m0 * kLog2e, mo1 = m1 * kLog2e;
       float ps0 = 0.f, ps1 = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        s[i][0] = exp2f(fmaf(s[i][0], kLog2e, -mo0)); s[i][1] = exp2f(fmaf(s[i][1], kLog2e, -mo0));
-        s[i][2] = exp2f(fmaf(s[i][2], kLog2e, -mo1)); s[i][3] = exp2f(fmaf(s[i][3], kLog2e, -mo1));
+        s[i][0] = fast_exp2(fmaf(s[i][0], kLog2e, -mo0)); s[i][1] = fast_exp2(fmaf(s[i][1], kLog2e, -mo0));
+        s[i][2] = fast_exp2(fmaf(s[i][2], kLog2e, -mo1)); s[i][3] = fast_exp2(fmaf(s[i][3], kLog2e, -mo1));
         ps0 += s[i][0] + s[i][1];
         ps1 += s[i][2] + s[i][3];
       }
@@ -321,42 +329,45 @@ k_attention(const __half* __restrict__ qkv, __half* __restrict__ out, int T, int
       // O += P V : P from the S accumulators (fp16), V fragments via transposing ldmatrix
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {       // 16 keys per step
-        const uint32_t a0 = pack_half2(s[2 * ks][0], s[2 * ks][1]), a1 = pack_half2(s[2 * ks][2], s[2 * ks][3]);
-        const uint32_t a2 = pack_half2(s[2 * ks + 1][0], s[2 * ks + 1][1]), a3 = pack_half2(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+        if (ks < ng) {
+          const uint32_t a0 = pack_half2(s[2 * ks][0], s[2 * ks][1]), a1 = pack_half2(s[2 * ks][2], s[2 * ks][3]);
+          const uint32_t a2 = pack_half2(s[2 * ks + 1][0], s[2 * ks + 1][1]), a3 = pack_half2(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+          uint32_t vf[4][4];
+          const int key = kb * 64 + ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
 #pragma unroll
-        for (int np = 0; np < 4; ++np) {     // pairs of 8-wide head-dim tiles
-          uint32_t b0, b1, b2, b3;
-          const int key = ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
-          ldsm_x4_t(sVa + sw_off(key, np * 2 + (lane >> 4)), b0, b1, b2, b3);
-          mma_16816(o[2 * np], a0, a1, a2, a3, b0, b1);
-          mma_16816(o[2 * np + 1], a0, a1, a2, a3, b2, b3);
+          for (int np = 0; np < 4; ++np)       // pairs of 8-wide head-dim tiles
+            ldsm_x4_t(sVa + sw_off(key, np * 2 + (lane >> 4)), vf[np][0], vf[np][1], vf[np][2], vf[np][3]);
+#pragma unroll
+          for (int np = 0; np < 4; ++np) {
+            mma_16816(o[2 * np], a0, a1, a2, a3, vf[np][0], vf[np][1]);
+            mma_16816(o[2 * np + 1], a0, a1, a2, a3, vf[np][2], vf[np][3]);
+          }
         }
       }
     }
-    __syncthreads();     // everyone is done with this K/V buffer before the next prefetch overwrites it
-  }
-  if (!active) return;
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float i0 = 1.f / l0, i1 = 1.f / l1;
-  const int r0 = qt * kAttnQ + warp * 16 + (lane >> 2), r1 = r0 + 8;
-  __half* ob = out + (long long)b * T * D + head * kHd + 2 * (lane & 3);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    __half* ob = out + (long long)b * T * D + head * kHd + 2 * (lane & 3);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (r0 < T) *reinterpret_cast<uint32_t*>(ob + (long long)r0 * D + i * 8) = pack_half2(o[i][0] * i0, o[i][1] * i0);
-    if (r1 < T) *reinterpret_cast<uint32_t*>(ob + (long long)r1 * D + i * 8) = pack_half2(o[i][2] * i1, o[i][3] * i1);
+    for (int i = 0; i < 8; ++i) {
+      if (r0 < T) *reinterpret_cast<uint32_t*>(ob + (long long)r0 * D + i * 8) = pack_half2(o[i][0] * i0, o[i][1] * i0);
+      if (r1 < T) *reinterpret_cast<uint32_t*>(ob + (long long)r1 * D + i * 8) = pack_half2(o[i][2] * i1, o[i][3] * i1);
+    }
   }
 }
 
 int attention_f16(const __half* qkv, __half* out, int batch, int T, int heads, cudaStream_t stream) {
   if (batch <= 0 || T <= 0 || heads <= 0) return BSCNAV_EINVAL;
-  static bool attr_set = false;
-  if (!attr_set) {
-    BSC_CUDA(cudaFuncSetAttribute(k_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    attr_set = true;
+  const int t_pad = (T + 15) / 16 * 16;      // only whole 16-key groups are ever read (see `ng` in the kernel)
+  const int smem = 2 * t_pad * 128;
+  if (smem > 200 * 1024) return BSCNAV_EINVAL;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    BSC_CUDA(cudaFuncSetAttribute(k_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
   }
-  BSC_LAUNCH(k_attention, dim3((unsigned)((T + kAttnQ - 1) / kAttnQ), (unsigned)heads, (unsigned)batch), kAttnThreads, kAttnSmem,
-             stream, qkv, out, T, heads);
+  BSC_LAUNCH(k_attention, dim3((unsigned)heads, (unsigned)batch), kAttnThreads, smem, stream, qkv, out, T, heads, t_pad);
   return BSCNAV_OK;
 }
 

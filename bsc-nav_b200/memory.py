@@ -84,6 +84,7 @@ class VoxelTokenMemory:
         self._store = None
         self._init_cache()
         self._pinned = {}
+        self._copy_stream = None
 
     # ------------------------------------------------------------------ state
     def _init_cache(self):
@@ -162,28 +163,65 @@ class VoxelTokenMemory:
             self._pinned[name] = buf
         return buf
 
-    def fuse_frames(self, rgb, depth, poses, sample_idx=None):
-        """Batched build step: rgb (B,H,W,3|4) uint8, depth (B,H,W) float32, poses (B,7) -- host arrays (copied through
-        pinned staging buffers) or device tensors.  Everything after the copy runs on the device, no host sync."""
-        poses = np.asarray(poses, dtype=np.float64).reshape(-1, 7)
-        tfs = self._chain.batch(poses)
+    def _inputs_to_device(self, rgb, depth):
+        """Host frames -> device through a side copy stream and two device buffers, so the copy of batch i+1 overlaps
+        the kernels of batch i.  Pinned torch tensors are copied directly; numpy arrays go through pinned staging."""
+        if torch.is_tensor(rgb) and rgb.is_cuda and torch.is_tensor(depth) and depth.is_cuda:
+            return rgb.contiguous(), depth.contiguous(), None
         if not torch.is_tensor(rgb):
             rgb = np.asarray(rgb)
             st = self._staging("rgb", rgb.shape, torch.uint8)
             st.numpy()[...] = rgb
-            rgb = st.to(self.device, non_blocking=True)
+            rgb = st
         if not torch.is_tensor(depth):
             depth = np.asarray(depth, dtype=np.float32)
             st = self._staging("depth", depth.shape, torch.float32)
             st.numpy()[...] = depth
-            depth = st.to(self.device, non_blocking=True)
-        rgb = rgb.to(self.device, non_blocking=True).contiguous()          # pinned host tensors copy asynchronously
-        depth = depth.to(self.device, non_blocking=True).contiguous()
+            depth = st
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._in_bufs = [None, None]
+            self._in_free = [None, None]
+            self._in_slot = 0
+        slot = self._in_slot = self._in_slot ^ 1
+        bufs = self._in_bufs[slot]
+        if bufs is None or bufs[0].shape != rgb.shape or bufs[1].shape != depth.shape:
+            bufs = self._in_bufs[slot] = (torch.empty(rgb.shape, dtype=torch.uint8, device=self.device),
+                                          torch.empty(depth.shape, dtype=torch.float32, device=self.device))
+            self._in_free[slot] = None
+        cur = torch.cuda.current_stream()
+        if self._in_free[slot] is not None:
+            self._copy_stream.wait_event(self._in_free[slot])     # kernels that read this buffer two batches ago are done
+        with torch.cuda.stream(self._copy_stream):
+            bufs[0].copy_(rgb, non_blocking=True)
+            bufs[1].copy_(depth, non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(self._copy_stream)
+        cur.wait_event(copied)
+        return bufs[0], bufs[1], slot
+
+    def fuse_frames(self, rgb, depth, poses, sample_idx=None):
+        """Batched build step: rgb (B,H,W,3|4) uint8, depth (B,H,W) float32, poses (B,7) -- pinned host tensors, numpy
+        arrays or device tensors.  Returns without synchronising: copies run on a side stream, kernels on the current one."""
+        poses = np.asarray(poses, dtype=np.float64).reshape(-1, 7)
+        tfs = self._chain.batch(poses)
+        rgb, depth, slot = self._inputs_to_device(rgb, depth)
         if sample_idx is None:
             sample_idx = self._sample_indices(rgb.shape[0])
         tokens = self._tokens_of(rgb)
         self._store.fuse(depth, tfs, tokens, sample_idx=sample_idx)
+        if slot is not None:
+            ev = torch.cuda.Event()
+            ev.record()
+            self._in_free[slot] = ev
         self.tf = self._chain.tf
+
+    def max_id_async(self):
+        """Non-blocking read of max_id: enqueues the device->host copy, returns a handle for max_id_wait()."""
+        return self._store.count_async()
+
+    def max_id_wait(self, handle) -> int:
+        return self._store.count_wait(handle)
 
     def obs2voxeltoken(self, obs, pose):
         """memory_2.py:842-903, one frame."""

@@ -77,6 +77,12 @@ class SpatialStore:
         self._scratch = None
         self._qscratch = None
         self.next_ordinal = 0
+        # small pinned rings so the per-batch parameters (poses, ordinals) and result reads never block the host
+        self._ring = [None] * 8
+        self._ring_ev = [None] * 8
+        self._ring_i = 0
+        self._cnt_ring = torch.zeros(4096, 2, dtype=torch.int32).pin_memory()
+        self._cnt_i = 0
         self.reset()
 
     # ------------------------------------------------------------------ build
@@ -98,15 +104,13 @@ class SpatialStore:
         assert depth.dtype == torch.float32 and depth.is_cuda and depth.is_contiguous() and depth.shape[1:] == (g.height, g.width)
         assert tokens.dtype == torch.float32 and tokens.is_contiguous() and tokens.shape == (B, g.n_patch_h * g.n_patch_w, g.dim)
         n_points = g.height * g.width if sample_idx is None else sample_idx.shape[1]
-        if not torch.is_tensor(poses):
-            poses = torch.from_numpy(np.ascontiguousarray(np.asarray(poses, dtype=np.float64).reshape(B, 16))).to(self.device, non_blocking=True)
-        assert poses.dtype == torch.float64 and poses.numel() == B * 16
         if ord_base is None:
             if self.next_ordinal + B * n_points >= 2 ** 32:
                 raise _lib.BscnavError("ordinal range exceeded (2^32 points per store)")
             ord_base = self.next_ordinal + np.arange(B, dtype=np.int64) * n_points
             self.next_ordinal += B * n_points
-        ob = torch.from_numpy(np.asarray(ord_base, dtype=np.int64).astype(np.uint32).view(np.int32)).to(self.device, non_blocking=True)
+        # poses (B x 16 f64) and ordinals (B x u32, padded to 8 bytes) travel in one pinned staging block
+        poses, ob = self._params_to_device(poses, ord_base, B)
         nbytes = _lib.check(self.lib.bscnav_fuse_scratch_bytes(B, n_points), "fuse_scratch_bytes")
         scratch = self._scratch_for(nbytes)
         rec = torch.empty(B * n_points, 4, dtype=torch.int32, device=self.device) if want_records else None
@@ -116,6 +120,42 @@ class SpatialStore:
                                                _lib.ptr(sample_idx), B, n_points, _lib.ptr(tokens), _lib.ptr(scratch), nbytes,
                                                _lib.ptr(rec), _lib.stream_ptr()), "fuse_frames")
         return rec
+
+    def _params_to_device(self, poses, ord_base, B):
+        """One pinned staging block per batch: [poses as B*16 float64 | B uint32 ordinals] -> (poses, ordinals) on the device."""
+        i = self._ring_i = (self._ring_i + 1) % len(self._ring)
+        if self._ring_ev[i] is not None:
+            self._ring_ev[i].synchronize()          # only blocks if the device is a full ring behind
+        buf = self._ring[i]
+        if buf is None or buf.numel() < B * 33:
+            buf = self._ring[i] = torch.empty(max(B, 64) * 33, dtype=torch.int32).pin_memory()
+        host = buf[: B * 33].numpy()
+        pose_on_device = torch.is_tensor(poses) and poses.is_cuda
+        if not pose_on_device:
+            host[: B * 32].view(np.float64)[:] = np.asarray(poses, dtype=np.float64).reshape(-1)
+        host[B * 32:].view(np.uint32)[:] = np.asarray(ord_base, dtype=np.int64).astype(np.uint32)
+        dev = buf[: B * 33].to(self.device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._ring_ev[i] = ev
+        pd = poses.reshape(-1).to(torch.float64).contiguous() if pose_on_device else dev[: B * 32].view(torch.float64)
+        return pd, dev[B * 32:]
+
+    def count_async(self):
+        """Enqueue a device->host read of (slots in use, overflow flag) into pinned memory; returns a handle for count_wait."""
+        i = self._cnt_i = (self._cnt_i + 1) % self._cnt_ring.shape[0]
+        self._cnt_ring[i].copy_(self.counters[:2], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return i, ev
+
+    def count_wait(self, handle) -> int:
+        i, ev = handle
+        ev.synchronize()
+        c = self._cnt_ring[i].tolist()
+        if c[1]:
+            raise _lib.BscnavError(f"slot capacity {self.g.max_slots} exceeded (reference: IndexError at memory_2.py:891)")
+        return int(c[0])
 
     def count(self) -> int:
         """Slots in use (max_id, memory_2.py:894); synchronises.  Raises if a batch overflowed the slot capacity."""

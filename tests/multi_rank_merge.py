@@ -1,0 +1,45 @@
+"""torchrun worker (2 ranks, NCCL): frames of one scene sharded over ranks -> export / all-gather / merge -> every rank's
+store equals the single-process joint build.  Launched by tests/test_gpu_merge.py::test_two_rank_nccl_merge."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import memory_port as mp  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = importlib.import_module("bsc-nav_b200")
+    dmod = importlib.import_module("bsc-nav_b200.dist")
+    H, W, GS, D, n = 96, 128, 64, 128, 9
+    chain = pkg.PoseChain([0, 0, -1], [-1, 0, 0], [0, 1, 0], [1, 0, 0, 0, -1, 0, 0, 0, -1], 1.5)
+    frames = [mp.synthetic_frame(f, H, W, n_frames=12) for f in range(n)]
+    depth = torch.from_numpy(np.stack([f[1] for f in frames])).cuda()
+    poses = np.stack([chain(f[2]) for f in frames])
+    tokens = torch.randn(n, 256, D, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    cfg = pkg.StoreConfig(height=H, width=W, grid_size=GS, floor_height=-2.0, map_height=2.0, token_dim=D, cache_size=3, bev=False)
+    ob = np.arange(n, dtype=np.int64) * H * W
+    joint = pkg.SpatialStore(cfg)
+    joint.fuse(depth, poses, tokens, ord_base=ob)
+    mine = list(dmod.shard_frames(n, rank, world))
+    st = pkg.SpatialStore(cfg)
+    st.fuse(depth[mine].contiguous(), poses[mine], tokens[mine].contiguous(), ord_base=ob[mine])
+    counts = dmod.merge_scene_across_ranks(st, int(ob[mine[0]]), int(ob[mine[-1]]) + H * W, st.g.max_slots * 3)
+    canon = lambda s: {k: [(float(t[0]), int(t[1]), int(t[2]), t[3].tobytes()) for t in v] for k, v in s.snapshot().items()}
+    assert canon(st) == canon(joint), f"rank {rank}: merged store differs from the joint build"
+    dist.barrier()
+    if rank == 0:
+        print("MERGE_OK", counts)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,96 @@
+"""GPU: the multi-GPU merge path (export_delta -> all-gather -> merge_delta).  Single-GPU tests simulate the rank
+shards with separate stores; the 2-rank NCCL test runs when the box has two GPUs."""
+import importlib
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import memory_port as mp
+
+pytestmark = pytest.mark.gpu
+
+H, W, GS, D = 96, 128, 64, 128
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _inputs(pkg, n_frames):
+    chain = pkg.PoseChain([0, 0, -1], [-1, 0, 0], [0, 1, 0], [1, 0, 0, 0, -1, 0, 0, 0, -1], 1.5)
+    frames = [mp.synthetic_frame(f, H, W, n_frames=12) for f in range(n_frames)]
+    depth = torch.from_numpy(np.stack([f[1] for f in frames])).cuda()
+    poses = np.stack([chain(f[2]) for f in frames])
+    tokens = torch.randn(n_frames, 256, D, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    return depth, poses, tokens
+
+
+def _canon(st):
+    """Order-independent view of a store: {cell key: [(r2, ordinal, h, feature bytes)]}."""
+    return {k: [(float(t[0]), int(t[1]), int(t[2]), t[3].tobytes()) for t in v] for k, v in st.snapshot().items()}
+
+
+@pytest.mark.parametrize("cache,bev", [(1, True), (4, False), (10, False)])
+def test_merge_equals_joint_build(pkg, cache, bev):
+    n = 8
+    depth, poses, tokens = _inputs(pkg, n)
+    cfg = pkg.StoreConfig(height=H, width=W, grid_size=GS, floor_height=-2.0, map_height=2.0, token_dim=D, cache_size=cache, bev=bev)
+    ob = np.arange(n, dtype=np.int64) * H * W
+    joint = pkg.SpatialStore(cfg)
+    joint.fuse(depth, poses, tokens, ord_base=ob)
+    shards = [range(0, 3), range(3, 8)]                  # uneven "ranks"
+    stores = []
+    for sh in shards:
+        s = pkg.SpatialStore(cfg)
+        idx = list(sh)
+        s.fuse(depth[idx].contiguous(), poses[idx], tokens[idx].contiguous(), ord_base=ob[idx])
+        stores.append(s)
+    deltas = []
+    for s, sh in zip(stores, shards):
+        d_cell, d_key, d_h, d_feat, n_dev = s.export_delta(int(ob[sh[0]]), int(ob[sh[-1]]) + H * W, max_out=s.g.max_slots * cache)
+        k = int(n_dev.item())
+        assert k == sum(len(v) for v in s.snapshot().values())
+        deltas.append((d_cell[:k].contiguous(), d_key[:k].contiguous(), d_h[:k].contiguous(), d_feat[:k].contiguous()))
+    stores[0].merge_delta(*deltas[1])
+    stores[1].merge_delta(*deltas[0])
+    want = _canon(joint)
+    assert _canon(stores[0]) == want
+    assert _canon(stores[1]) == want
+    # merging a delta twice changes nothing (idempotent)
+    stores[0].merge_delta(*deltas[1])
+    assert _canon(stores[0]) == want
+
+
+def test_query_after_merge_matches_joint(pkg):
+    n = 6
+    depth, poses, tokens = _inputs(pkg, n)
+    cfg = pkg.StoreConfig(height=H, width=W, grid_size=GS, floor_height=-2.0, map_height=2.0, token_dim=D, cache_size=2, bev=False)
+    ob = np.arange(n, dtype=np.int64) * H * W
+    joint = pkg.SpatialStore(cfg)
+    joint.fuse(depth, poses, tokens, ord_base=ob)
+    a, b = pkg.SpatialStore(cfg), pkg.SpatialStore(cfg)
+    a.fuse(depth[:3].contiguous(), poses[:3], tokens[:3].contiguous(), ord_base=ob[:3])
+    b.fuse(depth[3:].contiguous(), poses[3:], tokens[3:].contiguous(), ord_base=ob[3:])
+    d_cell, d_key, d_h, d_feat, n_dev = b.export_delta(int(ob[3]), int(ob[-1]) + H * W, max_out=b.g.max_slots * 2)
+    k = int(n_dev.item())
+    a.merge_delta(d_cell[:k].contiguous(), d_key[:k].contiguous(), d_h[:k].contiguous(), d_feat[:k].contiguous())
+    q = tokens[2, 77:79].contiguous()
+    s1, p1, c1 = joint.query(q, k=50)
+    s2, p2, c2 = a.query(q, k=50)
+    assert torch.equal(c1, c2) and torch.equal(p1, p2) and torch.equal(s1, s2)
+
+
+def test_two_rank_nccl_merge():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "multi_rank_merge.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "MERGE_OK" in out.stdout

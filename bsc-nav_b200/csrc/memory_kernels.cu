@@ -244,6 +244,7 @@ k_select(const uint4* __restrict__ rec, long long total, const int32_t* __restri
     if (key < ks[C - 1]) {
       for (int j = 0; j < C; ++j) {
         const unsigned long long old = atomicMin(&ks[j], key);
+        if (old == key) break;                 // already stored (the same point offered again): idempotent
         if (old > key) {
           key = old;
           if (key == BSCNAV_KEY_EMPTY) break;
@@ -279,7 +280,9 @@ k_commit(const uint4* __restrict__ rec, long long total, const int32_t* __restri
         if (win) {
           // claim a physical row whose current token is no longer among the kept keys (or was never used)
           unsigned long long* rk = row_key + (long long)slot * C;
-          for (int rr = 0; rr < C && dst_row < 0; ++rr) {
+          for (int rr = 0; rr < C; ++rr)       // the token may already own a row (same point offered again)
+            if (rk[rr] == key) win = false;
+          for (int rr = 0; rr < C && win && dst_row < 0; ++rr) {
             const unsigned long long cur = rk[rr];
             bool kept = false;
             for (int j = 0; j < C; ++j) kept |= (ks[j] == cur);

@@ -28,8 +28,14 @@ def _inputs(pkg, n_frames):
 
 
 def _canon(st):
-    """Order-independent view of a store: {cell key: [(r2, ordinal, h, feature bytes)]}."""
-    return {k: [(float(t[0]), int(t[1]), int(t[2]), t[3].tobytes()) for t in v] for k, v in st.snapshot().items()}
+    """Order-independent view of a store: {cell key: [(r2, ordinal, h, checksum of the feature row)]}."""
+    return {k: [(float(t[0]), int(t[1]), int(t[2]), float(np.dot(t[3].astype(np.float64), np.arange(1, t[3].size + 1))))
+                for t in v] for k, v in st.snapshot().items()}
+
+
+def _diff(a, b):
+    out = [f"{k}: {a.get(k)} != {b.get(k)}" for k in sorted(set(a) | set(b)) if a.get(k) != b.get(k)]
+    return f"{len(out)} differing cells; first: " + " | ".join(out[:3])
 
 
 @pytest.mark.parametrize("cache,bev", [(1, True), (4, False), (10, False)])
@@ -56,11 +62,13 @@ def test_merge_equals_joint_build(pkg, cache, bev):
     stores[0].merge_delta(*deltas[1])
     stores[1].merge_delta(*deltas[0])
     want = _canon(joint)
-    assert _canon(stores[0]) == want
-    assert _canon(stores[1]) == want
+    got0, got1 = _canon(stores[0]), _canon(stores[1])
+    assert got0 == want, _diff(got0, want)
+    assert got1 == want, _diff(got1, want)
     # merging a delta twice changes nothing (idempotent)
     stores[0].merge_delta(*deltas[1])
-    assert _canon(stores[0]) == want
+    got0 = _canon(stores[0])
+    assert got0 == want, _diff(got0, want)
 
 
 def test_query_after_merge_matches_joint(pkg):

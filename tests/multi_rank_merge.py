@@ -25,14 +25,15 @@ def main():
     depth = torch.from_numpy(np.stack([f[1] for f in frames])).cuda()
     poses = np.stack([chain(f[2]) for f in frames])
     tokens = torch.randn(n, 256, D, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
-    cfg = pkg.StoreConfig(height=H, width=W, grid_size=GS, floor_height=-2.0, map_height=2.0, token_dim=D, cache_size=3, bev=False)
+    cfg = pkg.StoreConfig(height=H, width=W, grid_size=GS, floor_height=-2.0, map_height=2.0, token_dim=D, cache_size=3, bev=False,
+                          max_slots=16384)
     ob = np.arange(n, dtype=np.int64) * H * W
     joint = pkg.SpatialStore(cfg)
     joint.fuse(depth, poses, tokens, ord_base=ob)
     mine = list(dmod.shard_frames(n, rank, world))
     st = pkg.SpatialStore(cfg)
     st.fuse(depth[mine].contiguous(), poses[mine], tokens[mine].contiguous(), ord_base=ob[mine])
-    counts = dmod.merge_scene_across_ranks(st, int(ob[mine[0]]), int(ob[mine[-1]]) + H * W, st.g.max_slots * 3)
+    counts = dmod.merge_scene_across_ranks(st, int(ob[mine[0]]), int(ob[mine[-1]]) + H * W, st.g.max_slots * 3)   # capacity of the export buffers, rows
     canon = lambda s: {k: [(float(t[0]), int(t[1]), int(t[2]), t[3].tobytes()) for t in v] for k, v in s.snapshot().items()}
     assert canon(st) == canon(joint), f"rank {rank}: merged store differs from the joint build"
     dist.barrier()

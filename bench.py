@@ -144,6 +144,40 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ---------------------------------------------------------------------------------------------- query leg (BASELINE configs[2])
+def query_leg(store, dev, peak_gbs):
+    """Goal queries over a fully occupied 512x512 grid (262 144 stored tokens, D=1024, K=100): per-query latency (Q=1)
+    and batched throughput (8 queries per pass).  HBM-bound: algorithmic bytes = N_tok*(D*4+4) per pass."""
+    g = store.g
+    n = g.gs * g.gs
+    gen = torch.Generator(device=dev).manual_seed(7)
+    store.feat[:n].normal_(generator=gen)
+    store.slot_cell[:n] = torch.arange(n, dtype=torch.int32, device=dev)
+    store.occupied_ids[:n] = torch.arange(n, dtype=torch.int32, device=dev)
+    store.row_key[:n].zero_()
+    store.slot_keys[:n].zero_()
+    store.tok_h[:n].fill_(100)
+    store.norm2[:n] = (store.feat[:n] ** 2).sum(1)
+    store.counters[0] = n
+    q = torch.randn(64, g.dim, device=dev, generator=torch.Generator(device=dev).manual_seed(11))
+    out = {}
+    for name, Q, reps in (("single", 1, 40), ("batch8", 8, 20)):
+        for _ in range(3):
+            store.query(q[:Q], k=100)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for r in range(reps):
+            store.query(q[(r * Q) % 56:(r * Q) % 56 + Q], k=100)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        gbs = n * (g.dim * 4 + 4) / (ms / 1e3) / 1e9
+        out[name] = {"queries_per_s": Q / (ms / 1e3), "ms_per_pass": ms, "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peak_gbs}
+    out["workload"] = "BASELINE configs[2] shape: 262144 stored tokens (512x512 grid fully occupied, C=1, D=1024), K=100, cosine + top-K"
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch.distributed as dist
@@ -262,6 +296,8 @@ def run_ours(args):
            "h2d_bytes_per_step": B * (H * W * 4 + H * W * 4 + 16 * 8 + 4), "d2h_bytes_per_step": 8,
            "api": "VoxelTokenMemory.fuse_frames + max_id_async (copies overlap the previous batch)", "slots_after": counts[-1]}
 
+    query = query_leg(store, dev, peak_gbs) if rank == 0 else None
+
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 operands / f32 accumulate (ViT), f64 (cell index), f32 (tokens)", "data": "synthetic",
@@ -269,7 +305,7 @@ def run_ours(args):
                        "l2": f"inputs larger than L2: {B * 2 * H * W * 4 / 1e6:.0f} MB of frames per step, pool of {P} frames",
                        "sharding": "one scene per rank, no data-path collective" if world > 1 else "single GPU"},
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "vit_tflops": cfg.flops_per_frame() * B * K / (ms / 1e3) / 1e12}
+            "vit_tflops": cfg.flops_per_frame() * B * K / (ms / 1e3) / 1e12, "query": query}
     if world == 1:
         v, detail = cpu_reference_rate(1, args.ref_points, os.cpu_count() or 1)
         line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": detail}

@@ -547,48 +547,41 @@ k_topk_decode(const bscnav_geom_t g, const unsigned long long* __restrict__ keys
   const int qi = blockIdx.x;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int D = g.dim, C = g.cache;
-  __shared__ int cnt;
-  if (threadIdx.x == 0) cnt = 0;
-  __syncthreads();
-  int local = 0;
-  for (int i = wib; i < k; i += kThreads / 32) {
-    const unsigned long long key = keys[(long long)qi * key_stride + i];
-    float sim = -INFINITY;
-    int row = -1, col = -1, h = -1;
-    if (key != BSCNAV_KEY_EMPTY) {
-      sim = from_orderable(~(uint32_t)(key >> 32));
-      const int cell = (int)(uint32_t)key;
-      if (g.levels == 1) {
-        row = cell / g.gs; col = cell - row * g.gs;
-        const int slot = occupied[cell];
-        float best = -INFINITY;
-        const float* qv = q + (long long)(q0 + qi) * D;
-        float qn = 0.f;
-        for (int c = lane; c < D; c += 32) qn = fmaf(qv[c], qv[c], qn);
-        qn = warp_sum(qn);
-        for (int j = 0; j < C; ++j) {
-          const long long r = (long long)slot * C + j;
-          if (row_key[r] == BSCNAV_KEY_EMPTY) continue;
-          float acc = 0.f;
-          for (int c = lane; c < D; c += 32) acc = fmaf(feat[r * D + c], qv[c], acc);
-          acc = warp_sum(acc);
-          const float s = acc / sqrtf(fmaxf(qn * norm2[r], 1e-16f));
-          if (s > best) { best = s; h = tok_h[r]; }
-        }
-      } else {
-        h = cell % g.levels; const int rc = cell / g.levels; row = rc / g.gs; col = rc - row * g.gs;
+  const int i = blockIdx.y * (kThreads / 32) + wib;        // one warp per winner
+  if (i >= k) return;
+  const unsigned long long key = keys[(long long)qi * key_stride + i];
+  float sim = -INFINITY;
+  int row = -1, col = -1, h = -1;
+  if (key != BSCNAV_KEY_EMPTY) {
+    sim = from_orderable(~(uint32_t)(key >> 32));
+    const int cell = (int)(uint32_t)key;
+    if (g.levels == 1) {
+      row = cell / g.gs; col = cell - row * g.gs;
+      const int slot = occupied[cell];
+      float best = -INFINITY;
+      const float* qv = q + (long long)(q0 + qi) * D;
+      float qn = 0.f;
+      for (int c = lane; c < D; c += 32) qn = fmaf(qv[c], qv[c], qn);
+      qn = warp_sum(qn);
+      for (int j = 0; j < C; ++j) {
+        const long long r = (long long)slot * C + j;
+        if (row_key[r] == BSCNAV_KEY_EMPTY) continue;
+        float acc = 0.f;
+        for (int c = lane; c < D; c += 32) acc = fmaf(feat[r * D + c], qv[c], acc);
+        acc = warp_sum(acc);
+        const float s = acc / sqrtf(fmaxf(qn * norm2[r], 1e-16f));
+        if (s > best) { best = s; h = tok_h[r]; }
       }
-      ++local;
+    } else {
+      h = cell % g.levels; const int rc = cell / g.levels; row = rc / g.gs; col = rc - row * g.gs;
     }
-    if (lane == 0) {
-      out_sim[(long long)qi * k + i] = sim;
-      int32_t* p = out_pos + ((long long)qi * k + i) * 3;
-      p[0] = row; p[1] = col; p[2] = h;
-    }
+    if (lane == 0) atomicAdd(&out_count[qi], 1);
   }
-  if (lane == 0 && local) atomicAdd(&cnt, local);
-  __syncthreads();
-  if (threadIdx.x == 0) out_count[qi] = cnt;
+  if (lane == 0) {
+    out_sim[(long long)qi * k + i] = sim;
+    int32_t* p = out_pos + ((long long)qi * k + i) * 3;
+    p[0] = row; p[1] = col; p[2] = h;
+  }
 }
 
 static int num_sms() {
@@ -766,7 +759,7 @@ int bscnav_query_topk(const bscnav_geom_t* g, const bscnav_store_t* st, const fl
   unsigned long long* bufA = reinterpret_cast<unsigned long long*>(base + align_up(lvl0 * 8, 256));
   unsigned long long* bufB = reinterpret_cast<unsigned long long*>(base + align_up(lvl0 * 8, 256) + align_up(cand * 8, 256));
   const int D = g->dim;
-  const int grid = num_sms() * 4;
+  const int grid = num_sms() * 3;      // 3 resident blocks of 256 threads per SM at ~76 registers: one full wave, grid-stride
   for (int q0 = 0; q0 < n_query; q0 += kQ) {
     const int nq = (n_query - q0) < kQ ? (n_query - q0) : kQ;
     const size_t smem = (size_t)nq * D * sizeof(float);
@@ -800,7 +793,8 @@ int bscnav_query_topk(const bscnav_geom_t* g, const bscnav_store_t* st, const fl
       unsigned long long* t = in; in = out; out = t;
       if (n_chunks == 1) break;
     }
-    BSC_LAUNCH(k_topk_decode, nq, kThreads, 0, stream, *g, in, in_stride, k, st->occupied_ids,
+    BSC_CUDA(cudaMemsetAsync(out_count + q0, 0, sizeof(int32_t) * nq, stream));
+    BSC_LAUNCH(k_topk_decode, dim3((unsigned)nq, (unsigned)((k + kThreads / 32 - 1) / (kThreads / 32))), kThreads, 0, stream, *g, in, in_stride, k, st->occupied_ids,
                reinterpret_cast<const unsigned long long*>(st->row_key), st->tok_h, st->feat, st->norm2, q, q0,
                out_sim + (long long)q0 * k, out_pos + (long long)q0 * k * 3, out_count + q0);
   }

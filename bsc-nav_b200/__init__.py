@@ -11,7 +11,7 @@ def __getattr__(name):
     import importlib
     lazy = {
         "SpatialStore": "store", "StoreConfig": "store", "ViTEngine": "vit", "pack_weights": "vit", "gaussian_pool": "vit",
-        "gemm_f16": "vit", "VoxelTokenMemory": "memory", "Memory": "memory", "GESObjectNavRobot": "agent",
+        "gemm_f16": "vit", "attention_f16": "vit", "VoxelTokenMemory": "memory", "Memory": "memory", "GESObjectNavRobot": "agent",
         "LocalizeAgent": "agent", "PoseChain": "geometry",
     }
     if name in lazy:

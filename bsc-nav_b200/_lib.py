@@ -51,6 +51,7 @@ _SIGS = {
     "bscnav_last_error": (C.c_char_p, []),
     "bscnav_launch_count": (C.c_int64, []),
     "bscnav_store_reset": (C.c_int, [C.POINTER(Geom), C.POINTER(Store), _P]),
+    "bscnav_store_row_norms": (C.c_int, [C.POINTER(Geom), C.POINTER(Store), C.c_int64, _P]),
     "bscnav_fuse_scratch_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "bscnav_fuse_frames": (C.c_int, [C.POINTER(Geom), C.POINTER(Store), _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P,
                                      C.c_int64, _P, _P]),
@@ -71,6 +72,7 @@ _SIGS = {
     "bscnav_vit_forward_frames": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
     "bscnav_vit_forward_images": (C.c_int, [_P, _P, C.c_int32, _P, _P]),
     "bscnav_gaussian_pool": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "bscnav_attention_f16": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "bscnav_gemm_f16": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
 }
 EXPORTS = tuple(_SIGS)

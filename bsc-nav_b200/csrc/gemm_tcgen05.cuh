@@ -41,6 +41,11 @@ int make_store_map(CUtensorMap* map, const void* ptr, long long rows, long long 
 // 2-D K-major fp16 operand [rows, K] -> tensor map with box {64, box_rows}, 128-byte swizzle
 int make_operand_map(CUtensorMap* map, const void* ptr, long long rows, long long K, int box_rows);
 
+// tcgen05 attention (attention_tc.cu): map128 / map16 = make_operand_map over the qkv tensor with 128- and 16-row boxes
+bool attention_tc_supported(int T);
+int attention_tc_launch(const CUtensorMap* map128, const CUtensorMap* map16, __half* out, int batch, int T, int heads,
+                        cudaStream_t stream);
+
 int gemm_block_n(int N);   // 256 when N % 256 == 0 (BN=128 is shared-memory-bandwidth bound at cta_group::1), else 128
 
 }  // namespace bscnav

@@ -313,6 +313,24 @@ k_commit(const uint4* __restrict__ rec, long long total, const int32_t* __restri
   }
 }
 
+// squared norms of rows [0, n_rows) with the association k_commit uses (lane-strided fma, shuffle tree), so a store
+// filled from disk scores bit-identically to the store that was saved
+__global__ void __launch_bounds__(kThreads)
+k_row_norms(const float* __restrict__ feat, float* __restrict__ norm2, long long n_rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * (kThreads / 32);
+  for (long long row = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); row < n_rows; row += warps) {
+    const float4* s = reinterpret_cast<const float4*>(feat + row * D);
+    float acc = 0.f;
+    for (int c = lane; c < (D >> 2); c += 32) {
+      const float4 v = ld_stream_f4(s + c);
+      acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) norm2[row] = acc;
+  }
+}
+
 __global__ void k_fill_u32(uint32_t* p, long long n, uint32_t v) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -665,6 +683,16 @@ int bscnav_store_reset(const bscnav_geom_t* g, const bscnav_store_t* st, void* s
   BSC_LAUNCH(k_fill_u64, grid, 256, 0, stream, reinterpret_cast<unsigned long long*>(st->slot_keys), rows, BSCNAV_KEY_EMPTY);
   BSC_LAUNCH(k_fill_u64, grid, 256, 0, stream, reinterpret_cast<unsigned long long*>(st->row_key), rows, BSCNAV_KEY_EMPTY);
   BSC_CUDA(cudaMemsetAsync(st->counters, 0, 8 * sizeof(int32_t), stream));
+  return BSCNAV_OK;
+}
+
+int bscnav_store_row_norms(const bscnav_geom_t* g, const bscnav_store_t* st, int64_t n_rows, void* stream_) {
+  if (int e = check_geom(g)) return e;
+  if (!st || !st->feat || !st->norm2 || n_rows < 0 || n_rows > (int64_t)g->max_slots * g->cache) return BSCNAV_EINVAL;
+  if (n_rows == 0) return BSCNAV_OK;
+  const long long blocks = (n_rows + kThreads / 32 - 1) / (kThreads / 32);
+  const int grid = (int)(blocks < (long long)num_sms() * 8 ? blocks : (long long)num_sms() * 8);
+  BSC_LAUNCH(k_row_norms, grid, kThreads, 0, (cudaStream_t)stream_, st->feat, st->norm2, (long long)n_rows, g->dim);
   return BSCNAV_OK;
 }
 

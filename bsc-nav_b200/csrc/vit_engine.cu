@@ -4,6 +4,7 @@
 //               fc1_w [M, D], fc2_w [D, M] (LayerScale folded) }
 //   float blob: patch_b [D] | cls_pos [D] | reg [n_reg, D] | pos [Np, D] | ln_pre_w, ln_pre_b [D] (if ln_pre) |
 //               per layer { ln1_w, ln1_b [D], qkv_b [3D], proj_b [D], ln2_w, ln2_b [D], fc1_b [M], fc2_b [D] } | ln_post_w, ln_post_b [D]
+#include <cstdlib>
 #include <vector>
 #include "gemm_tcgen05.cuh"
 #include "vit_kernels.cuh"
@@ -84,6 +85,8 @@ struct VitEngine {
   CUtensorMap map_a0, map_y, map_ao, map_h;          // activation operands
   CUtensorMap map_patch_w;
   CUtensorMap out_qkv, out_h, out_x;                 // store maps of the GEMM outputs
+  CUtensorMap qkv128, qkv16;                         // qkv tensor as attention operand (128- and 16-row boxes)
+  bool attn_tc = false;
   CUtensorMap map_qkv[64], map_proj[64], map_fc1[64], map_fc2[64];
   bool a0_cleared = false;
   // optional per-kernel timing (bench.py's roofline leg): CUDA events around every launch on the caller's stream
@@ -130,7 +133,8 @@ static int vit_run(VitEngine* e, int batch, float* out_tokens, cudaStream_t stre
     { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * 3.0 * D * D);
       if (int r = gemm_f16_launch(&e->map_y, &e->map_qkv[i], &e->out_qkv, rows, 3 * D, D, e1, stream)) return r; }
     { ProfScope ps(e, stream, kCatAttention, 4.0 * batch * (double)T * T * D);
-      if (int r = attention_f16(e->ws.qkv, e->ws.ao, batch, T, c.heads, stream)) return r; }
+      if (e->attn_tc) { if (int r = attention_tc_launch(&e->qkv128, &e->qkv16, e->ws.ao, batch, T, c.heads, stream)) return r; }
+      else if (int r = attention_f16(e->ws.qkv, e->ws.ao, batch, T, c.heads, stream)) return r; }
     GemmEpilogue e2{};
     e2.out = e->ws.x; e2.bias = wf + o.proj_b; e2.ld_out = D; e2.mode = kOutResidual;
     { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * (double)D * D);
@@ -194,6 +198,9 @@ int bscnav_vit_create(const bscnav_vit_cfg_t* c, const void* w_half, const float
   r = r ? r : make_operand_map(&e->map_y, e->ws.y, rows, D, 128);
   r = r ? r : make_operand_map(&e->map_ao, e->ws.ao, rows, D, 128);
   r = r ? r : make_operand_map(&e->map_h, e->ws.hmid, rows, M, 128);
+  e->attn_tc = attention_tc_supported(e->T) && getenv("BSCNAV_ATTENTION_TC") != nullptr;   // measured slower than mma.sync (119 vs 98 us @B=64)
+  r = r ? r : make_operand_map(&e->qkv128, e->ws.qkv, rows, 3 * D, 128);
+  r = r ? r : make_operand_map(&e->qkv16, e->ws.qkv, rows, 3 * D, 16);
   r = r ? r : make_store_map(&e->out_qkv, e->ws.qkv, rows, 3 * D, false);
   r = r ? r : make_store_map(&e->out_h, e->ws.hmid, rows, M, false);
   r = r ? r : make_store_map(&e->out_x, e->ws.x, rows, D, true);

@@ -12,6 +12,6 @@ int layernorm_half(const float* x, const float* g, const float* b, float eps, lo
 int layernorm_inplace(float* x, const float* g, const float* b, float eps, long long rows, int D, cudaStream_t s);
 int layernorm_patch_tokens(const float* x, const float* g, const float* b, float eps, int batch, int tokens, int skip, int D,
                            float* out, cudaStream_t s);
-int attention_f16(const __half* qkv, __half* out, int batch, int T, int heads, cudaStream_t stream);
+int attention_f16(const __half* qkv, __half* out, int batch, int T, int heads, cudaStream_t stream);   // mma.sync kernel
 
 }  // namespace bscnav

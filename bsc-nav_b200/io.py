@@ -56,7 +56,7 @@ def load_memory(mem, path: str):
     st.tok_h[:rows] = torch.from_numpy(np.load(path + "/bscnav_tok_h.npy")).to(st.device)
     feat = torch.from_numpy(np.load(path + "/bscnav_feat.npy")).to(st.device)
     st.feat[:rows] = feat
-    st.norm2[:rows] = (feat * feat).sum(dim=1)
+    st.row_norms(rows)
     st.counters[0] = n
     st.next_ordinal = int(meta[4])
     mem.minh, mem.maxh = [int(v) for v in np.load(path + "/map_height.npy")]

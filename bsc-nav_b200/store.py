@@ -90,6 +90,10 @@ class SpatialStore:
         _lib.check(self.lib.bscnav_store_reset(C.byref(self.g), C.byref(self.st), _lib.stream_ptr()), "store_reset")
         self.next_ordinal = 0
 
+    def row_norms(self, n_rows: int):
+        """Recompute norm2 of the first n_rows token rows on the device (used after loading rows from disk)."""
+        _lib.check(self.lib.bscnav_store_row_norms(C.byref(self.g), C.byref(self.st), int(n_rows), _lib.stream_ptr()), "row_norms")
+
     def _scratch_for(self, nbytes: int) -> torch.Tensor:
         if self._scratch is None or self._scratch.numel() < nbytes:
             self._scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)

@@ -155,3 +155,10 @@ def gemm_f16(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None,
     _lib.check(_lib.lib().bscnav_gemm_f16(_lib.ptr(a), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(out), M, N, K, out_mode, act,
                                           _lib.stream_ptr()), "gemm_f16")
     return out
+
+
+def attention_f16(qkv: torch.Tensor, batch: int, T: int, heads: int, impl: int = 1) -> torch.Tensor:
+    """Self-attention over a packed fp16 qkv tensor [batch*T, 3*heads*64] (q pre-scaled); impl 0 = mma.sync, 1 = tcgen05."""
+    out = torch.empty(batch * T, heads * 64, dtype=torch.float16, device=qkv.device)
+    _lib.check(_lib.lib().bscnav_attention_f16(_lib.ptr(qkv), _lib.ptr(out), batch, T, heads, impl, _lib.stream_ptr()), "attention_f16")
+    return out

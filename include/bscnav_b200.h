@@ -75,6 +75,10 @@ typedef struct {
 /* Reset a store to empty (replaces _init_cache, memory_2.py:708-722). */
 int bscnav_store_reset(const bscnav_geom_t* g, const bscnav_store_t* st, void* stream);
 
+/* Recompute norm2[0, n_rows) from feat (after filling token rows from a memory directory, memory_2.py:185-200);
+ * same summation order as the commit kernel, so a reloaded store scores bit-identically. */
+int bscnav_store_row_norms(const bscnav_geom_t* g, const bscnav_store_t* st, int64_t n_rows, void* stream);
+
 /* Scratch needed by bscnav_fuse_frames for a batch of n_frames x n_points points. */
 int64_t bscnav_fuse_scratch_bytes(int32_t n_frames, int32_t n_points);
 
@@ -175,6 +179,10 @@ int bscnav_gaussian_pool(const float* tokens, int32_t batch, int32_t grid, int32
  * tcgen05; out_mode 0: fp16 out, 1: fp16 out with activation `act`, 2: fp32 out += (residual accumulate). */
 int bscnav_gemm_f16(const void* a, const void* w, const float* bias, void* out, int32_t m, int32_t n, int32_t k,
                     int32_t out_mode, int32_t act, void* stream);
+
+/* Stand-alone attention entry (tests/bench): qkv fp16 [batch*T, 3*heads*64] (q pre-scaled by 1/sqrt(64)) ->
+ * out fp16 [batch*T, heads*64].  impl 0: mma.sync kernel (any T); impl 1: tcgen05 kernel (T <= 272). */
+int bscnav_attention_f16(const void* qkv, void* out, int32_t batch, int32_t T, int32_t heads, int32_t impl, void* stream);
 
 /* Number of kernels launched by this library since load (bench.py's gpu_launches). */
 int64_t bscnav_launch_count(void);

@@ -87,3 +87,16 @@ def test_gaussian_pool(pkg):
     t = torch.randn(3, 256, 1024, generator=torch.Generator().manual_seed(0))
     got = pkg.gaussian_pool(t.cuda()).cpu()
     torch.testing.assert_close(got, vit_ref.gaussian_pool(t), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("T,heads,batch", [(257, 16, 3), (261, 16, 2), (50, 12, 4), (128, 2, 2), (272, 4, 2), (200, 3, 1), (17, 1, 1)])
+@pytest.mark.parametrize("impl", [0, 1])
+def test_attention_kernels(pkg, T, heads, batch, impl):
+    g = torch.Generator("cuda").manual_seed(T + heads)
+    D = heads * 64
+    qkv = (torch.randn(batch * T, 3 * D, device="cuda", generator=g) * 0.8).half()
+    out = pkg.attention_f16(qkv, batch, T, heads, impl=impl).float().view(batch, T, heads, 64)
+    q, k, v = qkv.float().view(batch, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    ref = torch.softmax(q @ k.transpose(-1, -2), dim=-1) @ v          # q arrives pre-scaled
+    ref = ref.permute(0, 2, 1, 3)
+    torch.testing.assert_close(out, ref, rtol=2e-3, atol=2e-3)

@@ -259,6 +259,11 @@ extern "C" int bscnav_attention_f16(const void* qkv, void* out, int32_t batch, i
   if (!qkv || !out || batch <= 0 || T <= 0 || heads <= 0) return BSCNAV_EINVAL;
   if (impl == 0) return attention_f16(static_cast<const __half*>(qkv), static_cast<__half*>(out), batch, T, heads, (cudaStream_t)stream);
   CUtensorMap m128, m16;
+  if (impl == 2) {
+    if (int e = make_qkv_map3d(&m128, qkv, batch, T, 3LL * heads * 64, 128)) return e;
+    if (int e = make_qkv_map3d(&m16, qkv, batch, T, 3LL * heads * 64, 16)) return e;
+    return attention_ws_launch(&m128, &m16, static_cast<__half*>(out), batch, T, heads, (cudaStream_t)stream);
+  }
   if (int e = make_operand_map(&m128, qkv, (long long)batch * T, 3LL * heads * 64, 128)) return e;
   if (int e = make_operand_map(&m16, qkv, (long long)batch * T, 3LL * heads * 64, 16)) return e;
   return attention_tc_launch(&m128, &m16, static_cast<__half*>(out), batch, T, heads, (cudaStream_t)stream);

@@ -46,6 +46,12 @@ bool attention_tc_supported(int T);
 int attention_tc_launch(const CUtensorMap* map128, const CUtensorMap* map16, __half* out, int batch, int T, int heads,
                         cudaStream_t stream);
 
+// warp-specialised tcgen05 attention (attention_ws.cu): map128 / map16 = make_qkv_map3d with 128- and 16-row boxes
+int make_qkv_map3d(CUtensorMap* map, const void* ptr, long long batch, long long T, long long width, int box_rows);
+bool attention_ws_supported(int T);
+int attention_ws_launch(const CUtensorMap* map128, const CUtensorMap* map16, __half* out, int batch, int T, int heads,
+                        cudaStream_t stream);
+
 int gemm_block_n(int N);   // 256 when N % 256 == 0 (BN=128 is shared-memory-bandwidth bound at cta_group::1), else 128
 
 }  // namespace bscnav

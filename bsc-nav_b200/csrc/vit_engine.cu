@@ -86,7 +86,8 @@ struct VitEngine {
   CUtensorMap map_patch_w;
   CUtensorMap out_qkv, out_h, out_x;                 // store maps of the GEMM outputs
   CUtensorMap qkv128, qkv16;                         // qkv tensor as attention operand (128- and 16-row boxes)
-  bool attn_tc = false;
+  CUtensorMap qkv3d128, qkv3d16;                     // the same tensor as {column, token, frame} (attention_ws.cu)
+  int attn_impl = 0;                                 // 0 mma.sync, 1 tcgen05 v1, 2 tcgen05 warp-specialised
   CUtensorMap map_qkv[64], map_proj[64], map_fc1[64], map_fc2[64];
   bool a0_cleared = false;
   // optional per-kernel timing (bench.py's roofline leg): CUDA events around every launch on the caller's stream
@@ -133,7 +134,10 @@ static int vit_run(VitEngine* e, int batch, float* out_tokens, cudaStream_t stre
     { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * 3.0 * D * D);
       if (int r = gemm_f16_launch(&e->map_y, &e->map_qkv[i], &e->out_qkv, rows, 3 * D, D, e1, stream)) return r; }
     { ProfScope ps(e, stream, kCatAttention, 4.0 * batch * (double)T * T * D);
-      if (e->attn_tc) { if (int r = attention_tc_launch(&e->qkv128, &e->qkv16, e->ws.ao, batch, T, c.heads, stream)) return r; }
+      if (e->attn_impl == 2) {
+        // the 3-D map's frame extent is the engine's max_batch: frames >= batch are simply never addressed
+        if (int r = attention_ws_launch(&e->qkv3d128, &e->qkv3d16, e->ws.ao, batch, T, c.heads, stream)) return r;
+      } else if (e->attn_impl == 1) { if (int r = attention_tc_launch(&e->qkv128, &e->qkv16, e->ws.ao, batch, T, c.heads, stream)) return r; }
       else if (int r = attention_f16(e->ws.qkv, e->ws.ao, batch, T, c.heads, stream)) return r; }
     GemmEpilogue e2{};
     e2.out = e->ws.x; e2.bias = wf + o.proj_b; e2.ld_out = D; e2.mode = kOutResidual;
@@ -198,7 +202,12 @@ int bscnav_vit_create(const bscnav_vit_cfg_t* c, const void* w_half, const float
   r = r ? r : make_operand_map(&e->map_y, e->ws.y, rows, D, 128);
   r = r ? r : make_operand_map(&e->map_ao, e->ws.ao, rows, D, 128);
   r = r ? r : make_operand_map(&e->map_h, e->ws.hmid, rows, M, 128);
-  e->attn_tc = attention_tc_supported(e->T) && getenv("BSCNAV_ATTENTION_TC") != nullptr;   // measured slower than mma.sync (119 vs 98 us @B=64)
+  const char* impl_env = getenv("BSCNAV_ATTENTION");
+  e->attn_impl = impl_env ? atoi(impl_env) : 0;
+  if (e->attn_impl == 2 && !attention_ws_supported(e->T)) e->attn_impl = 0;
+  if (e->attn_impl == 1 && !attention_tc_supported(e->T)) e->attn_impl = 0;
+  r = r ? r : make_qkv_map3d(&e->qkv3d128, e->ws.qkv, max_batch, e->T, 3 * D, 128);
+  r = r ? r : make_qkv_map3d(&e->qkv3d16, e->ws.qkv, max_batch, e->T, 3 * D, 16);
   r = r ? r : make_operand_map(&e->qkv128, e->ws.qkv, rows, 3 * D, 128);
   r = r ? r : make_operand_map(&e->qkv16, e->ws.qkv, rows, 3 * D, 16);
   r = r ? r : make_store_map(&e->out_qkv, e->ws.qkv, rows, 3 * D, false);

@@ -69,8 +69,10 @@ def test_tiny_vit_matches_oracle(pkg, base):
     assert _rel(got, ref) < 1e-3
 
 
+@pytest.mark.parametrize("attn", ["0", "2"])
 @pytest.mark.parametrize("base", ["clip-vit-l14", "dinov2-vitl14-reg", "clip-vit-b32"])
-def test_full_vit_matches_oracle(pkg, base):
+def test_full_vit_matches_oracle(pkg, base, attn, monkeypatch):
+    monkeypatch.setenv("BSCNAV_ATTENTION", attn)      # read when the engine is created: 0 = mma.sync, 2 = tcgen05 warp-specialised
     cfg = pkg.CONFIGS[base]
     w = pkg.random_weights(cfg, seed=0)
     eng = pkg.ViTEngine(cfg, w, max_batch=4)
@@ -90,7 +92,7 @@ def test_gaussian_pool(pkg):
 
 
 @pytest.mark.parametrize("T,heads,batch", [(257, 16, 3), (261, 16, 2), (50, 12, 4), (128, 2, 2), (272, 4, 2), (200, 3, 1), (17, 1, 1)])
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 def test_attention_kernels(pkg, T, heads, batch, impl):
     g = torch.Generator("cuda").manual_seed(T + heads)
     D = heads * 64
@@ -100,3 +102,14 @@ def test_attention_kernels(pkg, T, heads, batch, impl):
     ref = torch.softmax(q @ k.transpose(-1, -2), dim=-1) @ v          # q arrives pre-scaled
     ref = ref.permute(0, 2, 1, 3)
     torch.testing.assert_close(out, ref, rtol=2e-3, atol=2e-3)
+
+
+def test_attention_ws_many_items_matches_mma(pkg):
+    """The persistent tcgen05 kernel over several waves of (frame, head) items (barrier phases wrap many times)."""
+    B, T, heads = 23, 257, 16
+    g = torch.Generator("cuda").manual_seed(9)
+    qkv = (torch.randn(B * T, 3 * heads * 64, device="cuda", generator=g) * 0.8).half()
+    a = pkg.attention_f16(qkv, B, T, heads, impl=0).float()
+    for _ in range(3):
+        b = pkg.attention_f16(qkv, B, T, heads, impl=2).float()
+        torch.testing.assert_close(b, a, rtol=2e-3, atol=2e-3)

@@ -1,0 +1,41 @@
+"""Runs the unproject/scatter kernels (bench shape: 55 dense 640x480 frames into a 512x512 BEV store, C=1, D=1024) and the
+query kernels (262 144 stored tokens, K=100, Q=1 and Q=8) a few times: the command ncu wraps for the HBM-kernel captures,
+and -- without ncu -- a CUDA-event timing of each phase.  Not the benchmark."""
+import importlib, os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+pkg = importlib.import_module("bsc-nav_b200")
+synth = importlib.import_module("bsc-nav_b200.synth")
+
+B = int(os.environ.get("B", 55)); REPS = int(os.environ.get("REPS", 3)); VOX = int(os.environ.get("VOXEL", 0))
+H, W, GS, D = 480, 640, 512, 1024
+
+def timeit(fn, n):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n): fn(i)
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+scfg = pkg.StoreConfig(height=H, width=W, grid_size=GS, token_dim=D, cache_size=1, bev=not VOX)
+st = pkg.SpatialStore(scfg)
+chain = pkg.PoseChain([0, 0, -1], [-1, 0, 0], [0, 1, 0], [1, 0, 0, 0, -1, 0, 0, 0, -1], 1.5)
+frames = [synth.synthetic_frame(f, H, W) for f in range(2 * B)]
+depth = torch.from_numpy(np.stack([f[1] for f in frames])).cuda()
+poses = torch.from_numpy(np.stack([chain(f[2]) for f in frames]).reshape(2 * B, 16)).cuda()
+tokens = torch.randn(B, 256, D, device="cuda")
+ms = timeit(lambda i: st.fuse(depth[(i % 2) * B:(i % 2) * B + B], poses[(i % 2) * B:(i % 2) * B + B], tokens), REPS)
+U = st.count()
+alg = B * (H * W * 4 + 256 * D * 4) + U * (D * 4 * 2 + 16)
+print(f"fuse B={B} voxel={VOX}: {ms:.3f} ms/batch  {B / ms * 1e3:.0f} frames/s  slots {U}  algorithmic {alg / 1e6:.1f} MB -> {alg / ms / 1e6:.0f} GB/s")
+n = GS * GS
+if not VOX:
+    st.counters[0] = n; st.row_key.zero_(); st.slot_keys.zero_()
+    st.slot_cell.copy_(torch.arange(n, dtype=torch.int32, device="cuda")); st.occupied_ids.copy_(torch.arange(n, dtype=torch.int32, device="cuda"))
+    st.feat.normal_(); st.norm2.copy_((st.feat ** 2).sum(1)); st.tok_h.fill_(100)
+    q = torch.randn(64, D, device="cuda")
+    for Q in (1, 8, 64):
+        st.query(q[:Q], k=100)
+        ms = timeit(lambda i: st.query(q[:Q], k=100), REPS)
+        print(f"query Q={Q} over {n} tokens: {ms:.3f} ms/pass  {Q / ms * 1e3:.0f} queries/s  {n * (D * 4 + 4) * ((Q + 7) // 8) / ms / 1e6:.0f} GB/s algorithmic")

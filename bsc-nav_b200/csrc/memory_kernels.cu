@@ -5,7 +5,7 @@
 //
 // Reference semantics restated here (each kernel cites its lines): memory_2.py:744-756, 842-894, 326-358,
 // 623-671; utils.py:153-214.
-#include "common.cuh"
+#include "memory_kernels.cuh"
 
 namespace bscnav {
 
@@ -435,14 +435,6 @@ k_export_write(const unsigned long long* __restrict__ row_key, const int32_t* __
 // candidate filter, composite sort key  (~orderable(sim) << 32) | cell  -> ascending key == descending sim,
 // ties by ascending (row, col, h) because cell is the row-major linear index.
 static constexpr int kQ = 8;
-__device__ __forceinline__ uint32_t orderable(float f) {
-  const uint32_t b = __float_as_uint(f);
-  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float from_orderable(uint32_t o) {
-  return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
-}
-
 template <int NV>   // NV = D / 128 float4 per lane
 __global__ void __launch_bounds__(kThreads)
 k_query_slots(const bscnav_geom_t g, const float* __restrict__ feat, const float* __restrict__ norm2,
@@ -484,12 +476,7 @@ k_query_slots(const bscnav_geom_t g, const float* __restrict__ feat, const float
       if (g.levels == 1) {            // BEV keys: the token's own height takes part in the filter
         h = tok_h[r];
       }
-      bool ok = true;
-      if (flt.radius2 >= 0) {
-        const long long dr = row - flt.cur[0], dc = col - flt.cur[1], dh = h - flt.cur[2];
-        ok = dr * dr + dc * dc + dh * dh <= flt.radius2;
-      }
-      if (flt.floor_min <= flt.floor_max) ok = ok && h >= flt.floor_min && h <= flt.floor_max;
+      const bool ok = filter_pass(flt, row, col, h);
       if (!ok) { if (g.levels != 1) { cand = false; break; } else continue; }
       float4 v[NV];
       const float4* fr = reinterpret_cast<const float4*>(feat + r * D);
@@ -526,7 +513,7 @@ k_query_slots(const bscnav_geom_t g, const float* __restrict__ feat, const float
 }
 
 // Q2: per-chunk top-K by bitonic sort in shared memory; applied repeatedly until one chunk remains.
-static constexpr int kChunk = 4096;
+static constexpr int kChunk = kTopkChunk;
 __global__ void __launch_bounds__(1024)
 k_topk_chunks(const unsigned long long* __restrict__ in, long long in_stride, const int32_t* __restrict__ n_dev, int n_host,
               unsigned long long* __restrict__ out, long long out_stride, int k) {
@@ -602,7 +589,9 @@ k_topk_decode(const bscnav_geom_t g, const unsigned long long* __restrict__ keys
   }
 }
 
-static int num_sms() {
+int mem_num_sms();
+static int num_sms() { return mem_num_sms(); }
+int mem_num_sms() {
   static int n = 0;
   if (!n) {
     int dev = 0;
@@ -613,7 +602,8 @@ static int num_sms() {
   return n;
 }
 
-static int check_geom(const bscnav_geom_t* g) {
+static int check_geom(const bscnav_geom_t* g) { return mem_check_geom(g); }
+int mem_check_geom(const bscnav_geom_t* g) {
   if (!g) return BSCNAV_EINVAL;
   if (g->height <= 0 || g->width <= 0 || g->gs <= 0 || g->levels <= 0 || g->cache <= 0 || g->cache > 64) return BSCNAV_EINVAL;
   if (g->dim <= 0 || g->dim % 128 != 0 || g->dim > 2048) return BSCNAV_EINVAL;
@@ -658,6 +648,22 @@ static int run_store_update(const bscnav_geom_t* g, const bscnav_store_t* st, co
   BSC_LAUNCH(k_commit, n_blocks, kThreads, 0, stream, s.rec, total, st->occupied_ids,
              reinterpret_cast<const unsigned long long*>(st->slot_keys), reinterpret_cast<unsigned long long*>(st->row_key),
              st->tok_h, st->norm2, st->feat, tokens, g->cache, g->dim);
+  return BSCNAV_OK;
+}
+
+int launch_topk_chunks(const unsigned long long* in, long long in_stride, const int32_t* n_dev, int n_host, int n_chunks,
+                       int n_query, unsigned long long* out, long long out_stride, int k, cudaStream_t stream) {
+  BSC_LAUNCH(k_topk_chunks, dim3((unsigned)n_chunks, (unsigned)n_query), 1024, 0, stream, in, in_stride, n_dev, n_host, out,
+             out_stride, k);
+  return BSCNAV_OK;
+}
+
+int launch_topk_decode(const bscnav_geom_t* g, const bscnav_store_t* st, const unsigned long long* keys, long long key_stride, int k,
+                       const float* q, int n_query, float* out_sim, int32_t* out_pos, int32_t* out_count, cudaStream_t stream) {
+  BSC_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int32_t) * n_query, stream));
+  BSC_LAUNCH(k_topk_decode, dim3((unsigned)n_query, (unsigned)((k + kThreads / 32 - 1) / (kThreads / 32))), kThreads, 0, stream, *g,
+             keys, key_stride, k, st->occupied_ids, reinterpret_cast<const unsigned long long*>(st->row_key), st->tok_h, st->feat,
+             st->norm2, q, 0, out_sim, out_pos, out_count);
   return BSCNAV_OK;
 }
 

@@ -1,0 +1,343 @@
+// Batched goal queries (BASELINE configs[2] and [3]: thousands of text-goal queries, batch-256 image queries):
+// cosine similarity of Q queries against every stored token, per-cell max, top-K  (memory_2.py:642-671), for many
+// queries per pass over the store.
+//
+// One query is HBM-bound (k_query_slots streams the fp32 rows once).  Eight or more queries per pass are not: on the
+// CUDA cores the scan turns shared-memory bound (measured 0.65 ms for 8 queries, 5.2 ms for 64).  So the batch path puts
+// the contraction on the tensor cores and keeps the reference's exact fp32 arithmetic only where it decides the result:
+//
+//   1. shadow      unit-normalised fp16 copy of the token rows (built once per store state by k_build_shadow)
+//   2. GEMM        approx[q, row] = q^[q, :] . f^[row, :]   (k_gemm_f16 on tcgen05, fp32 accumulate) -- within
+//                  eps = 1.1e-3 of the exact cosine: both operands are rounded once to fp16 (relative 2^-11 each),
+//                  |sum(f^ q^) - cos| <= (2^-10 + 2^-22) sum|f^_i q^_i| <= 9.8e-4 by Cauchy-Schwarz, plus fp32
+//                  accumulation and subnormal terms < 1e-4
+//   3. histogram   per query, 2048 bins of width 2^-10 over [-1, 1] of the per-cell max of approx (k_batch_hist)
+//   4. select      tb = bin holding the K-th largest approx value; every cell whose bin is >= tb - 3 becomes a
+//                  candidate (k_batch_select).  At least K cells have approx >= edge(tb), hence exact >= edge(tb) - eps;
+//                  a rejected cell has approx < edge(tb) - 3 * 2^-10, hence exact < edge(tb) - 2.93e-3 + eps, which is
+//                  below edge(tb) - eps because eps < 1.46e-3: no rejected cell can belong to the exact top-K
+//   5. re-score    exact fp32 cosine of each candidate with the very FMA order of k_query_slots, composite key,
+//                  bitonic top-K, decode (shared stages)  ->  results are bit-identical to the single-query path
+//
+// A query whose candidate count exceeds kCandCap (more than ~4000 cells within 4e-3 of its K-th similarity) is flagged
+// with out_count = -1; the host re-issues it through bscnav_query_topk.
+#include "gemm_tcgen05.cuh"
+#include "memory_kernels.cuh"
+
+namespace bscnav {
+
+static constexpr int kBins = 2048;
+static constexpr int kCandCap = kTopkChunk;
+static constexpr int kMarginBins = 3;
+static constexpr int kSelSlots = 2048;      // cells per block in the histogram / select passes
+static constexpr int kPassQueries = 256;    // queries per GEMM pass
+
+__device__ __forceinline__ int sim_bin(float s) {
+  const int b = (int)((s + 1.0f) * 1024.0f);          // NaN converts to 0
+  return b < 0 ? 0 : (b > kBins - 1 ? kBins - 1 : b);
+}
+
+// unit-normalised fp16 copy of rows [0, slots_in_use * C); one warp per row
+__global__ void __launch_bounds__(kMemThreads)
+k_build_shadow(const float* __restrict__ feat, const int32_t* __restrict__ counters, int C, int D, __half* __restrict__ shadow) {
+  const int lane = threadIdx.x & 31;
+  const long long n_rows = (long long)counters[0] * C;
+  const long long warps = (long long)gridDim.x * (kMemThreads / 32);
+  for (long long row = (long long)blockIdx.x * (kMemThreads / 32) + (threadIdx.x >> 5); row < n_rows; row += warps) {
+    const float4* s = reinterpret_cast<const float4*>(feat + row * D);
+    float acc = 0.f;
+    for (int c = lane; c < (D >> 2); c += 32) {
+      const float4 v = s[c];
+      acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
+    }
+    acc = warp_sum(acc);
+    const float inv = acc > 0.f ? 1.0f / sqrtf(acc) : 0.f;
+    uint2* d = reinterpret_cast<uint2*>(shadow + row * D);
+    for (int c = lane; c < (D >> 2); c += 32) {
+      const float4 v = s[c];
+      const __half2 a = __floats2half2_rn(v.x * inv, v.y * inv), b = __floats2half2_rn(v.z * inv, v.w * inv);
+      d[c] = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+    }
+  }
+}
+
+// queries: squared norm with the association k_query_slots uses (so the exact re-scoring matches it bit for bit) and
+// the unit-normalised fp16 operand of the GEMM; one warp per query
+__global__ void __launch_bounds__(kMemThreads)
+k_prep_queries(const float* __restrict__ q, int n_query, int D, __half* __restrict__ qh, float* __restrict__ qn2) {
+  const int lane = threadIdx.x & 31;
+  const int qi = blockIdx.x * (kMemThreads / 32) + (threadIdx.x >> 5);
+  if (qi >= n_query) return;
+  const float4* s = reinterpret_cast<const float4*>(q + (long long)qi * D);
+  float acc = 0.f;
+  for (int c = lane; c < (D >> 2); c += 32) {
+    const float4 v = s[c];
+    acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) qn2[qi] = acc;
+  const float inv = acc > 0.f ? 1.0f / sqrtf(acc) : 0.f;
+  uint2* d = reinterpret_cast<uint2*>(qh + (long long)qi * D);
+  for (int c = lane; c < (D >> 2); c += 32) {
+    const float4 v = s[c];
+    const __half2 a = __floats2half2_rn(v.x * inv, v.y * inv), b = __floats2half2_rn(v.z * inv, v.w * inv);
+    d[c] = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+  }
+}
+
+// per token row: does it take part in this batch?  (non-empty, passes the region / floor filter of memory_2.py:624-640;
+// voxel keys: the whole cell passes or fails; BEV keys: the token's own height decides, as in k_query_slots)
+__global__ void __launch_bounds__(kMemThreads)
+k_row_ok(const bscnav_geom_t g, const unsigned long long* __restrict__ row_key, const int32_t* __restrict__ slot_cell,
+         const int32_t* __restrict__ tok_h, const int32_t* __restrict__ counters, const bscnav_filter_t flt,
+         uint8_t* __restrict__ row_ok) {
+  const long long r = (long long)blockIdx.x * kMemThreads + threadIdx.x;
+  const int C = g.cache;
+  if (r >= (long long)counters[0] * C) return;
+  const int slot = (int)(r / C);
+  bool ok = row_key[r] != BSCNAV_KEY_EMPTY;
+  if (ok) {
+    const int cell = slot_cell[slot];
+    int row, col, h;
+    if (g.levels == 1) { row = cell / g.gs; col = cell - row * g.gs; h = tok_h[r]; }
+    else { h = cell % g.levels; const int rc = cell / g.levels; row = rc / g.gs; col = rc - row * g.gs; }
+    ok = filter_pass(flt, row, col, h);
+  }
+  row_ok[r] = ok ? 1 : 0;
+}
+
+__device__ __forceinline__ float approx_cell(const float* __restrict__ sims_q, const uint8_t* __restrict__ row_ok, int slot, int C) {
+  float best = -INFINITY;
+  for (int j = 0; j < C; ++j) {
+    const long long r = (long long)slot * C + j;
+    if (row_ok[r]) best = fmaxf(best, sims_q[r]);
+  }
+  return best;
+}
+
+__global__ void __launch_bounds__(kMemThreads)
+k_batch_hist(const float* __restrict__ sims, long long ld, const uint8_t* __restrict__ row_ok, const int32_t* __restrict__ counters,
+             int C, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t h[kBins];
+  const int qi = blockIdx.y;
+  const int n_slots = counters[0];
+  const int slot0 = blockIdx.x * kSelSlots;
+  if (slot0 >= n_slots) return;
+  for (int b = threadIdx.x; b < kBins; b += kMemThreads) h[b] = 0;
+  __syncthreads();
+  const float* sq = sims + (long long)qi * ld;
+  for (int i = threadIdx.x; i < kSelSlots; i += kMemThreads) {
+    const int slot = slot0 + i;
+    if (slot < n_slots) {
+      const float s = approx_cell(sq, row_ok, slot, C);
+      if (s > -INFINITY) atomicAdd(&h[sim_bin(s)], 1u);
+    }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < kBins; b += kMemThreads)
+    if (h[b]) atomicAdd(&hist[(long long)qi * kBins + b], h[b]);
+}
+
+__global__ void __launch_bounds__(kMemThreads)
+k_batch_select(const float* __restrict__ sims, long long ld, const uint8_t* __restrict__ row_ok, const int32_t* __restrict__ counters,
+               int C, const uint32_t* __restrict__ hist, int k, int32_t* __restrict__ cand, int32_t* __restrict__ cand_count,
+               int32_t* __restrict__ overflow) {
+  static_assert(kBins == 8 * kMemThreads, "one thread owns eight bins");
+  __shared__ uint32_t part[kMemThreads], above_of[kMemThreads];
+  __shared__ int s_tb;
+  __shared__ uint32_t s_ncand;
+  const int qi = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int n_slots = counters[0];
+  const int slot0 = blockIdx.x * kSelSlots;
+  if (slot0 >= n_slots) return;
+  // threshold bin: the bin that holds the k-th largest value (0 when fewer than k cells take part)
+  uint32_t local[8], sum = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { local[i] = hist[(long long)qi * kBins + tid * 8 + i]; sum += local[i]; }
+  part[tid] = sum;
+  if (tid == 0) { s_tb = 0; s_ncand = 0; }
+  __syncthreads();
+  if (tid < 32) {
+    uint32_t p8[8], s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { p8[i] = part[8 * lane + i]; s += p8[i]; }
+    uint32_t suf = s;                                   // inclusive suffix sum over lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_down_sync(0xffffffffu, suf, o);
+      if (lane + o < 32) suf += t;
+    }
+    uint32_t above = suf - s;                           // values in bins above this lane's 64 bins
+#pragma unroll
+    for (int i = 7; i >= 0; --i) { above_of[8 * lane + i] = above; above += p8[i]; }
+  }
+  __syncthreads();
+  {
+    uint32_t above = above_of[tid];
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+      const uint32_t c = above + local[i];
+      if (above < (uint32_t)k && c >= (uint32_t)k) s_tb = tid * 8 + i;
+      above = c;
+    }
+  }
+  __syncthreads();
+  const int t = s_tb > kMarginBins ? s_tb - kMarginBins : 0;
+  if (t >= tid * 8 && t < tid * 8 + 8) {
+    uint32_t n = above_of[tid];
+    for (int i = t - tid * 8; i < 8; ++i) n += local[i];
+    s_ncand = n;
+  }
+  __syncthreads();
+  if (s_ncand > (uint32_t)kCandCap) {
+    if (blockIdx.x == 0 && tid == 0) overflow[qi] = (int32_t)s_ncand;
+    return;
+  }
+  const float* sq = sims + (long long)qi * ld;
+  for (int i = tid; i < kSelSlots; i += kMemThreads) {
+    const int slot = slot0 + i;
+    if (slot < n_slots) {
+      const float s = approx_cell(sq, row_ok, slot, C);
+      if (s > -INFINITY && sim_bin(s) >= t) {
+        const int pos = atomicAdd(&cand_count[qi], 1);
+        if (pos < kCandCap) cand[(long long)qi * kCandCap + pos] = slot;
+      }
+    }
+  }
+}
+
+// exact fp32 cosine of every candidate cell, arithmetic identical to k_query_slots; one warp per candidate
+__global__ void __launch_bounds__(kMemThreads)
+k_batch_rescore(const bscnav_geom_t g, const float* __restrict__ feat, const float* __restrict__ norm2,
+                const uint8_t* __restrict__ row_ok, const int32_t* __restrict__ slot_cell, const float* __restrict__ q,
+                const float* __restrict__ qn2, const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_count,
+                const int32_t* __restrict__ overflow, unsigned long long* __restrict__ keys) {
+  const int qi = blockIdx.y, lane = threadIdx.x & 31;
+  const int D = g.dim, C = g.cache;
+  const int n = overflow[qi] ? 0 : min(cand_count[qi], kCandCap);
+  const float4* qv = reinterpret_cast<const float4*>(q + (long long)qi * D);
+  const float w1 = qn2[qi];
+  const int warps = gridDim.x * (kMemThreads / 32);
+  for (int idx = blockIdx.x * (kMemThreads / 32) + (threadIdx.x >> 5); idx < n; idx += warps) {
+    const int slot = cand[(long long)qi * kCandCap + idx];
+    float best = -INFINITY;
+    for (int j = 0; j < C; ++j) {
+      const long long r = (long long)slot * C + j;
+      if (!row_ok[r]) continue;
+      const float4* fr = reinterpret_cast<const float4*>(feat + r * D);
+      float acc = 0.f;
+      for (int c = lane; c < (D >> 2); c += 32) {
+        const float4 v = ld_stream_f4(fr + c), qq = qv[c];
+        acc = fmaf(v.x, qq.x, acc); acc = fmaf(v.y, qq.y, acc); acc = fmaf(v.z, qq.z, acc); acc = fmaf(v.w, qq.w, acc);
+      }
+      acc = warp_sum(acc);
+      const float s = acc / sqrtf(fmaxf(w1 * norm2[r], 1e-16f));      // F.cosine_similarity, memory_2.py:656
+      best = fmaxf(best, s);
+    }
+    if (lane == 0 && best > -INFINITY)
+      keys[(long long)qi * kCandCap + idx] = ((unsigned long long)(~orderable(best)) << 32) | (uint32_t)slot_cell[slot];
+  }
+}
+
+__global__ void k_mark_overflow(const int32_t* __restrict__ overflow, int n_query, int32_t* __restrict__ out_count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_query && overflow[i]) out_count[i] = -1;
+}
+
+struct BatchScratch {
+  __half* qh; float* qn2; uint8_t* row_ok; float* sims; uint32_t* hist; int32_t* cand_count; int32_t* overflow;
+  int32_t* cand; unsigned long long* keys; unsigned long long* sorted;
+};
+static long long batch_rows(const bscnav_geom_t* g, long long n_rows_hint) {
+  const long long cap = align_up((long long)g->max_slots * g->cache, 256);
+  long long n = n_rows_hint > 0 ? align_up(n_rows_hint, 256) : cap;
+  return n < cap ? n : cap;
+}
+static int64_t batch_layout(const bscnav_geom_t* g, int n_query, int k, long long n_rows_hint, BatchScratch* s, char* base) {
+  const long long P = n_query < kPassQueries ? n_query : kPassQueries, N = batch_rows(g, n_rows_hint);
+  long long off = 0;
+  auto take = [&](long long bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes, 1024); return p; };
+  char* p;
+  p = take(align_up(P, 128) * g->dim * 2); if (s) s->qh = reinterpret_cast<__half*>(p);
+  p = take(P * 4); if (s) s->qn2 = reinterpret_cast<float*>(p);
+  p = take((long long)g->max_slots * g->cache); if (s) s->row_ok = reinterpret_cast<uint8_t*>(p);
+  p = take(P * N * 4); if (s) s->sims = reinterpret_cast<float*>(p);
+  p = take(P * kBins * 4); if (s) s->hist = reinterpret_cast<uint32_t*>(p);
+  p = take(P * 4); if (s) s->cand_count = reinterpret_cast<int32_t*>(p);
+  p = take(P * 4); if (s) s->overflow = reinterpret_cast<int32_t*>(p);
+  p = take(P * kCandCap * 4); if (s) s->cand = reinterpret_cast<int32_t*>(p);
+  p = take(P * kCandCap * 8); if (s) s->keys = reinterpret_cast<unsigned long long*>(p);
+  p = take(P * (long long)k * 8); if (s) s->sorted = reinterpret_cast<unsigned long long*>(p);
+  return off;
+}
+
+}  // namespace bscnav
+
+using namespace bscnav;
+
+extern "C" {
+
+int64_t bscnav_shadow_bytes(const bscnav_geom_t* g) {
+  if (mem_check_geom(g)) return BSCNAV_EINVAL;
+  return align_up((long long)g->max_slots * g->cache, 256) * g->dim * 2;
+}
+
+int bscnav_store_build_shadow(const bscnav_geom_t* g, const bscnav_store_t* st, void* shadow, void* stream_) {
+  if (int e = mem_check_geom(g)) return e;
+  if (!st || !st->feat || !st->counters || !shadow) return BSCNAV_EINVAL;
+  BSC_LAUNCH(k_build_shadow, mem_num_sms() * 8, kMemThreads, 0, (cudaStream_t)stream_, st->feat, st->counters, g->cache, g->dim,
+             static_cast<__half*>(shadow));
+  return BSCNAV_OK;
+}
+
+int64_t bscnav_query_batch_scratch_bytes(const bscnav_geom_t* g, int32_t n_query, int32_t k, int64_t n_rows_hint) {
+  if (mem_check_geom(g) || n_query <= 0 || k <= 0 || k > 1024) return BSCNAV_EINVAL;
+  return batch_layout(g, n_query, k, n_rows_hint, nullptr, nullptr);
+}
+
+int bscnav_query_topk_batch(const bscnav_geom_t* g, const bscnav_store_t* st, const void* shadow, const float* q, int32_t n_query,
+                            int32_t k, const bscnav_filter_t* filter, int64_t n_rows_hint, void* scratch, int64_t scratch_bytes,
+                            float* out_sim, int32_t* out_pos, int32_t* out_count, void* stream_) {
+  if (int e = mem_check_geom(g)) return e;
+  if (!st || !shadow || !q || !scratch || !out_sim || !out_pos || !out_count || n_query <= 0 || k <= 0 || k > 1024) return BSCNAV_EINVAL;
+  BatchScratch s;
+  if (batch_layout(g, n_query, k, n_rows_hint, &s, static_cast<char*>(scratch)) > scratch_bytes) return BSCNAV_EINVAL;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  bscnav_filter_t flt;
+  if (filter) flt = *filter; else { flt.radius2 = -1; flt.cur[0] = flt.cur[1] = flt.cur[2] = 0; flt.floor_min = 1; flt.floor_max = 0; flt.reserved = 0; }
+  const int D = g->dim, C = g->cache;
+  const long long N = batch_rows(g, n_rows_hint);                  // GEMM columns: token rows, a multiple of 256
+  const long long cap_rows = (long long)g->max_slots * C;
+  const int slot_blocks = (int)((N / C + kSelSlots - 1) / kSelSlots);
+  BSC_LAUNCH(k_row_ok, (unsigned)((cap_rows + kMemThreads - 1) / kMemThreads), kMemThreads, 0, stream, *g,
+             reinterpret_cast<const unsigned long long*>(st->row_key), st->slot_cell, st->tok_h, st->counters, flt, s.row_ok);
+  CUtensorMap map_w;
+  if (int e = make_operand_map(&map_w, shadow, N, D, gemm_block_n((int)N))) return e;
+  for (int q0 = 0; q0 < n_query; q0 += kPassQueries) {
+    const int P = n_query - q0 < kPassQueries ? n_query - q0 : kPassQueries;
+    const float* qp = q + (long long)q0 * D;
+    BSC_LAUNCH(k_prep_queries, (P + kMemThreads / 32 - 1) / (kMemThreads / 32), kMemThreads, 0, stream, qp, P, D, s.qh, s.qn2);
+    CUtensorMap map_a;
+    if (int e = make_operand_map(&map_a, s.qh, align_up(P, 128), D, 128)) return e;   // rows past P: never stored (M = P)
+    GemmEpilogue epi{};
+    epi.out = s.sims; epi.bias = nullptr; epi.table = nullptr; epi.ld_out = N; epi.mode = kOutFloat; epi.act = 0;
+    if (int e = gemm_f16_launch(&map_a, &map_w, nullptr, P, (int)N, D, epi, stream)) return e;
+    BSC_CUDA(cudaMemsetAsync(s.hist, 0, (size_t)P * kBins * 4, stream));
+    BSC_CUDA(cudaMemsetAsync(s.cand_count, 0, (size_t)P * 4, stream));
+    BSC_CUDA(cudaMemsetAsync(s.overflow, 0, (size_t)P * 4, stream));
+    BSC_CUDA(cudaMemsetAsync(s.keys, 0xFF, (size_t)P * kCandCap * 8, stream));       // BSCNAV_KEY_EMPTY
+    BSC_LAUNCH(k_batch_hist, dim3((unsigned)slot_blocks, (unsigned)P), kMemThreads, 0, stream, s.sims, N, s.row_ok, st->counters, C,
+               s.hist);
+    BSC_LAUNCH(k_batch_select, dim3((unsigned)slot_blocks, (unsigned)P), kMemThreads, 0, stream, s.sims, N, s.row_ok, st->counters,
+               C, s.hist, k, s.cand, s.cand_count, s.overflow);
+    BSC_LAUNCH(k_batch_rescore, dim3(16, (unsigned)P), kMemThreads, 0, stream, *g, st->feat, st->norm2, s.row_ok, st->slot_cell, qp,
+               s.qn2, s.cand, s.cand_count, s.overflow, s.keys);
+    if (int e = launch_topk_chunks(s.keys, kCandCap, nullptr, kCandCap, 1, P, s.sorted, k, k, stream)) return e;
+    if (int e = launch_topk_decode(g, st, s.sorted, k, k, qp, P, out_sim + (long long)q0 * k, out_pos + (long long)q0 * k * 3,
+                                   out_count + q0, stream)) return e;
+    BSC_LAUNCH(k_mark_overflow, (P + 255) / 256, 256, 0, stream, s.overflow, P, out_count + q0);
+  }
+  return BSCNAV_OK;
+}
+
+}  // extern "C"

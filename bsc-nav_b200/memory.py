@@ -286,8 +286,13 @@ class VoxelTokenMemory:
         return top_pos[0:1].copy(), top_pos, top_sim
 
     def voxel_localized_batch(self, queries, K=100, region_radius=np.inf, curr_grid=None):
-        """Batched form: queries (Q, D) -> device tensors (sims (Q,K), positions (Q,K,3), counts (Q,))."""
-        return self._store.query(self._query_vector(queries), k=K, region_radius=region_radius, curr_grid=curr_grid)
+        """Batched form: queries (Q, D) -> device tensors (sims (Q,K), positions (Q,K,3), counts (Q,)); the same values as Q
+        calls of voxel_localized, computed by the tensor-core candidate + exact re-scoring path (SpatialStore.query_batch)."""
+        floor = None
+        if getattr(self.args, "load_single_floor", False) and self.floor_min_height is not None:
+            floor = (self.floor_min_height, self.floor_max_height)
+        return self._store.query_batch(self._query_vector(queries), k=K, region_radius=region_radius, curr_grid=curr_grid,
+                                       floor_range=floor)
 
     def long_memory_filter(self):
         """memory_2.py:686-704."""

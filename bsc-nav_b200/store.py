@@ -76,6 +76,9 @@ class SpatialStore:
                                                                    self.feat, self.counters)])
         self._scratch = None
         self._qscratch = None
+        self._bscratch = None
+        self._shadow = None            # fp16 unit-normalised copy of the token rows (batched queries), built lazily
+        self._shadow_valid = False
         self.next_ordinal = 0
         # small pinned rings so the per-batch parameters (poses, ordinals) and result reads never block the host
         self._ring = [None] * 8
@@ -89,10 +92,12 @@ class SpatialStore:
     def reset(self):
         _lib.check(self.lib.bscnav_store_reset(C.byref(self.g), C.byref(self.st), _lib.stream_ptr()), "store_reset")
         self.next_ordinal = 0
+        self._shadow_valid = False
 
     def row_norms(self, n_rows: int):
         """Recompute norm2 of the first n_rows token rows on the device (used after loading rows from disk)."""
         _lib.check(self.lib.bscnav_store_row_norms(C.byref(self.g), C.byref(self.st), int(n_rows), _lib.stream_ptr()), "row_norms")
+        self._shadow_valid = False
 
     def _scratch_for(self, nbytes: int) -> torch.Tensor:
         if self._scratch is None or self._scratch.numel() < nbytes:
@@ -105,6 +110,7 @@ class SpatialStore:
         tokens (B, n_patch, D) f32 device; sample_idx (B, n_points) int32 device or None for dense raster order."""
         g = self.g
         B = depth.shape[0]
+        self._shadow_valid = False
         assert depth.dtype == torch.float32 and depth.is_cuda and depth.is_contiguous() and depth.shape[1:] == (g.height, g.width)
         assert tokens.dtype == torch.float32 and tokens.is_contiguous() and tokens.shape == (B, g.n_patch_h * g.n_patch_w, g.dim)
         n_points = g.height * g.width if sample_idx is None else sample_idx.shape[1]
@@ -175,12 +181,7 @@ class SpatialStore:
         q = q.to(self.device, torch.float32).contiguous()
         Q = q.shape[0]
         assert q.shape[1] == g.dim
-        flt = _lib.Filter(radius2=-1, floor_min=1, floor_max=0, reserved=0)
-        if region_radius != np.inf:
-            flt.radius2 = int(np.floor(float(region_radius) ** 2))   # d2 integer: d2 <= r^2  <=>  d2 <= floor(r^2)
-            flt.cur[:] = [int(v) for v in curr_grid]
-        if floor_range is not None:
-            flt.floor_min, flt.floor_max = int(floor_range[0]), int(floor_range[1])
+        flt = self._filter(region_radius, curr_grid, floor_range)
         nbytes = _lib.check(self.lib.bscnav_query_scratch_bytes(C.byref(g), Q, k), "query_scratch_bytes")
         if self._qscratch is None or self._qscratch.numel() < nbytes:
             self._qscratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
@@ -190,6 +191,54 @@ class SpatialStore:
         _lib.check(self.lib.bscnav_query_topk(C.byref(g), C.byref(self.st), _lib.ptr(q), Q, k, C.byref(flt),
                                               _lib.ptr(self._qscratch), nbytes, _lib.ptr(sims), _lib.ptr(pos), _lib.ptr(cnt),
                                               _lib.stream_ptr()), "query_topk")
+        return sims, pos, cnt
+
+    def _filter(self, region_radius, curr_grid, floor_range):
+        flt = _lib.Filter(radius2=-1, floor_min=1, floor_max=0, reserved=0)
+        if region_radius != np.inf:
+            flt.radius2 = int(np.floor(float(region_radius) ** 2))   # d2 integer: d2 <= r^2  <=>  d2 <= floor(r^2)
+            flt.cur[:] = [int(v) for v in curr_grid]
+        if floor_range is not None:
+            flt.floor_min, flt.floor_max = int(floor_range[0]), int(floor_range[1])
+        return flt
+
+    def invalidate_shadow(self):
+        """Call after writing token rows behind the store's back (tests, loaders)."""
+        self._shadow_valid = False
+
+    def query_batch(self, q: torch.Tensor, k: int = 100, region_radius=np.inf, curr_grid=None, floor_range=None, check: bool = True):
+        """Many queries per pass over the store: q (Q, D) -> the same (sims, positions, counts) as `query`, bit for bit.
+        Candidates come from a tcgen05 GEMM against an fp16 shadow of the rows, the result from exact fp32 re-scoring
+        (csrc/query_batch.cu).  With check=True (default) the call synchronises once to read the slot count (bounds the GEMM
+        to the used rows) and to re-issue, through the exact path, any query the batch path flagged (count -1)."""
+        g = self.g
+        q = q.to(self.device, torch.float32).contiguous()
+        Q = q.shape[0]
+        assert q.shape[1] == g.dim
+        if self._shadow is None:
+            nbytes = _lib.check(self.lib.bscnav_shadow_bytes(C.byref(g)), "shadow_bytes")
+            self._shadow = torch.zeros(nbytes // 2, dtype=torch.float16, device=self.device)
+        if not self._shadow_valid:
+            _lib.check(self.lib.bscnav_store_build_shadow(C.byref(g), C.byref(self.st), _lib.ptr(self._shadow), _lib.stream_ptr()),
+                       "build_shadow")
+            self._shadow_valid = True
+        hint = self.count() * g.cache if check else 0
+        flt = self._filter(region_radius, curr_grid, floor_range)
+        nbytes = _lib.check(self.lib.bscnav_query_batch_scratch_bytes(C.byref(g), Q, k, hint), "query_batch_scratch_bytes")
+        if self._bscratch is None or self._bscratch.numel() < nbytes:
+            self._bscratch = None
+            self._bscratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        sims = torch.empty(Q, k, dtype=torch.float32, device=self.device)
+        pos = torch.empty(Q, k, 3, dtype=torch.int32, device=self.device)
+        cnt = torch.empty(Q, dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.bscnav_query_topk_batch(C.byref(g), C.byref(self.st), _lib.ptr(self._shadow), _lib.ptr(q), Q, k,
+                                                    C.byref(flt), hint, _lib.ptr(self._bscratch), nbytes, _lib.ptr(sims),
+                                                    _lib.ptr(pos), _lib.ptr(cnt), _lib.stream_ptr()), "query_topk_batch")
+        if check:
+            flagged = (cnt < 0).nonzero().flatten().tolist()
+            for i in flagged:                       # candidate set too large for the batch path: exact path for this query
+                s1, p1, c1 = self.query(q[i:i + 1], k=k, region_radius=region_radius, curr_grid=curr_grid, floor_range=floor_range)
+                sims[i], pos[i], cnt[i] = s1[0], p1[0], c1[0]
         return sims, pos, cnt
 
     # ------------------------------------------------------------------ multi-GPU deltas
@@ -209,6 +258,7 @@ class SpatialStore:
         return d_cell, d_key, d_h, d_feat, n
 
     def merge_delta(self, d_cell, d_key, d_h, d_feat):
+        self._shadow_valid = False
         n = d_cell.numel()
         chunk = 1 << 20
         for s in range(0, n, chunk):

@@ -119,6 +119,23 @@ int bscnav_query_topk(const bscnav_geom_t* g, const bscnav_store_t* st, const fl
                       const bscnav_filter_t* filter, void* scratch, int64_t scratch_bytes,
                       float* out_sim, int32_t* out_pos, int32_t* out_count, void* stream);
 
+/* Batched queries: the same result as bscnav_query_topk (bit-identical similarities and positions) for many queries per
+ * pass over the store.  Candidates come from a tensor-core GEMM against a unit-normalised fp16 shadow of the token rows
+ * (error bound 1.1e-3 on the cosine), are widened by a safety margin that provably contains the exact top-K, and are
+ * re-scored with the exact fp32 arithmetic (csrc/query_batch.cu).
+ *   shadow       half[align(max_slots*cache, 256) * dim], caller-owned; (re)build it with bscnav_store_build_shadow after the
+ *                store changed (fuse / merge / load) and before querying
+ *   n_rows_hint  upper bound on slots_in_use * cache known to the host (limits the GEMM to the used part of the store),
+ *                or 0 for the full capacity
+ *   out_count[i] = -1 flags a query whose candidate set exceeded the internal capacity (thousands of cells within 4e-3 of
+ *                its K-th similarity): re-issue that query through bscnav_query_topk. */
+int64_t bscnav_shadow_bytes(const bscnav_geom_t* g);
+int bscnav_store_build_shadow(const bscnav_geom_t* g, const bscnav_store_t* st, void* shadow, void* stream);
+int64_t bscnav_query_batch_scratch_bytes(const bscnav_geom_t* g, int32_t n_query, int32_t k, int64_t n_rows_hint);
+int bscnav_query_topk_batch(const bscnav_geom_t* g, const bscnav_store_t* st, const void* shadow, const float* q,
+                            int32_t n_query, int32_t k, const bscnav_filter_t* filter, int64_t n_rows_hint, void* scratch,
+                            int64_t scratch_bytes, float* out_sim, int32_t* out_pos, int32_t* out_count, void* stream);
+
 /* Merge compacted deltas (e.g. all-gathered from other ranks) into the store under the same winner rule.
  *   d_cell int32[n], d_key uint64[n], d_h int32[n], d_feat float[n*D]; entries with d_cell < 0 are skipped.
  * Slot numbering of cells first seen through a merge follows delta order. */

@@ -145,9 +145,25 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------- query leg (BASELINE configs[2])
-def query_leg(store, dev, peak_gbs):
-    """Goal queries over a fully occupied 512x512 grid (262 144 stored tokens, D=1024, K=100): per-query latency (Q=1)
-    and batched throughput (8 queries per pass).  HBM-bound: algorithmic bytes = N_tok*(D*4+4) per pass."""
+def cpu_query_rate(n_slots: int, n_queries: int = 2):
+    """The reference's query arithmetic on the host (oracle port of memory_2.py:642-671: per-voxel cosine, max, sort, top-K)
+    over a bounded sample of `n_slots` stored tokens; returns seconds per query per stored token."""
+    from oracle import memory_port as mp
+    rng = np.random.default_rng(7)
+    feats = rng.standard_normal((n_slots, D), dtype=np.float32)
+    keys = np.stack([np.arange(n_slots) // GS, np.arange(n_slots) % GS, np.full(n_slots, 100)], axis=1)
+    slot_feats = [feats[i:i + 1] for i in range(n_slots)]
+    q = rng.standard_normal((n_queries, D), dtype=np.float32)
+    t0 = time.perf_counter()
+    for i in range(n_queries):
+        mp.query_topk(keys, slot_feats, q[i:i + 1], K=100)
+    return (time.perf_counter() - t0) / n_queries / n_slots
+
+
+def query_leg(store, dev, peak_gbs, with_cpu):
+    """Goal queries over a fully occupied 512x512 grid (262 144 stored tokens, D=1024, K=100), BASELINE configs[2]/[3]:
+    one query at a time (exact fp32 scan, HBM-bound: algorithmic bytes = N_tok*(D*4+4) per pass), and batches of 256 / 2048
+    queries through the tensor-core candidate + exact re-scoring path (results bit-identical to the single-query path)."""
     g = store.g
     n = g.gs * g.gs
     gen = torch.Generator(device=dev).manual_seed(7)
@@ -157,25 +173,65 @@ def query_leg(store, dev, peak_gbs):
     store.row_key[:n].zero_()
     store.slot_keys[:n].zero_()
     store.tok_h[:n].fill_(100)
-    store.norm2[:n] = (store.feat[:n] ** 2).sum(1)
+    store.row_norms(n)
     store.counters[0] = n
-    q = torch.randn(64, g.dim, device=dev, generator=torch.Generator(device=dev).manual_seed(11))
+    q = torch.randn(2048, g.dim, device=dev, generator=torch.Generator(device=dev).manual_seed(11))
+    q_host = q.cpu().pin_memory()
     out = {}
-    for name, Q, reps in (("single", 1, 40), ("batch8", 8, 20)):
+
+    def timed(fn, reps):
         for _ in range(3):
-            store.query(q[:Q], k=100)
+            fn(0)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for r in range(reps):
-            store.query(q[(r * Q) % 56:(r * Q) % 56 + Q], k=100)
+            fn(r)
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
-        gbs = n * (g.dim * 4 + 4) / (ms / 1e3) / 1e9
-        out[name] = {"queries_per_s": Q / (ms / 1e3), "ms_per_pass": ms, "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peak_gbs}
-    out["workload"] = "BASELINE configs[2] shape: 262144 stored tokens (512x512 grid fully occupied, C=1, D=1024), K=100, cosine + top-K"
+        return e0.elapsed_time(e1) / reps
+
+    ms = timed(lambda r: store.query(q[r % 64:r % 64 + 1], k=100), 40)
+    gbs = n * (g.dim * 4 + 4) / (ms / 1e3) / 1e9
+    out["single"] = {"queries_per_s": 1e3 / ms, "ms_per_pass": ms, "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peak_gbs,
+                     "path": "k_query_slots (exact fp32 scan) + bitonic top-K"}
+    for name, Q, reps in (("batch256", 256, 20), ("batch2048", 2048, 5)):
+        ms = timed(lambda r: store.query_batch(q[:Q], k=100, check=False), reps)
+        # shadow rows (fp16) read once per 256-query pass, similarity matrix written once and read twice
+        passes = (Q + 255) // 256
+        alg = passes * n * g.dim * 2 + 3 * Q * n * 4
+        out[name] = {"queries_per_s": Q / (ms / 1e3), "ms_per_call": ms, "algorithmic_GBps": alg / (ms / 1e3) / 1e9,
+                     "frac_of_hbm_peak": alg / (ms / 1e3) / 1e9 / peak_gbs,
+                     "path": "tcgen05 candidate GEMM (fp16 shadow) + histogram select + exact fp32 re-score; device-resident queries"}
+
+    def e2e_call(r):        # host queries in (pinned), host results out: the call a user of voxel_localized_batch makes
+        qd = q_host[:256].to(dev, non_blocking=True)
+        sims, pos, cnt = store.query_batch(qd, k=100, check=False)
+        return sims.cpu(), pos.cpu(), cnt.cpu()
+    ms = timed(e2e_call, 10)
+    out["batch256_e2e"] = {"queries_per_s": 256 / (ms / 1e3), "ms_per_call": ms, "h2d_bytes": 256 * g.dim * 4,
+                           "d2h_bytes": 256 * 100 * 16 + 256 * 4}
+    if with_cpu:
+        sample = 20000
+        per = cpu_query_rate(sample)
+        out["cpu_baseline"] = {"queries_per_s": 1.0 / (per * n), "cores": 1, "kind": "port",
+                               "sample": f"oracle port of voxel_localized over {sample} of {n} stored tokens, scaled linearly"}
+    out["workload"] = "BASELINE configs[2]/[3] shape: 262144 stored tokens (512x512 grid fully occupied, C=1, D=1024), K=100, cosine + top-K"
     return out
+
+
+def gemm_traffic():
+    """Mean DRAM traffic per k_gemm_f16 launch of a step, from the committed ncu --set full capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        d = json.load(f)
+    per = {l["kernel"].split()[0]: l["traffic_bytes"] for l in d["launches"]}
+    try:   # one layer = qkv + proj + fc1 + fc2
+        return float(per["qkv"] + per["proj"] + per["fc1"] + per["fc2"]) / 4.0
+    except KeyError:
+        return None
 
 
 # ---------------------------------------------------------------------------------------------- our arm
@@ -272,7 +328,9 @@ def run_ours(args):
     achieved = g_flops / (g_ms / 1e3) / 1e12
     step_ms_prof = sum(v[0] for v in prof.values()) / 2
     roofline = {"bound": "tensor", "kernel": "k_gemm_f16 (tcgen05, fp16 x fp16 -> fp32)", "achieved": achieved, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": gemm_traffic(),
+                "traffic_source": "profiles/r01_gemm_traffic.json (ncu --set full, mean over the four GEMM shapes of a layer, B=55)",
+                "peak_source": peak_src,
                 "launches_per_step": g_n // 2, "share_of_step": (g_ms / 2) / (ms / K),
                 "breakdown_ms_per_step": {k: v[0] / 2 for k, v in prof.items()},
                 "attention_tflops": prof["attention"][1] / (prof["attention"][0] / 1e3) / 1e12 if prof["attention"][0] else None}
@@ -296,7 +354,7 @@ def run_ours(args):
            "h2d_bytes_per_step": B * (H * W * 4 + H * W * 4 + 16 * 8 + 4), "d2h_bytes_per_step": 8,
            "api": "VoxelTokenMemory.fuse_frames + max_id_async (copies overlap the previous batch)", "slots_after": counts[-1]}
 
-    query = query_leg(store, dev, peak_gbs) if rank == 0 else None
+    query = query_leg(store, dev, peak_gbs, with_cpu=(world == 1)) if rank == 0 else None
 
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -63,6 +63,7 @@ _SIGS = {
     "bscnav_query_batch_scratch_bytes": (C.c_int64, [C.POINTER(Geom), C.c_int32, C.c_int32, C.c_int64]),
     "bscnav_query_topk_batch": (C.c_int, [C.POINTER(Geom), C.POINTER(Store), _P, _P, C.c_int32, C.c_int32, C.POINTER(Filter),
                                           C.c_int64, _P, C.c_int64, _P, _P, _P, _P]),
+    "bscnav_cluster_centers": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "bscnav_merge_delta": (C.c_int, [C.POINTER(Geom), C.POINTER(Store), _P, _P, _P, _P, C.c_int32, _P, C.c_int64, _P]),
     "bscnav_export_scratch_bytes": (C.c_int64, [C.POINTER(Geom)]),
     "bscnav_export_delta": (C.c_int, [C.POINTER(Geom), C.POINTER(Store), C.c_uint32, C.c_uint32, _P, _P, _P, _P, C.c_int32,

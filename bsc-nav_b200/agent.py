@@ -41,15 +41,22 @@ class GESObjectNavRobot:
 
     # -- BSCAgent.py:479-497
     def weighted_cluster_centers(self, top_k_positions, top_k_similarity, eps=10, min_samples=5):
-        from sklearn.cluster import DBSCAN
-        labels = DBSCAN(eps=eps, min_samples=min_samples).fit_predict(top_k_positions)
-        cluster_info = []
-        for lbl in [l for l in set(labels) if l != -1]:
-            m = labels == lbl
-            cluster_info.append((np.mean(top_k_similarity[m]),
-                                 np.average(top_k_positions[m], axis=0, weights=top_k_similarity[m]), np.sum(m)))
-        cluster_info.sort(key=lambda x: x[0], reverse=True)
-        return np.array([c[1] for c in cluster_info]), labels, [c[2] for c in cluster_info]
+        """Same signature and return values as the reference (host arrays in and out); DBSCAN, the weighted centres and the
+        ordering run in bscnav_cluster_centers on the device (csrc/cluster.cu) -- no scikit-learn on the product path."""
+        import torch
+        pos = np.asarray(top_k_positions).reshape(-1, 3)
+        sim = np.asarray(top_k_similarity, dtype=np.float32).reshape(-1)
+        n = len(sim)
+        if n == 0:
+            return np.zeros((0,)), np.zeros((0,), dtype=np.int64), []
+        store = self.memory.store
+        dev = store.device
+        out = store.cluster_centers(torch.from_numpy(sim).to(dev)[None], torch.from_numpy(pos.astype(np.int32)).to(dev)[None],
+                                    torch.tensor([n], dtype=torch.int32, device=dev), eps=eps, min_samples=min_samples,
+                                    max_clusters=max(1, min(n, 256)))
+        centers, _mean, sizes, labels, n_c = (t[0].cpu().numpy() for t in out)
+        n_c = int(n_c)
+        return centers[:n_c].copy(), labels.astype(np.int64), [int(v) for v in sizes[:n_c]]
 
     # -- BSCAgent.py:587-664
     def working_memory_retrival(self, prompts, vis_aug=False, text_aug=True, region_radius=np.inf, curr_grid=None):

@@ -1,4 +1,5 @@
 // tcgen05 / TMEM / TMA GEMM for sm_100a -- see gemm_tcgen05.cuh for the design.
+#include <cstdlib>
 #include "gemm_tcgen05.cuh"
 #include "tc_ptx.cuh"
 
@@ -33,7 +34,11 @@ template <int ACT> __device__ __forceinline__ float act_fn(float v) {
   return v * r;
 }
 
-template <int BN, int MODE, int ACT>
+// CL = 2: two CTAs of a cluster work on vertically adjacent output tiles (same weight panel).  Each loads its own A tile
+// and HALF of the shared B tile, multicast into both CTAs' shared memory: 32 KB instead of 48 KB enter each SM per k-block.
+// At full MMA rate a 128 x 256 x 64 k-block lasts 512 cycles, i.e. 148 SMs x 48 KB / 512 cycles = 26 TB/s of operand
+// traffic out of L2 -- more than L2 delivers (the tensor pipe measured 70 % active); multicast brings it to 17 TB/s.
+template <int BN, int MODE, int ACT, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
            const __grid_constant__ CUtensorMap map_out, int M, int N, int K, const GemmEpilogue epi) {
@@ -50,14 +55,17 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (M + BM - 1) / BM, n_tiles = N / BN, k_blocks = K / BK;
-  const int total_tiles = m_tiles * n_tiles;
+  const int m_groups = (m_tiles + CL - 1) / CL;             // CL == 2: pairs of row blocks (the last pair may be half empty)
+  const int total_tiles = m_groups * n_tiles;
+  const int rank = CL == 2 ? (int)cluster_ctarank() : 0;
+  const int tile0 = blockIdx.x / CL, tile_step = gridDim.x / CL;
   // Tile order.  m-fastest: the ~148 resident tiles share one weight panel (good when A fits L2, K <= N).
   // n-fastest: the n_tiles tiles of one row block run side by side and share the A panel, so a long-K activation
   // matrix (fc2: 116 MB) streams from HBM once instead of once per weight panel (measured 413 MB -> A-size reads).
   const bool n_fastest = K > N;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::kStages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, CL); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, 32 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -69,6 +77,7 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();        // the peer's barriers are initialised before anything is multicast to them
   tcgen05_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
@@ -77,15 +86,18 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_blk = n_fastest ? tile / n_tiles : tile % m_tiles, n_blk = n_fastest ? tile % n_tiles : tile / m_tiles;
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+        const int m_blk = (n_fastest ? tile / n_tiles : tile % m_groups) * CL + rank, n_blk = n_fastest ? tile % n_tiles : tile / m_groups;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);       // CL == 2: both CTAs' MMAs have read this stage
           const uint32_t a_dst = smem_base + stage * C::kStageBytes;
           const uint32_t b_dst = a_dst + C::kABytes;
           mbar_arrive_expect_tx(full_bar + 8 * stage, C::kStageBytes);
-          tma_load_2d(a_dst, &map_a, full_bar + 8 * stage, kb * BK, m_blk * BM);
-          tma_load_2d(b_dst, &map_w, full_bar + 8 * stage, kb * BK, n_blk * BN);
+          tma_load_2d(a_dst, &map_a, full_bar + 8 * stage, kb * BK, m_blk * BM);     // rows past M arrive as zeros
+          if (CL == 2)      // map_w has a BN/2-row box here: my half of the panel, into both CTAs
+            tma_load_2d_multicast(b_dst + rank * (C::kBBytes / 2), &map_w, full_bar + 8 * stage, kb * BK, n_blk * BN + rank * (BN / 2), 3);
+          else
+            tma_load_2d(b_dst, &map_w, full_bar + 8 * stage, kb * BK, n_blk * BN);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -98,7 +110,7 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -113,7 +125,8 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
             // advance 32 bytes (16 fp16) inside the swizzle atom: +2 in the (addr >> 4) field
             tcgen05_mma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          tcgen05_commit(empty_bar + 8 * stage);        // smem stage reusable once these MMAs have read it
+          if (CL == 2) tcgen05_commit_multicast(empty_bar + 8 * stage, 3);   // the stage is refilled by both CTAs' producers
+          else tcgen05_commit(empty_bar + 8 * stage);   // smem stage reusable once these MMAs have read it
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
         tcgen05_commit(tfull_bar + 8 * acc);             // accumulator complete -> epilogue
@@ -140,8 +153,8 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     const int sw = lane & 7;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_blk = n_fastest ? tile / n_tiles : tile % m_tiles, n_blk = n_fastest ? tile % n_tiles : tile / m_tiles;
+    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+      const int m_blk = (n_fastest ? tile / n_tiles : tile % m_groups) * CL + rank, n_blk = n_fastest ? tile % n_tiles : tile / m_groups;
       const int m0 = m_blk * BM + quarter * 32;
       const int m = m0 + lane;
       const bool in_m = m < M;
@@ -237,6 +250,7 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
 
   tcgen05_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();        // no CTA leaves while its peer may still multicast into it or arrive on its barriers
   if (warp == kMmaWarp) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::kTmemCols) : "memory");
@@ -322,43 +336,77 @@ static int sm_count() {
   return n;
 }
 
+static int max_cluster_pairs(const void* fn, int smem) {
+  // how many 2-CTA clusters of this kernel the device runs at once (GPCs with an odd SM count leave one SM unpaired)
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * 74); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = sm_count() / 2; }
+  return n < sm_count() / 2 ? n : sm_count() / 2;
+}
+
 template <int BN, int MODE, int ACT = 0>
-static int launch_bn_mode(const CUtensorMap* map_a, const CUtensorMap* map_w, const CUtensorMap* map_out, int M, int N, int K,
-                          const GemmEpilogue& epi, cudaStream_t stream) {
+static int launch_bn_mode(const CUtensorMap* map_a, const CUtensorMap* map_w, const CUtensorMap* map_w_half, const CUtensorMap* map_out,
+                          int M, int N, int K, const GemmEpilogue& epi, cudaStream_t stream) {
   static bool attr_set = false;
+  static int pairs = 0;
   if (!attr_set) {
-    BSC_CUDA(cudaFuncSetAttribute((k_gemm_f16<BN, MODE, ACT>), cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem));
+    BSC_CUDA(cudaFuncSetAttribute((k_gemm_f16<BN, MODE, ACT, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem));
+    BSC_CUDA(cudaFuncSetAttribute((k_gemm_f16<BN, MODE, ACT, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem));
+    pairs = max_cluster_pairs(reinterpret_cast<const void*>(k_gemm_f16<BN, MODE, ACT, 2>), Cfg<BN>::kSmem);
     attr_set = true;
   }
-  const int tiles = ((M + BM - 1) / BM) * (N / BN);
+  const int m_tiles = (M + BM - 1) / BM, n_tiles = N / BN;
+  if (map_w_half && m_tiles >= 2 && pairs > 0) {
+    // cluster variant: pairs of row blocks; persistent over `pairs` clusters
+    const int groups = ((m_tiles + 1) / 2) * n_tiles;
+    const int clusters = groups < pairs ? groups : pairs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = Cfg<BN>::kSmem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    BSC_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_f16<BN, MODE, ACT, 2>, *map_a, *map_w_half, *map_out, M, N, K, epi));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return BSCNAV_OK;
+  }
+  const int tiles = m_tiles * n_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  BSC_LAUNCH((k_gemm_f16<BN, MODE, ACT>), grid, kGemmThreads, Cfg<BN>::kSmem, stream, *map_a, *map_w, *map_out, M, N, K, epi);
+  BSC_LAUNCH((k_gemm_f16<BN, MODE, ACT, 1>), grid, kGemmThreads, Cfg<BN>::kSmem, stream, *map_a, *map_w, *map_out, M, N, K, epi);
   return BSCNAV_OK;
 }
 
 template <int BN>
-static int launch_bn(const CUtensorMap* map_a, const CUtensorMap* map_w, const CUtensorMap* map_out, int M, int N, int K,
-                     const GemmEpilogue& epi, cudaStream_t stream) {
+static int launch_bn(const CUtensorMap* map_a, const CUtensorMap* map_w, const CUtensorMap* map_w_half, const CUtensorMap* map_out,
+                     int M, int N, int K, const GemmEpilogue& epi, cudaStream_t stream) {
   switch (epi.mode) {
-    case kOutHalf: return launch_bn_mode<BN, kOutHalf>(map_a, map_w, map_out, M, N, K, epi, stream);
+    case kOutHalf: return launch_bn_mode<BN, kOutHalf>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream);
     case kOutHalfAct:
-      if (epi.act == 0) return launch_bn_mode<BN, kOutHalfAct, 0>(map_a, map_w, map_out, M, N, K, epi, stream);
-      return launch_bn_mode<BN, kOutHalfAct, 1>(map_a, map_w, map_out, M, N, K, epi, stream);
-    case kOutResidual: return launch_bn_mode<BN, kOutResidual>(map_a, map_w, map_out, M, N, K, epi, stream);
-    case kOutPatchEmbed: return launch_bn_mode<BN, kOutPatchEmbed>(map_a, map_w, map_out, M, N, K, epi, stream);
-    case kOutFloat: return launch_bn_mode<BN, kOutFloat>(map_a, map_w, map_out, M, N, K, epi, stream);
+      if (epi.act == 0) return launch_bn_mode<BN, kOutHalfAct, 0>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream);
+      return launch_bn_mode<BN, kOutHalfAct, 1>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream);
+    case kOutResidual: return launch_bn_mode<BN, kOutResidual>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream);
+    case kOutPatchEmbed: return launch_bn_mode<BN, kOutPatchEmbed>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream);
+    case kOutFloat: return launch_bn_mode<BN, kOutFloat>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream);
     default: return BSCNAV_EINVAL;
   }
 }
 
 int gemm_f16_launch(const CUtensorMap* map_a, const CUtensorMap* map_w, const CUtensorMap* map_out, int M, int N, int K,
-                    const GemmEpilogue& epi, cudaStream_t stream) {
+                    const GemmEpilogue& epi, cudaStream_t stream, const CUtensorMap* map_w_half) {
   if (M <= 0 || N <= 0 || K <= 0 || N % 128 != 0 || K % BK != 0 || !epi.out) return BSCNAV_EINVAL;
   const bool via_tma = epi.mode == kOutHalf || epi.mode == kOutHalfAct || epi.mode == kOutResidual;
   if (via_tma && !map_out) return BSCNAV_EINVAL;
   if (!map_out) map_out = map_a;       // unused by the direct-store epilogues
-  if (gemm_block_n(N) == 256) return launch_bn<256>(map_a, map_w, map_out, M, N, K, epi, stream);
-  return launch_bn<128>(map_a, map_w, map_out, M, N, K, epi, stream);
+  static int use_cluster = -1;
+  if (use_cluster < 0) { const char* e = getenv("BSCNAV_GEMM_CLUSTER"); use_cluster = e ? atoi(e) : 0; }
+  if (!use_cluster) map_w_half = nullptr;
+  if (gemm_block_n(N) == 256) return launch_bn<256>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream);
+  return launch_bn<128>(map_a, map_w, nullptr, map_out, M, N, K, epi, stream);
 }
 
 }  // namespace bscnav
@@ -372,10 +420,13 @@ extern "C" int bscnav_gemm_f16(const void* a, const void* w, const float* bias, 
   CUtensorMap ma, mw, mo;
   if (int e = make_operand_map(&ma, a, m, k, BM)) return e;
   if (int e = make_operand_map(&mw, w, n, k, gemm_block_n(n))) return e;
+  CUtensorMap mwh;
+  const bool half_ok = gemm_block_n(n) == 256;
+  if (half_ok) if (int e = make_operand_map(&mwh, w, n, k, 128)) return e;
   const bool via_tma = out_mode != kOutFloat;
   if (via_tma)
     if (int e = make_store_map(&mo, out, m, n, out_mode == kOutResidual)) return e;
   GemmEpilogue epi{};
   epi.out = out; epi.bias = bias; epi.table = nullptr; epi.ld_out = n; epi.mode = out_mode; epi.act = act;
-  return gemm_f16_launch(&ma, &mw, via_tma ? &mo : nullptr, m, n, k, epi, (cudaStream_t)stream);
+  return gemm_f16_launch(&ma, &mw, via_tma ? &mo : nullptr, m, n, k, epi, (cudaStream_t)stream, half_ok ? &mwh : nullptr);
 }

@@ -34,8 +34,10 @@ struct GemmEpilogue {
 };
 
 // map_out: store map of the output tensor (make_store_map) for the fp16 / residual epilogues; null for the others
+// map_w_half: the same weight matrix with a 128-row box (make_operand_map(..., 128)); when given (and N % 256 == 0, at least
+// two row blocks) the 2-CTA cluster variant runs: each CTA loads half of the weight tile and multicasts it to its peer
 int gemm_f16_launch(const CUtensorMap* map_a, const CUtensorMap* map_w, const CUtensorMap* map_out, int M, int N, int K,
-                    const GemmEpilogue& epi, cudaStream_t stream);
+                    const GemmEpilogue& epi, cudaStream_t stream, const CUtensorMap* map_w_half = nullptr);
 int make_store_map(CUtensorMap* map, const void* ptr, long long rows, long long N, bool is_float);
 
 // 2-D K-major fp16 operand [rows, K] -> tensor map with box {64, box_rows}, 128-byte swizzle

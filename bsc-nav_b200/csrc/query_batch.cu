@@ -29,7 +29,7 @@ namespace bscnav {
 static constexpr int kBins = 2048;
 static constexpr int kCandCap = kTopkChunk;
 static constexpr int kMarginBins = 3;
-static constexpr int kSelSlots = 2048;      // cells per block in the histogram / select passes
+static constexpr int kSelSlots = 8192;      // cells per block in the histogram / select passes (256 threads x 8 x 4)
 static constexpr int kPassQueries = 256;    // queries per GEMM pass
 
 __device__ __forceinline__ int sim_bin(float s) {
@@ -115,6 +115,50 @@ __device__ __forceinline__ float approx_cell(const float* __restrict__ sims_q, c
   return best;
 }
 
+// Visit every participating cell of the block's chunk [slot0, slot0 + kSelSlots): f(slot, per-cell max of approx).
+// C == 1 (the 512 x 512 BEV grid): each thread owns groups of four consecutive cells and issues all of its 128-bit
+// similarity loads and 32-bit flag loads before using any of them (the passes are latency-bound otherwise: measured
+// 219 us -> see profiles/); other C: plain loop.
+template <typename F>
+__device__ __forceinline__ void visit_chunk(const float* __restrict__ sims_q, const uint8_t* __restrict__ row_ok, int slot0, int n_slots,
+                                            int C, F f) {
+  if (C == 1) {
+    constexpr int kIter = kSelSlots / (kMemThreads * 4);
+    float4 v[kIter];
+    uint32_t ok[kIter];
+#pragma unroll
+    for (int i = 0; i < kIter; ++i) {
+      const int s = slot0 + (i * kMemThreads + threadIdx.x) * 4;
+      if (s + 3 < n_slots) {             // slot0 and the row stride are multiples of 4: both loads are aligned
+        v[i] = ld_stream_f4(reinterpret_cast<const float4*>(sims_q + s));
+        ok[i] = *reinterpret_cast<const uint32_t*>(row_ok + s);
+      } else {
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+        ok[i] = 0;
+        for (int e = 0; e < 4; ++e)
+          if (s + e < n_slots && row_ok[s + e]) { t[e] = sims_q[s + e]; ok[i] |= 1u << (8 * e); }
+        v[i] = make_float4(t[0], t[1], t[2], t[3]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kIter; ++i) {
+      const int s = slot0 + (i * kMemThreads + threadIdx.x) * 4;
+      if (ok[i] & 0x000000FFu) f(s, v[i].x);
+      if (ok[i] & 0x0000FF00u) f(s + 1, v[i].y);
+      if (ok[i] & 0x00FF0000u) f(s + 2, v[i].z);
+      if (ok[i] & 0xFF000000u) f(s + 3, v[i].w);
+    }
+  } else {
+    for (int i = threadIdx.x; i < kSelSlots; i += kMemThreads) {
+      const int slot = slot0 + i;
+      if (slot < n_slots) {
+        const float sv = approx_cell(sims_q, row_ok, slot, C);
+        if (sv > -INFINITY) f(slot, sv);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kMemThreads)
 k_batch_hist(const float* __restrict__ sims, long long ld, const uint8_t* __restrict__ row_ok, const int32_t* __restrict__ counters,
              int C, uint32_t* __restrict__ hist) {
@@ -125,14 +169,9 @@ k_batch_hist(const float* __restrict__ sims, long long ld, const uint8_t* __rest
   if (slot0 >= n_slots) return;
   for (int b = threadIdx.x; b < kBins; b += kMemThreads) h[b] = 0;
   __syncthreads();
-  const float* sq = sims + (long long)qi * ld;
-  for (int i = threadIdx.x; i < kSelSlots; i += kMemThreads) {
-    const int slot = slot0 + i;
-    if (slot < n_slots) {
-      const float s = approx_cell(sq, row_ok, slot, C);
-      if (s > -INFINITY) atomicAdd(&h[sim_bin(s)], 1u);
-    }
-  }
+  visit_chunk(sims + (long long)qi * ld, row_ok, slot0, n_slots, C, [&](int, float sv) {
+    if (sv == sv) atomicAdd(&h[sim_bin(sv)], 1u);          // NaN similarities take no part (fmaxf drops them in the exact path)
+  });
   __syncthreads();
   for (int b = threadIdx.x; b < kBins; b += kMemThreads)
     if (h[b]) atomicAdd(&hist[(long long)qi * kBins + b], h[b]);
@@ -193,17 +232,12 @@ k_batch_select(const float* __restrict__ sims, long long ld, const uint8_t* __re
     if (blockIdx.x == 0 && tid == 0) overflow[qi] = (int32_t)s_ncand;
     return;
   }
-  const float* sq = sims + (long long)qi * ld;
-  for (int i = tid; i < kSelSlots; i += kMemThreads) {
-    const int slot = slot0 + i;
-    if (slot < n_slots) {
-      const float s = approx_cell(sq, row_ok, slot, C);
-      if (s > -INFINITY && sim_bin(s) >= t) {
-        const int pos = atomicAdd(&cand_count[qi], 1);
-        if (pos < kCandCap) cand[(long long)qi * kCandCap + pos] = slot;
-      }
+  visit_chunk(sims + (long long)qi * ld, row_ok, slot0, n_slots, C, [&](int slot, float sv) {
+    if (sv == sv && sim_bin(sv) >= t) {
+      const int pos = atomicAdd(&cand_count[qi], 1);
+      if (pos < kCandCap) cand[(long long)qi * kCandCap + pos] = slot;
     }
-  }
+  });
 }
 
 // exact fp32 cosine of every candidate cell, arithmetic identical to k_query_slots; one warp per candidate
@@ -237,6 +271,33 @@ k_batch_rescore(const bscnav_geom_t g, const float* __restrict__ feat, const flo
     if (lane == 0 && best > -INFINITY)
       keys[(long long)qi * kCandCap + idx] = ((unsigned long long)(~orderable(best)) << 32) | (uint32_t)slot_cell[slot];
   }
+}
+
+// ascending sort of one query's candidate keys (at most kCandCap, usually a few hundred): bitonic network over the next
+// power of two above the candidate count instead of the full 4096 the shared chunk sorter always sorts
+__global__ void __launch_bounds__(1024)
+k_sort_candidates(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ cand_count,
+                  const int32_t* __restrict__ overflow, int k, unsigned long long* __restrict__ sorted) {
+  __shared__ unsigned long long s[kCandCap];
+  const int qi = blockIdx.x;
+  const int n = overflow[qi] ? 0 : min(cand_count[qi], kCandCap);
+  int S = 32;
+  while (S < n) S <<= 1;
+  for (int i = threadIdx.x; i < S; i += 1024) s[i] = i < n ? keys[(long long)qi * kCandCap + i] : BSCNAV_KEY_EMPTY;
+  __syncthreads();
+  for (int size = 2; size <= S; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < S / 2; t += 1024) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const unsigned long long a = s[lo], b = s[hi];
+        if ((a > b) == up) { s[lo] = b; s[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < k; i += 1024) sorted[(long long)qi * k + i] = i < S ? s[i] : BSCNAV_KEY_EMPTY;
 }
 
 __global__ void k_mark_overflow(const int32_t* __restrict__ overflow, int n_query, int32_t* __restrict__ out_count) {
@@ -332,7 +393,7 @@ int bscnav_query_topk_batch(const bscnav_geom_t* g, const bscnav_store_t* st, co
                C, s.hist, k, s.cand, s.cand_count, s.overflow);
     BSC_LAUNCH(k_batch_rescore, dim3(16, (unsigned)P), kMemThreads, 0, stream, *g, st->feat, st->norm2, s.row_ok, st->slot_cell, qp,
                s.qn2, s.cand, s.cand_count, s.overflow, s.keys);
-    if (int e = launch_topk_chunks(s.keys, kCandCap, nullptr, kCandCap, 1, P, s.sorted, k, k, stream)) return e;
+    BSC_LAUNCH(k_sort_candidates, (unsigned)P, 1024, 0, stream, s.keys, s.cand_count, s.overflow, k, s.sorted);
     if (int e = launch_topk_decode(g, st, s.sorted, k, k, qp, P, out_sim + (long long)q0 * k, out_pos + (long long)q0 * k * 3,
                                    out_count + q0, stream)) return e;
     BSC_LAUNCH(k_mark_overflow, (P + 255) / 256, 256, 0, stream, s.overflow, P, out_count + q0);

@@ -89,6 +89,8 @@ struct VitEngine {
   CUtensorMap qkv3d128, qkv3d16;                     // the same tensor as {column, token, frame} (attention_ws.cu)
   int attn_impl = 0;                                 // 0 mma.sync, 1 tcgen05 v1, 2 tcgen05 warp-specialised
   CUtensorMap map_qkv[64], map_proj[64], map_fc1[64], map_fc2[64];
+  CUtensorMap half_qkv[64], half_proj[64], half_fc1[64], half_fc2[64];   // 128-row boxes of the same weights (cluster multicast)
+  bool has_half[4] = {false, false, false, false};
   bool a0_cleared = false;
   // optional per-kernel timing (bench.py's roofline leg): CUDA events around every launch on the caller's stream
   bool profile = false;
@@ -132,7 +134,7 @@ static int vit_run(VitEngine* e, int batch, float* out_tokens, cudaStream_t stre
     GemmEpilogue e1{};
     e1.out = e->ws.qkv; e1.bias = wf + o.qkv_b; e1.ld_out = 3 * D; e1.mode = kOutHalf;
     { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * 3.0 * D * D);
-      if (int r = gemm_f16_launch(&e->map_y, &e->map_qkv[i], &e->out_qkv, rows, 3 * D, D, e1, stream)) return r; }
+      if (int r = gemm_f16_launch(&e->map_y, &e->map_qkv[i], &e->out_qkv, rows, 3 * D, D, e1, stream, e->has_half[0] ? &e->half_qkv[i] : nullptr)) return r; }
     { ProfScope ps(e, stream, kCatAttention, 4.0 * batch * (double)T * T * D);
       if (e->attn_impl == 2) {
         // the 3-D map's frame extent is the engine's max_batch: frames >= batch are simply never addressed
@@ -142,17 +144,17 @@ static int vit_run(VitEngine* e, int batch, float* out_tokens, cudaStream_t stre
     GemmEpilogue e2{};
     e2.out = e->ws.x; e2.bias = wf + o.proj_b; e2.ld_out = D; e2.mode = kOutResidual;
     { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * (double)D * D);
-      if (int r = gemm_f16_launch(&e->map_ao, &e->map_proj[i], &e->out_x, rows, D, D, e2, stream)) return r; }
+      if (int r = gemm_f16_launch(&e->map_ao, &e->map_proj[i], &e->out_x, rows, D, D, e2, stream, e->has_half[1] ? &e->half_proj[i] : nullptr)) return r; }
     { ProfScope ps(e, stream, kCatLayerNorm, (double)rows * D * 6);
       if (int r = layernorm_half(e->ws.x, wf + o.ln2_w, wf + o.ln2_b, c.ln_eps, rows, D, e->ws.y, stream)) return r; }
     GemmEpilogue e3{};
     e3.out = e->ws.hmid; e3.bias = wf + o.fc1_b; e3.ld_out = M; e3.mode = kOutHalfAct; e3.act = c.act;
     { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * (double)M * D);
-      if (int r = gemm_f16_launch(&e->map_y, &e->map_fc1[i], &e->out_h, rows, M, D, e3, stream)) return r; }
+      if (int r = gemm_f16_launch(&e->map_y, &e->map_fc1[i], &e->out_h, rows, M, D, e3, stream, e->has_half[2] ? &e->half_fc1[i] : nullptr)) return r; }
     GemmEpilogue e4{};
     e4.out = e->ws.x; e4.bias = wf + o.fc2_b; e4.ld_out = D; e4.mode = kOutResidual;
     { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * (double)M * D);
-      if (int r = gemm_f16_launch(&e->map_h, &e->map_fc2[i], &e->out_x, rows, D, M, e4, stream)) return r; }
+      if (int r = gemm_f16_launch(&e->map_h, &e->map_fc2[i], &e->out_x, rows, D, M, e4, stream, e->has_half[3] ? &e->half_fc2[i] : nullptr)) return r; }
   }
   return layernorm_patch_tokens(e->ws.x, wf + e->L.ln_post_w, wf + e->L.ln_post_b, c.ln_eps, batch, T, 1 + c.n_reg, D,
                                 out_tokens, stream);
@@ -222,6 +224,12 @@ int bscnav_vit_create(const bscnav_vit_cfg_t* c, const void* w_half, const float
     r = r ? r : make_operand_map(&e->map_proj[i], e->wh + o.proj_w, D, D, gemm_block_n((int)D));
     r = r ? r : make_operand_map(&e->map_fc1[i], e->wh + o.fc1_w, M, D, gemm_block_n((int)M));
     r = r ? r : make_operand_map(&e->map_fc2[i], e->wh + o.fc2_w, D, M, gemm_block_n((int)D));
+    e->has_half[0] = gemm_block_n((int)(3 * D)) == 256; e->has_half[1] = e->has_half[3] = gemm_block_n((int)D) == 256;
+    e->has_half[2] = gemm_block_n((int)M) == 256;
+    if (e->has_half[0]) r = r ? r : make_operand_map(&e->half_qkv[i], e->wh + o.qkv_w, 3 * D, D, 128);
+    if (e->has_half[1]) r = r ? r : make_operand_map(&e->half_proj[i], e->wh + o.proj_w, D, D, 128);
+    if (e->has_half[2]) r = r ? r : make_operand_map(&e->half_fc1[i], e->wh + o.fc1_w, M, D, 128);
+    if (e->has_half[3]) r = r ? r : make_operand_map(&e->half_fc2[i], e->wh + o.fc2_w, D, M, 128);
   }
   if (r) { delete e; return r; }
   *out_engine = e;

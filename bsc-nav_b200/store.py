@@ -241,6 +241,24 @@ class SpatialStore:
                 sims[i], pos[i], cnt[i] = s1[0], p1[0], c1[0]
         return sims, pos, cnt
 
+    def cluster_centers(self, sims: torch.Tensor, pos: torch.Tensor, cnt: torch.Tensor, eps: float = 10, min_samples: int = 5,
+                        max_clusters: int = 32):
+        """Device form of weighted_cluster_centers (BSCAgent.py:479-497) over query results (sims (Q,K), pos (Q,K,3), cnt (Q,)):
+        returns (centers (Q,max_clusters,3) f64, mean_sim (Q,max_clusters) f64, sizes (Q,max_clusters) i32, labels (Q,K) i32,
+        n_clusters (Q,) i32), device tensors; clusters ordered by descending mean similarity."""
+        Q, K = sims.shape
+        dev = self.device
+        centers = torch.zeros(Q, max_clusters, 3, dtype=torch.float64, device=dev)
+        mean_sim = torch.zeros(Q, max_clusters, dtype=torch.float64, device=dev)
+        sizes = torch.zeros(Q, max_clusters, dtype=torch.int32, device=dev)
+        labels = torch.empty(Q, K, dtype=torch.int32, device=dev)
+        n_c = torch.empty(Q, dtype=torch.int32, device=dev)
+        _lib.check(self.lib.bscnav_cluster_centers(_lib.ptr(pos.contiguous()), _lib.ptr(sims.contiguous()), _lib.ptr(cnt.contiguous()),
+                                                   Q, K, float(eps), int(min_samples), int(max_clusters), _lib.ptr(centers),
+                                                   _lib.ptr(mean_sim), _lib.ptr(sizes), _lib.ptr(labels), _lib.ptr(n_c),
+                                                   _lib.stream_ptr()), "cluster_centers")
+        return centers, mean_sim, sizes, labels, n_c
+
     # ------------------------------------------------------------------ multi-GPU deltas
     def export_delta(self, ord_lo: int, ord_hi: int, max_out: int):
         g = self.g

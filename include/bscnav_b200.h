@@ -136,6 +136,17 @@ int bscnav_query_topk_batch(const bscnav_geom_t* g, const bscnav_store_t* st, co
                             int32_t n_query, int32_t k, const bscnav_filter_t* filter, int64_t n_rows_hint, void* scratch,
                             int64_t scratch_bytes, float* out_sim, int32_t* out_pos, int32_t* out_count, void* stream);
 
+/* Cluster centres of each query's top-K cells (weighted_cluster_centers, BSCAgent.py:479-497): DBSCAN(eps, min_samples) over
+ * the integer positions with scikit-learn's labelling (clusters numbered by their smallest core index, a border point joins
+ * the lowest-numbered cluster that reaches it, noise = -1), then per cluster the similarity-weighted centre and the mean
+ * similarity, clusters ordered by descending mean similarity.
+ *   pos int32[n_query*k*3], sim float[n_query*k], count int32[n_query]   -- the outputs of bscnav_query_topk(_batch)
+ *   out_centers double[n_query*max_clusters*3], out_mean_sim double[n_query*max_clusters], out_sizes int32[n_query*max_clusters],
+ *   out_labels int32[n_query*k], out_n_clusters int32[n_query]; k <= 1024 */
+int bscnav_cluster_centers(const int32_t* pos, const float* sim, const int32_t* count, int32_t n_query, int32_t k, double eps,
+                           int32_t min_samples, int32_t max_clusters, double* out_centers, double* out_mean_sim,
+                           int32_t* out_sizes, int32_t* out_labels, int32_t* out_n_clusters, void* stream);
+
 /* Merge compacted deltas (e.g. all-gathered from other ranks) into the store under the same winner rule.
  *   d_cell int32[n], d_key uint64[n], d_h int32[n], d_feat float[n*D]; entries with d_cell < 0 are skipped.
  * Slot numbering of cells first seen through a merge follows delta order. */

@@ -13,11 +13,11 @@ static constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 static constexpr int kTmaWarp = kEpiWarps;          // the scheduler favours the highest warp id: the single-thread
 static constexpr int kMmaWarp = kEpiWarps + 1;      // MMA issuer must never wait behind ALU-bound epilogue warps
 
-template <int BN> struct Cfg {
-  static constexpr int kStages = BN == 256 ? 4 : 6;
+template <int BN, int CL = 1> struct Cfg {
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (BN / CL) * BK * 2;                        // CL == 2: this CTA's half of the weight tile
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256 && CL == 1) ? 4 : 6;
   static constexpr int kBarBytes = 256;
   static constexpr int kStagingBytes = kEpiWarps * 4096;                    // per epilogue warp: 32 rows x 128 B (TMA store box)
   static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;   // + slack for 1024-byte alignment
@@ -34,15 +34,18 @@ template <int ACT> __device__ __forceinline__ float act_fn(float v) {
   return v * r;
 }
 
-// CL = 2: two CTAs of a cluster work on vertically adjacent output tiles (same weight panel).  Each loads its own A tile
-// and HALF of the shared B tile, multicast into both CTAs' shared memory: 32 KB instead of 48 KB enter each SM per k-block.
-// At full MMA rate a 128 x 256 x 64 k-block lasts 512 cycles, i.e. 148 SMs x 48 KB / 512 cycles = 26 TB/s of operand
-// traffic out of L2 -- more than L2 delivers (the tensor pipe measured 70 % active); multicast brings it to 17 TB/s.
+// CL = 2: the CTA pair of a cluster computes two vertically adjacent output tiles (same weight panel) as ONE 256 x BN MMA
+// (tcgen05.mma.cta_group::2).  Each CTA keeps its own 128 rows of A and only HALF of the weight tile in shared memory, the
+// leader (rank 0) issues the MMAs for both, each CTA's TMEM receives its own 128 x BN accumulator and runs its own epilogue.
+// Why: at cta_group::1 a 128 x 256 x 64 k-block moves 48 KB into shared memory (TMA) and 48 KB out of it (MMA operands) per
+// 512 tensor-pipe cycles, ~190 B/clk against ~128 B/clk of shared-memory bandwidth -- the tensor pipe measured 70 % active.
+// The pair form moves 32 KB in and 32 KB out per SM.  (Multicasting the weight tile at cta_group::1 was measured: it only
+// relieves L2, and was not faster.)
 template <int BN, int MODE, int ACT, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
            const __grid_constant__ CUtensorMap map_out, int M, int N, int K, const GemmEpilogue epi) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CL>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* bars = smem + C::kStages * C::kStageBytes + C::kStagingBytes;
@@ -65,15 +68,21 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
   const bool n_fastest = K > N;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::kStages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, CL); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, 32 * kEpiWarps); }
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    // CL == 2: the leader's accumulator-empty barrier collects the epilogue threads of both CTAs
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, CL * 32 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
   }
   if (warp == kMmaWarp) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CL == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -89,23 +98,28 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const int m_blk = (n_fastest ? tile / n_tiles : tile % m_groups) * CL + rank, n_blk = n_fastest ? tile % n_tiles : tile / m_groups;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(empty_bar + 8 * stage, phase ^ 1);       // CL == 2: both CTAs' MMAs have read this stage
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);       // CL == 2: released by the leader's commit in both CTAs
           const uint32_t a_dst = smem_base + stage * C::kStageBytes;
           const uint32_t b_dst = a_dst + C::kABytes;
-          mbar_arrive_expect_tx(full_bar + 8 * stage, C::kStageBytes);
-          tma_load_2d(a_dst, &map_a, full_bar + 8 * stage, kb * BK, m_blk * BM);     // rows past M arrive as zeros
-          if (CL == 2)      // map_w has a BN/2-row box here: my half of the panel, into both CTAs
-            tma_load_2d_multicast(b_dst + rank * (C::kBBytes / 2), &map_w, full_bar + 8 * stage, kb * BK, n_blk * BN + rank * (BN / 2), 3);
-          else
+          if (CL == 2) {
+            // bytes of both CTAs complete on the leader's barrier; the leader expects the pair's total
+            const uint32_t full_leader = mapa_shared(full_bar + 8 * stage, 0);
+            if (rank == 0) mbar_arrive_expect_tx(full_bar + 8 * stage, 2 * C::kStageBytes);
+            tma_load_2d_2sm(a_dst, &map_a, full_leader, kb * BK, m_blk * BM);              // rows past M arrive as zeros
+            tma_load_2d_2sm(b_dst, &map_w, full_leader, kb * BK, n_blk * BN + rank * (BN / 2));   // map_w: BN/2-row box
+          } else {
+            mbar_arrive_expect_tx(full_bar + 8 * stage, C::kStageBytes);
+            tma_load_2d(a_dst, &map_a, full_bar + 8 * stage, kb * BK, m_blk * BM);
             tma_load_2d(b_dst, &map_w, full_bar + 8 * stage, kb * BK, n_blk * BN);
+          }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == kMmaWarp) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BN);
+    // ------------------------------------------------------------------ MMA issuer (one thread; CL == 2: of the leader CTA)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BN, CL == 2 ? 256 : 128);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -123,13 +137,15 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
             // advance 32 bytes (16 fp16) inside the swizzle atom: +2 in the (addr >> 4) field
-            tcgen05_mma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CL == 2) tcgen05_mma_f16_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            else tcgen05_mma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          if (CL == 2) tcgen05_commit_multicast(empty_bar + 8 * stage, 3);   // the stage is refilled by both CTAs' producers
+          if (CL == 2) tcgen05_commit_2sm(empty_bar + 8 * stage, 3);   // both CTAs' stages are free once these MMAs have read them
           else tcgen05_commit(empty_bar + 8 * stage);   // smem stage reusable once these MMAs have read it
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        tcgen05_commit(tfull_bar + 8 * acc);             // accumulator complete -> epilogue
+        if (CL == 2) tcgen05_commit_2sm(tfull_bar + 8 * acc, 3);   // accumulators complete in both CTAs -> both epilogues
+        else tcgen05_commit(tfull_bar + 8 * acc);        // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -187,7 +203,8 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         tmem_ld_wait();
         if (it == kCols / kIter - 1) {                    // accumulator fully read: hand the TMEM stage back to the MMA warp
           tcgen05_fence_before();
-          mbar_arrive(tempty_bar + 8 * acc);
+          if (CL == 2) mbar_arrive_cluster(mapa_shared(tempty_bar + 8 * acc, 0));   // the MMA issuer lives in the leader CTA
+          else mbar_arrive(tempty_bar + 8 * acc);
         }
         if (kViaTma) {                                    // staging buffer free again? (previous bulk op has read it)
           if (lane == 0) bulk_wait_read0();
@@ -250,10 +267,11 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
 
   tcgen05_fence_before();
   __syncthreads();
-  if (CL == 2) cluster_sync_all();        // no CTA leaves while its peer may still multicast into it or arrive on its barriers
+  if (CL == 2) cluster_sync_all();        // no CTA leaves while its peer may still read its shared memory or arrive on its barriers
   if (warp == kMmaWarp) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::kTmemCols) : "memory");
+    if (CL == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::kTmemCols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::kTmemCols) : "memory");
   }
 }
 
@@ -355,18 +373,18 @@ static int launch_bn_mode(const CUtensorMap* map_a, const CUtensorMap* map_w, co
   static bool attr_set = false;
   static int pairs = 0;
   if (!attr_set) {
-    BSC_CUDA(cudaFuncSetAttribute((k_gemm_f16<BN, MODE, ACT, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem));
-    BSC_CUDA(cudaFuncSetAttribute((k_gemm_f16<BN, MODE, ACT, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem));
-    pairs = max_cluster_pairs(reinterpret_cast<const void*>(k_gemm_f16<BN, MODE, ACT, 2>), Cfg<BN>::kSmem);
+    BSC_CUDA(cudaFuncSetAttribute((k_gemm_f16<BN, MODE, ACT, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, 1>::kSmem));
+    BSC_CUDA(cudaFuncSetAttribute((k_gemm_f16<BN, MODE, ACT, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, 2>::kSmem));
+    pairs = max_cluster_pairs(reinterpret_cast<const void*>(k_gemm_f16<BN, MODE, ACT, 2>), Cfg<BN, 2>::kSmem);
     attr_set = true;
   }
   const int m_tiles = (M + BM - 1) / BM, n_tiles = N / BN;
   if (map_w_half && m_tiles >= 2 && pairs > 0) {
-    // cluster variant: pairs of row blocks; persistent over `pairs` clusters
+    // CTA-pair variant (cta_group::2): pairs of row blocks; persistent over `pairs` clusters
     const int groups = ((m_tiles + 1) / 2) * n_tiles;
     const int clusters = groups < pairs ? groups : pairs;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = Cfg<BN>::kSmem; cfg.stream = stream;
+    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = Cfg<BN, 2>::kSmem; cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -377,7 +395,8 @@ static int launch_bn_mode(const CUtensorMap* map_a, const CUtensorMap* map_w, co
   }
   const int tiles = m_tiles * n_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  BSC_LAUNCH((k_gemm_f16<BN, MODE, ACT, 1>), grid, kGemmThreads, Cfg<BN>::kSmem, stream, *map_a, *map_w, *map_out, M, N, K, epi);
+  constexpr int smem1 = Cfg<BN, 1>::kSmem;
+  BSC_LAUNCH((k_gemm_f16<BN, MODE, ACT, 1>), grid, kGemmThreads, smem1, stream, *map_a, *map_w, *map_out, M, N, K, epi);
   return BSCNAV_OK;
 }
 
@@ -403,7 +422,7 @@ int gemm_f16_launch(const CUtensorMap* map_a, const CUtensorMap* map_w, const CU
   if (via_tma && !map_out) return BSCNAV_EINVAL;
   if (!map_out) map_out = map_a;       // unused by the direct-store epilogues
   static int use_cluster = -1;
-  if (use_cluster < 0) { const char* e = getenv("BSCNAV_GEMM_CLUSTER"); use_cluster = e ? atoi(e) : 0; }
+  if (use_cluster < 0) { const char* e = getenv("BSCNAV_GEMM_CLUSTER"); use_cluster = e ? atoi(e) : 1; }   // CTA pairs by default
   if (!use_cluster) map_w_half = nullptr;
   if (gemm_block_n(N) == 256) return launch_bn<256>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream);
   return launch_bn<128>(map_a, map_w, nullptr, map_out, M, N, K, epi, stream);

@@ -85,6 +85,13 @@ class VoxelTokenMemory:
         self._init_cache()
         self._pinned = {}
         self._copy_stream = None
+        # unproject/scatter of batch i runs on a side stream next to the ViT of batch i+1 (different pipes: float64/XU and
+        # HBM against the tensor cores); token buffers are double-buffered between the two
+        self._fuse_stream = None
+        self._tok_bufs = [None, None]
+        self._tok_free = [None, None]
+        self._tok_slot = 0
+        self._last_fuse = None
 
     # ------------------------------------------------------------------ state
     def _init_cache(self):
@@ -96,6 +103,7 @@ class VoxelTokenMemory:
                           token_dim=self.token_dim, cache_size=self.cache_size, bev=self.bev, max_slots=self._max_slots,
                           calib_mat=self.calib_mat)
         if self._store is not None and self._store.cfg == cfg:
+            self._join()
             self._store.reset()
         else:
             self._store = None
@@ -107,6 +115,7 @@ class VoxelTokenMemory:
 
     def _clear_memory(self):
         """memory_2.py:147-164."""
+        self._join()
         self._store.reset()
         self._chain.reset()
 
@@ -116,14 +125,17 @@ class VoxelTokenMemory:
 
     @property
     def max_id(self) -> int:
+        self._join()
         return self._store.count()
 
     @property
     def grid_rgb_pos(self) -> np.ndarray:
+        self._join()
         return self._store.positions()
 
     @property
     def store(self) -> SpatialStore:
+        self._join()               # whoever reaches for the store directly sees every scatter issued so far
         return self._store
 
     # ------------------------------------------------------------------ build
@@ -132,9 +144,9 @@ class VoxelTokenMemory:
         t = torch.from_numpy(np.ascontiguousarray(img)).to(self.device).unsqueeze(0)
         return self._tokens_of(t)[0].reshape(self.n_patch_w, self.n_patch_h, -1)
 
-    def _tokens_of(self, rgb_dev: torch.Tensor) -> torch.Tensor:
+    def _tokens_of(self, rgb_dev: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         if isinstance(self.dinov2, ViTEngine):
-            return self.dinov2.forward_frames(rgb_dev)
+            return self.dinov2.forward_frames(rgb_dev, out=out)
         # any other module with the reference's plug-point signature: pre-process as the reference does
         x = rgb_dev[..., :3].permute(0, 3, 1, 2).float() / 255
         x = torch.nn.functional.interpolate(x, size=(self.args.query_height, self.args.query_width), mode="bilinear",
@@ -191,7 +203,8 @@ class VoxelTokenMemory:
             self._in_free[slot] = None
         cur = torch.cuda.current_stream()
         if self._in_free[slot] is not None:
-            self._copy_stream.wait_event(self._in_free[slot])     # kernels that read this buffer two batches ago are done
+            for ev in self._in_free[slot]:
+                self._copy_stream.wait_event(ev)                  # kernels that read this buffer two batches ago are done
         with torch.cuda.stream(self._copy_stream):
             bufs[0].copy_(rgb, non_blocking=True)
             bufs[1].copy_(depth, non_blocking=True)
@@ -202,22 +215,56 @@ class VoxelTokenMemory:
 
     def fuse_frames(self, rgb, depth, poses, sample_idx=None):
         """Batched build step: rgb (B,H,W,3|4) uint8, depth (B,H,W) float32, poses (B,7) -- pinned host tensors, numpy
-        arrays or device tensors.  Returns without synchronising: copies run on a side stream, kernels on the current one."""
+        arrays or device tensors.  Returns without synchronising: copies run on a side stream, the ViT on the current one,
+        unprojection + scatter on a second side stream (overlapping the next call's ViT)."""
         poses = np.asarray(poses, dtype=np.float64).reshape(-1, 7)
         tfs = self._chain.batch(poses)
         rgb, depth, slot = self._inputs_to_device(rgb, depth)
         if sample_idx is None:
             sample_idx = self._sample_indices(rgb.shape[0])
-        tokens = self._tokens_of(rgb)
-        self._store.fuse(depth, tfs, tokens, sample_idx=sample_idx)
+        done = self.fuse_device(rgb, depth, tfs, sample_idx=sample_idx)
         if slot is not None:
             ev = torch.cuda.Event()
-            ev.record()
-            self._in_free[slot] = ev
+            ev.record()                                   # the ViT has read rgb; `done`: the scatter has read depth
+            self._in_free[slot] = (ev, done)
         self.tf = self._chain.tf
+
+    def fuse_device(self, rgb_dev, depth_dev, tfs, sample_idx=None, ord_base=None):
+        """ViT on the current stream, then unprojection + scatter on the side stream.  Returns the event that marks the
+        end of the scatter.  Inputs are device tensors that stay valid until that event."""
+        main = torch.cuda.current_stream()
+        if self._fuse_stream is None:
+            self._fuse_stream = torch.cuda.Stream(device=self.device)
+        B = rgb_dev.shape[0]
+        k = self._tok_slot = self._tok_slot ^ 1
+        buf = self._tok_bufs[k]
+        shape = (B, self.n_patch_h * self.n_patch_w, self.token_dim)
+        if buf is None or buf.shape[0] < B:
+            buf = self._tok_bufs[k] = torch.empty(shape, dtype=torch.float32, device=self.device)
+            self._tok_free[k] = None
+        if self._tok_free[k] is not None:
+            main.wait_event(self._tok_free[k])            # the scatter that read this token buffer two calls ago is done
+        tokens = self._tokens_of(rgb_dev, out=buf[:B]) if isinstance(self.dinov2, ViTEngine) else self._tokens_of(rgb_dev)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        side = self._fuse_stream if os.environ.get("BSCNAV_OVERLAP", "1") != "0" else main     # 0: everything on one stream (A/B)
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            self._store.fuse(depth_dev, tfs, tokens, sample_idx=sample_idx, ord_base=ord_base)
+            done = torch.cuda.Event()
+            done.record(side)
+        self._tok_free[k] = done
+        self._last_fuse = done
+        return done
+
+    def _join(self):
+        """Make the current stream wait for the last scatter (before reading the store)."""
+        if self._last_fuse is not None:
+            torch.cuda.current_stream().wait_event(self._last_fuse)
 
     def max_id_async(self):
         """Non-blocking read of max_id: enqueues the device->host copy, returns a handle for max_id_wait()."""
+        self._join()
         return self._store.count_async()
 
     def max_id_wait(self, handle) -> int:
@@ -275,6 +322,7 @@ class VoxelTokenMemory:
     def voxel_localized(self, prompt, K=100, batch_size=300, region_radius=np.inf, curr_grid=None):
         """memory_2.py:563-671.  Returns (best (1,3), top-K positions (K',3) int64, top-K similarities (K',) float64).
         `batch_size` is accepted and ignored (the reference overwrites it at :593)."""
+        self._join()
         q = self._query_vector(prompt)
         floor = None
         if getattr(self.args, "load_single_floor", False) and self.floor_min_height is not None:
@@ -288,6 +336,7 @@ class VoxelTokenMemory:
     def voxel_localized_batch(self, queries, K=100, region_radius=np.inf, curr_grid=None):
         """Batched form: queries (Q, D) -> device tensors (sims (Q,K), positions (Q,K,3), counts (Q,)); the same values as Q
         calls of voxel_localized, computed by the tensor-core candidate + exact re-scoring path (SpatialStore.query_batch)."""
+        self._join()
         floor = None
         if getattr(self.args, "load_single_floor", False) and self.floor_min_height is not None:
             floor = (self.floor_min_height, self.floor_max_height)
@@ -341,6 +390,7 @@ class VoxelTokenMemory:
     # ------------------------------------------------------------------ persistence (npy set of memory_2.py:1136-1145)
     def save_memory(self, path=None):
         from . import io
+        self._join()
         io.save_memory(self, path or self.memory_save_path)
 
     def load_memory(self, init_state=None, build_map=False):

@@ -242,6 +242,10 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION on some boxes) goes to stderr
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ge = importlib.import_module("__graft_entry__")
     blib = importlib.import_module("bsc-nav_b200._lib")
@@ -356,7 +360,13 @@ def run_ours(args):
            "h2d_bytes_per_step": B * (H * W * 4 + H * W * 4 + 16 * 8 + 4), "d2h_bytes_per_step": 8,
            "api": "VoxelTokenMemory.fuse_frames + max_id_async (copies overlap the previous batch)", "slots_after": counts[-1]}
 
-    query = query_leg(store, dev, peak_gbs, with_cpu=(world == 1)) if rank == 0 else None
+    # every rank serves queries over its own scene (BASELINE configs[3]: scenes sharded across GPUs, no collective on the data path)
+    query = query_leg(store, dev, peak_gbs, with_cpu=(world == 1 and rank == 0))
+    if world > 1:
+        t = torch.tensor([query["batch256"]["queries_per_s"], query["single"]["queries_per_s"]], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        query["all_ranks"] = {"batch256_queries_per_s": float(t[0]), "single_queries_per_s": float(t[1]), "ranks": world,
+                              "sharding": "one scene per rank"}
 
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -34,6 +34,10 @@ class Store(C.Structure):
                                           "norm2", "feat", "counters")]
 
 
+class Colour(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("grid_rgb", "weight", "cv_key", "cv_map")]
+
+
 class Filter(C.Structure):
     _fields_ = [("radius2", C.c_int64), ("cur", C.c_int32 * 3), ("floor_min", C.c_int32), ("floor_max", C.c_int32),
                 ("reserved", C.c_int32)]
@@ -64,6 +68,10 @@ _SIGS = {
     "bscnav_query_topk_batch": (C.c_int, [C.POINTER(Geom), C.POINTER(Store), _P, _P, C.c_int32, C.c_int32, C.POINTER(Filter),
                                           C.c_int64, _P, C.c_int64, _P, _P, _P, _P]),
     "bscnav_cluster_centers": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    "bscnav_colour_reset": (C.c_int, [C.POINTER(Geom), C.POINTER(Colour), _P]),
+    "bscnav_colour_scratch_bytes": (C.c_int64, [C.POINTER(Geom), C.c_int32, C.c_int32]),
+    "bscnav_colour_frames": (C.c_int, [C.POINTER(Geom), C.POINTER(Store), C.POINTER(Colour), _P, _P, C.c_int32, _P, _P, _P, C.c_int32,
+                                       C.c_int32, _P, C.c_int64, _P]),
     "bscnav_merge_delta": (C.c_int, [C.POINTER(Geom), C.POINTER(Store), _P, _P, _P, _P, C.c_int32, _P, C.c_int64, _P]),
     "bscnav_export_scratch_bytes": (C.c_int64, [C.POINTER(Geom)]),
     "bscnav_export_delta": (C.c_int, [C.POINTER(Geom), C.POINTER(Store), C.c_uint32, C.c_uint32, _P, _P, _P, _P, C.c_int32,

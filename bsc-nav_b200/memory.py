@@ -39,7 +39,7 @@ class _NullEnv:
 
 class VoxelTokenMemory:
     def __init__(self, args, memory_path=None, init_state=None, build_map=False, preload_dino=None, preload_yolo=None,
-                 need_diffusion=True, env=None, cache_size=10, bev=False, max_slots=None, max_batch=64):
+                 need_diffusion=True, env=None, cache_size=10, bev=False, max_slots=None, max_batch=64, colour=False):
         self.args = args
         self.device = "cuda"                                   # memory_2.py:41
         if preload_dino is None:
@@ -75,6 +75,7 @@ class VoxelTokenMemory:
         self.maxh = int(self.map_height / self.cs)
         self.minh = int(self.floor_height / self.cs)
         self.bev = bool(bev)
+        self.colour = bool(colour)           # keep grid_rgb / weight / cv_map / max_height (memory_2.py:888-903)
         self._max_slots = max_slots
         self._max_batch = max_batch
         self.long_memory_dict = []
@@ -101,7 +102,7 @@ class VoxelTokenMemory:
                           floor_height=self.floor_height, map_height=self.map_height, min_depth=self.min_depth,
                           max_depth=self.max_depth, n_patch_h=self.n_patch_h, n_patch_w=self.n_patch_w,
                           token_dim=self.token_dim, cache_size=self.cache_size, bev=self.bev, max_slots=self._max_slots,
-                          calib_mat=self.calib_mat)
+                          calib_mat=self.calib_mat, colour=self.colour)
         if self._store is not None and self._store.cfg == cfg:
             self._join()
             self._store.reset()
@@ -132,6 +133,28 @@ class VoxelTokenMemory:
     def grid_rgb_pos(self) -> np.ndarray:
         self._join()
         return self._store.positions()
+
+    def _colour(self, i):
+        if not self.colour:
+            raise _lib.BscnavError("construct the memory with colour=True to keep grid_rgb / weight / cv_map / max_height")
+        self._join()
+        return self._store.colour_views()[i]
+
+    @property
+    def grid_rgb(self) -> np.ndarray:       # (max_id, 3) uint8, memory_2.py:896-898
+        return self._colour(0)
+
+    @property
+    def weight(self) -> np.ndarray:         # (max_id,) float32, memory_2.py:899
+        return self._colour(1)
+
+    @property
+    def cv_map(self) -> np.ndarray:         # (gs, gs, 3) uint8, memory_2.py:903
+        return self._colour(2)
+
+    @property
+    def max_height(self) -> np.ndarray:     # (gs, gs) float64, memory_2.py:902
+        return self._colour(3)
 
     @property
     def store(self) -> SpatialStore:
@@ -250,7 +273,8 @@ class VoxelTokenMemory:
         side = self._fuse_stream if os.environ.get("BSCNAV_OVERLAP", "1") != "0" else main     # 0: everything on one stream (A/B)
         with torch.cuda.stream(side):
             side.wait_event(ready)
-            self._store.fuse(depth_dev, tfs, tokens, sample_idx=sample_idx, ord_base=ord_base)
+            self._store.fuse(depth_dev, tfs, tokens, sample_idx=sample_idx, ord_base=ord_base,
+                             rgb=rgb_dev if self.colour else None)
             done = torch.cuda.Event()
             done.record(side)
         self._tok_free[k] = done

@@ -32,6 +32,7 @@ class StoreConfig:
     bev: bool = False              # key reduced over h: the north-star "512x512 BEV feature grid"
     max_slots: int | None = None   # default gs*gs, the reference's capacity (memory_2.py:715-718)
     calib_mat: np.ndarray | None = None
+    colour: bool = False           # keep grid_rgb / weight / cv_map / max_height (memory_2.py:888-903); voxel keys only
 
     def geom(self) -> _lib.Geom:
         gs, cs = int(self.grid_size), float(self.cell_size)
@@ -74,6 +75,16 @@ class SpatialStore:
         self.st = _lib.Store(*[C.c_void_p(t.data_ptr()) for t in (self.occupied_ids, self.first_touch, self.slot_cell,
                                                                    self.slot_keys, self.row_key, self.tok_h, self.norm2,
                                                                    self.feat, self.counters)])
+        self.col = None
+        if cfg.colour:
+            if g.levels == 1:
+                raise _lib.BscnavError("colour channels are defined per voxel (row, col, h): not available with bev=True")
+            self.grid_rgb = torch.empty(g.max_slots, 3, dtype=torch.uint8, device=dev)
+            self.weight = torch.empty(g.max_slots, dtype=torch.float32, device=dev)
+            self.cv_key = torch.empty(g.gs * g.gs, dtype=torch.int64, device=dev)
+            self.cv_map = torch.empty(g.gs, g.gs, 3, dtype=torch.uint8, device=dev)
+            self.col = _lib.Colour(*[C.c_void_p(t.data_ptr()) for t in (self.grid_rgb, self.weight, self.cv_key, self.cv_map)])
+        self._cscratch = None
         self._scratch = None
         self._qscratch = None
         self._bscratch = None
@@ -91,6 +102,8 @@ class SpatialStore:
     # ------------------------------------------------------------------ build
     def reset(self):
         _lib.check(self.lib.bscnav_store_reset(C.byref(self.g), C.byref(self.st), _lib.stream_ptr()), "store_reset")
+        if self.col is not None:
+            _lib.check(self.lib.bscnav_colour_reset(C.byref(self.g), C.byref(self.col), _lib.stream_ptr()), "colour_reset")
         self.next_ordinal = 0
         self._shadow_valid = False
 
@@ -105,7 +118,7 @@ class SpatialStore:
         return self._scratch
 
     def fuse(self, depth: torch.Tensor, poses, tokens: torch.Tensor, sample_idx: torch.Tensor | None = None,
-             ord_base=None, want_records: bool = False):
+             ord_base=None, want_records: bool = False, rgb: torch.Tensor | None = None):
         """Fuse a batch: depth (B,H,W) f32 device, poses (B,4,4) float64 (host array or device tensor),
         tokens (B, n_patch, D) f32 device; sample_idx (B, n_points) int32 device or None for dense raster order."""
         g = self.g
@@ -129,7 +142,26 @@ class SpatialStore:
         _lib.check(self.lib.bscnav_fuse_frames(C.byref(g), C.byref(self.st), _lib.ptr(depth), _lib.ptr(poses), _lib.ptr(ob),
                                                _lib.ptr(sample_idx), B, n_points, _lib.ptr(tokens), _lib.ptr(scratch), nbytes,
                                                _lib.ptr(rec), _lib.stream_ptr()), "fuse_frames")
+        if self.col is not None:
+            # colour side channels of the same batch (same visiting order and ordinals): memory_2.py:888-903
+            if rgb is None:
+                raise _lib.BscnavError("this store keeps colour channels: fuse() needs the batch's rgb frames")
+            assert rgb.dtype == torch.uint8 and rgb.is_cuda and rgb.is_contiguous() and rgb.shape[:3] == depth.shape
+            cb = _lib.check(self.lib.bscnav_colour_scratch_bytes(C.byref(g), B, n_points), "colour_scratch_bytes")
+            if self._cscratch is None or self._cscratch.numel() < cb:
+                self._cscratch = torch.empty(cb, dtype=torch.uint8, device=self.device)
+            _lib.check(self.lib.bscnav_colour_frames(C.byref(g), C.byref(self.st), C.byref(self.col), _lib.ptr(depth), _lib.ptr(rgb),
+                                                     int(rgb.shape[3]), _lib.ptr(poses), _lib.ptr(ob), _lib.ptr(sample_idx), B,
+                                                     n_points, _lib.ptr(self._cscratch), cb, _lib.stream_ptr()), "colour_frames")
         return rec
+
+    def colour_views(self):
+        """Host copies in the reference's formats: grid_rgb (max_id,3) u8, weight (max_id,) f32, cv_map (gs,gs,3) u8,
+        max_height (gs,gs) f64 (-inf where no point fell)."""
+        n = self.count()
+        key = self.cv_key.cpu().numpy().view(np.uint64).reshape(self.g.gs, self.g.gs)
+        mh = np.where(key == 0, -np.inf, ((key - np.uint64(1)) >> np.uint64(32)).astype(np.float64))
+        return self.grid_rgb[:n].cpu().numpy(), self.weight[:n].cpu().numpy(), self.cv_map.cpu().numpy(), mh
 
     def _params_to_device(self, poses, ord_base, B):
         """One pinned staging block per batch: [poses as B*16 float64 | B uint32 ordinals] -> (poses, ordinals) on the device."""

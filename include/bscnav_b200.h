@@ -58,7 +58,8 @@ typedef struct {
  *   tok_h        int32[S*C]     h-minh of the point that produced the row (the position reported in BEV mode)
  *   norm2        float[S*C]     squared L2 norm of the row
  *   feat         float[S*C*D]   token rows                          (feat.h5df 'features', memory_2.py:335-354)
- *   counters     int32[8]       [0] = number of slots in use (max_id, memory_2.py:894), [1] = capacity-overflow flag
+ *   counters     int32[8]       [0] = number of slots in use (max_id, memory_2.py:894), [1] = capacity-overflow flag,
+ *                               [2] = slots whose colour is initialised (bscnav_colour_frames)
  */
 typedef struct {
   int32_t*  occupied_ids;
@@ -146,6 +147,29 @@ int bscnav_query_topk_batch(const bscnav_geom_t* g, const bscnav_store_t* st, co
 int bscnav_cluster_centers(const int32_t* pos, const float* sim, const int32_t* count, int32_t n_query, int32_t k, double eps,
                            int32_t min_samples, int32_t max_clusters, double* out_centers, double* out_mean_sim,
                            int32_t* out_sizes, int32_t* out_labels, int32_t* out_n_clusters, void* stream);
+
+/* Colour / occupancy side channels (memory_2.py:888-903; csrc/colour.cu), voxel keys only (levels > 1).  Optional: call
+ * bscnav_colour_frames right after bscnav_fuse_frames with the same batch (same depth, poses, ord_base, sample_idx) from the
+ * first batch on.  Results are those of the reference's sequential loop, bit for bit.
+ *   grid_rgb uint8[max_slots*3]   alpha-weighted colour mean, cast to uint8 after every update   (memory_2.py:896-898)
+ *   weight   float[max_slots]     accumulated alpha                                             (:899)
+ *   cv_key   uint64[gs*gs]        0 = empty, else ((h-minh) << 32 | ordinal) + 1 of the highest point of the (row, col);
+ *                                 max_height[row, col] = (cv_key - 1) >> 32, -inf where empty     (:901-902)
+ *   cv_map   uint8[gs*gs*3]       its colour                                                     (:903)
+ * rgb: uint8[n_frames*H*W*channels] (channels 3 or 4, alpha ignored).  counters[2] of the store tracks the slots whose colour
+ * has been initialised. */
+typedef struct {
+  uint8_t*  grid_rgb;
+  float*    weight;
+  uint64_t* cv_key;
+  uint8_t*  cv_map;
+} bscnav_colour_t;
+int bscnav_colour_reset(const bscnav_geom_t* g, const bscnav_colour_t* c, void* stream);
+int64_t bscnav_colour_scratch_bytes(const bscnav_geom_t* g, int32_t n_frames, int32_t n_points);
+int bscnav_colour_frames(const bscnav_geom_t* g, const bscnav_store_t* st, const bscnav_colour_t* c, const float* depth,
+                         const uint8_t* rgb, int32_t channels, const double* poses, const uint32_t* ord_base,
+                         const int32_t* sample_idx, int32_t n_frames, int32_t n_points, void* scratch, int64_t scratch_bytes,
+                         void* stream);
 
 /* Merge compacted deltas (e.g. all-gathered from other ranks) into the store under the same winner rule.
  *   d_cell int32[n], d_key uint64[n], d_h int32[n], d_feat float[n*D]; entries with d_cell < 0 are skipped.

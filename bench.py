@@ -195,6 +195,9 @@ def query_leg(store, dev, peak_gbs, with_cpu):
     gbs = n * (g.dim * 4 + 4) / (ms / 1e3) / 1e9
     out["single"] = {"queries_per_s": 1e3 / ms, "ms_per_pass": ms, "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peak_gbs,
                      "path": "k_query_slots (exact fp32 scan) + bitonic top-K"}
+    ms = timed(lambda r: store.query_batch(q[r % 64:r % 64 + 1], k=100, check=False), 40)
+    out["single_via_batch_path"] = {"queries_per_s": 1e3 / ms, "ms_per_query": ms,
+                                    "path": "one query through the candidate GEMM (reads the fp16 shadow: half the bytes) + exact re-score"}
     for name, Q, reps in (("batch256", 256, 20), ("batch2048", 2048, 5)):
         ms = timed(lambda r: store.query_batch(q[:Q], k=100, check=False), reps)
         # shadow rows (fp16) read once per 256-query pass, similarity matrix written once and read twice

@@ -78,6 +78,7 @@ class VoxelTokenMemory:
         self.colour = bool(colour)           # keep grid_rgb / weight / cv_map / max_height (memory_2.py:888-903)
         self._max_slots = max_slots
         self._max_batch = max_batch
+        self.batch_query_min_slots = 32768
         self.long_memory_dict = []
         self.base_height = []
         self.floor_min_height = None
@@ -351,7 +352,12 @@ class VoxelTokenMemory:
         floor = None
         if getattr(self.args, "load_single_floor", False) and self.floor_min_height is not None:
             floor = (self.floor_min_height, self.floor_max_height)
-        sims, pos, cnt = self._store.query(q[:1], k=K, region_radius=region_radius, curr_grid=curr_grid, floor_range=floor)
+        # large stores: the tensor-core candidate + exact re-score path reads the fp16 shadow (half the bytes of the fp32 scan) and
+        # returns bit-identical results; small stores: the plain exact scan (no shadow to maintain)
+        if self._store.count() >= self.batch_query_min_slots:
+            sims, pos, cnt = self._store.query_batch(q[:1], k=K, region_radius=region_radius, curr_grid=curr_grid, floor_range=floor)
+        else:
+            sims, pos, cnt = self._store.query(q[:1], k=K, region_radius=region_radius, curr_grid=curr_grid, floor_range=floor)
         n = int(cnt[0])
         top_pos = pos[0, :n].cpu().numpy().astype(np.int64)
         top_sim = sims[0, :n].cpu().numpy().astype(np.float64)

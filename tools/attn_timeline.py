@@ -8,6 +8,9 @@ B, T, H = 54, 257, 16
 qkv = (torch.randn(B * T, 3 * H * 64, device="cuda") * 0.8).half()
 for _ in range(3): pkg.attention_f16(qkv, B, T, H, impl=2)
 torch.cuda.synchronize()
+if not hasattr(lib, "bscnav_debug_attention_timeline"):
+    sys.exit("this needs the instrumented build of csrc/attention_ws.cu (WS_STAMP clock64 stamps + bscnav_debug_attention_timeline): "
+             "see DESIGN.md section 3.1; the shipped kernel carries no instrumentation")
 lib.bscnav_debug_attention_timeline.argtypes = [C.c_int, C.c_void_p]
 lib.bscnav_debug_attention_timeline(1, None)
 pkg.attention_f16(qkv, B, T, H, impl=2)

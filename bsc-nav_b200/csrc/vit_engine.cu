@@ -60,6 +60,7 @@ struct Workspace {
   __half* qkv;   // [B*T, 3D]
   __half* ao;    // [B*T, D]
   __half* hmid;  // [B*T, M]
+  float* pre_tab; // resize tap tables of the pre-processing kernel
   long long total;
 };
 static void workspace_layout(const bscnav_vit_cfg_t* c, int max_batch, Workspace* w, char* base) {
@@ -72,6 +73,7 @@ static void workspace_layout(const bscnav_vit_cfg_t* c, int max_batch, Workspace
   w->qkv = reinterpret_cast<__half*>(take(B * T * 3 * D * 2));
   w->ao = reinterpret_cast<__half*>(take(B * T * D * 2));
   w->hmid = reinterpret_cast<__half*>(take(B * T * M * 2));
+  w->pre_tab = reinterpret_cast<float*>(take(preprocess_table_bytes(c->image)));
   w->total = off;
 }
 
@@ -277,7 +279,7 @@ int bscnav_vit_forward_frames(void* engine, const uint8_t* rgb, int32_t batch, i
   if (int r = clear_a0_once(e, stream)) return r;
   { ProfScope ps(e, stream, kCatPre, (double)batch * height * width * channels);
     if (int r = preprocess_frames(rgb, batch, height, width, channels, e->cfg.image, e->cfg.patch, e->cfg.patch_k_pad, e->ws.a0,
-                                  out_pre, stream)) return r; }
+                                  out_pre, e->ws.pre_tab, stream)) return r; }
   return vit_run(e, batch, out_tokens, stream);
 }
 

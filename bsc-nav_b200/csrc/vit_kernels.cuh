@@ -4,8 +4,10 @@
 
 namespace bscnav {
 
+// tables: preprocess_table_bytes(S) bytes of device scratch for the resize tap tables (null: per-pixel kernel)
+int64_t preprocess_table_bytes(int S);
 int preprocess_frames(const uint8_t* rgb, int batch, int H, int W, int ch, int S, int P, int k_pad, __half* a0, float* out_pre,
-                      cudaStream_t stream);
+                      float* tables, cudaStream_t stream);
 int im2col_images(const float* img, int batch, int S, int P, int k_pad, __half* a0, cudaStream_t stream);
 int fill_prefix_tokens(float* x, const float* cls_pos, const float* reg, int batch, int tokens, int n_reg, int D, cudaStream_t stream);
 int layernorm_half(const float* x, const float* g, const float* b, float eps, long long rows, int D, __half* out, cudaStream_t s);

@@ -118,6 +118,8 @@ k_attention_ws(const __grid_constant__ CUtensorMap map128, const __grid_constant
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  pdl_wait();                      // the qkv tensor comes from the previous kernel in the stream
+  pdl_launch_dependents();
 
   if (warp == 12) {
     // ------------------------------------------------------------------------------------------ TMA producer
@@ -356,7 +358,7 @@ int attention_ws_launch(const CUtensorMap* map128, const CUtensorMap* map16, __h
   }
   const int n_items = batch * heads;
   const int grid = n_items < sms ? n_items : sms;
-  BSC_LAUNCH(k_attention_ws, grid, kWsThreads, kWsSmem, stream, *map128, *map16, out, T, heads, n_items);
+  BSC_LAUNCH_PDL(k_attention_ws, grid, kWsThreads, kWsSmem, stream, *map128, *map16, out, T, heads, n_items);
   return BSCNAV_OK;
 }
 

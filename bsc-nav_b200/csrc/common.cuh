@@ -33,6 +33,26 @@ inline int cuda_fail(cudaError_t e, const char* what) {
     if (_e != cudaSuccess) return ::bscnav::cuda_fail(_e, #kernel);        \
   } while (0)
 
+// Programmatic dependent launch: the kernel may start while its predecessor in the stream is still draining; it must execute
+// pdl_wait() before touching global memory.  Hides launch latency and the prologue (barrier init, TMEM allocation, descriptor
+// prefetch) of the ~170 back-to-back kernels of a ViT forward.  BSCNAV_PDL=0 launches them fully serialised (A/B, debugging).
+bool pdl_enabled();
+#define BSC_LAUNCH_PDL(kernel, grid, block, smem, stream, ...)                                   \
+  do {                                                                                           \
+    cudaLaunchConfig_t _cfg = {};                                                                \
+    _cfg.gridDim = (grid); _cfg.blockDim = (block); _cfg.dynamicSmemBytes = (smem); _cfg.stream = (stream); \
+    cudaLaunchAttribute _at[1];                                                                  \
+    _at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                              \
+    _at[0].val.programmaticStreamSerializationAllowed = ::bscnav::pdl_enabled() ? 1 : 0;         \
+    _cfg.attrs = _at; _cfg.numAttrs = 1;                                                         \
+    cudaError_t _e = cudaLaunchKernelEx(&_cfg, kernel, __VA_ARGS__);                             \
+    ::bscnav::g_launches.fetch_add(1, std::memory_order_relaxed);                                \
+    if (_e != cudaSuccess) return ::bscnav::cuda_fail(_e, #kernel);                              \
+  } while (0)
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -89,6 +89,9 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
   if (CL == 2) cluster_sync_all();        // the peer's barriers are initialised before anything is multicast to them
   tcgen05_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  // everything above touched only this CTA's shared memory / TMEM: from here on the previous kernel's results are needed
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer
@@ -385,10 +388,12 @@ static int launch_bn_mode(const CUtensorMap* map_a, const CUtensorMap* map_w, co
     const int clusters = groups < pairs ? groups : pairs;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = Cfg<BN, 2>::kSmem; cfg.stream = stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 2;
     BSC_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_f16<BN, MODE, ACT, 2>, *map_a, *map_w_half, *map_out, M, N, K, epi));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return BSCNAV_OK;
@@ -396,7 +401,7 @@ static int launch_bn_mode(const CUtensorMap* map_a, const CUtensorMap* map_w, co
   const int tiles = m_tiles * n_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
   constexpr int smem1 = Cfg<BN, 1>::kSmem;
-  BSC_LAUNCH((k_gemm_f16<BN, MODE, ACT, 1>), grid, kGemmThreads, smem1, stream, *map_a, *map_w, *map_out, M, N, K, epi);
+  BSC_LAUNCH_PDL((k_gemm_f16<BN, MODE, ACT, 1>), grid, kGemmThreads, smem1, stream, *map_a, *map_w, *map_out, M, N, K, epi);
   return BSCNAV_OK;
 }
 

@@ -5,12 +5,18 @@
 //
 // Reference semantics restated here (each kernel cites its lines): memory_2.py:744-756, 842-894, 326-358,
 // 623-671; utils.py:153-214.
+#include <cstdlib>
 #include "memory_kernels.cuh"
 
 namespace bscnav {
 
 thread_local char g_last_error[256] = {0};
 std::atomic<long long> g_launches{0};
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("BSCNAV_PDL"); on = e ? (atoi(e) != 0) : 1; }
+  return on != 0;
+}
 
 static constexpr int kThreads = 256;
 static constexpr int kItems = 4;                 // points per thread in the ordered-scan kernels

@@ -209,6 +209,8 @@ k_layernorm(const float* __restrict__ x, const float* __restrict__ gamma, const 
             long long rows, void* __restrict__ out, int tokens, int skip) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  pdl_wait();                      // x comes from the previous kernel in the stream (programmatic dependent launch)
+  pdl_launch_dependents();
   if (row >= rows) return;
   constexpr int D = NV * 128;
   long long in_row = row;
@@ -259,7 +261,7 @@ template <int MODE>
 static int layernorm_dispatch(const float* x, const float* g, const float* b, float eps, long long rows, int D, void* out,
                               int tokens, int skip, cudaStream_t stream) {
   const int grid = (int)((rows + 7) / 8);
-#define BSC_LN_CASE(NV) case NV: BSC_LAUNCH((k_layernorm<NV, MODE>), grid, 256, 0, stream, x, g, b, eps, rows, out, tokens, skip); break;
+#define BSC_LN_CASE(NV) case NV: BSC_LAUNCH_PDL((k_layernorm<NV, MODE>), grid, 256, 0, stream, x, g, b, eps, rows, out, tokens, skip); break;
   switch (D / 128) {
     BSC_LN_CASE(1) BSC_LN_CASE(2) BSC_LN_CASE(3) BSC_LN_CASE(4) BSC_LN_CASE(5) BSC_LN_CASE(6) BSC_LN_CASE(7) BSC_LN_CASE(8)
     BSC_LN_CASE(10) BSC_LN_CASE(12) BSC_LN_CASE(16)

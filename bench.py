@@ -363,6 +363,25 @@ def run_ours(args):
            "h2d_bytes_per_step": B * (H * W * 4 + H * W * 4 + 16 * 8 + 4), "d2h_bytes_per_step": 8,
            "api": "VoxelTokenMemory.fuse_frames + max_id_async (copies overlap the previous batch)", "slots_after": counts[-1]}
 
+    # ---- N > 1: the collective path -- treat the ranks' stores as frame shards of ONE scene: export the rows each rank produced,
+    # one all-gather over NVLink, every rank merges the others' rows under the same winner rule (dist.merge_scene_across_ranks)
+    merge = None
+    if world > 1:
+        dmod = importlib.import_module("bsc-nav_b200.dist")
+        mem._join()
+        slots_before = store.count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        counts = dmod.merge_scene_across_ranks(store, 0, 2 ** 32 - 1, slots_before * store.g.cache + 16)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        merge = {"ms": float(t[0]), "rows_exported_per_rank": counts, "allgather_bytes": int(sum(counts)) * (D * 4 + 16),
+                 "slots_before": slots_before, "slots_after": store.count(),
+                 "what": "export delta + all-gather (NCCL) + merge of the other ranks' rows; host-timed protocol steps included"}
+
     # every rank serves queries over its own scene (BASELINE configs[3]: scenes sharded across GPUs, no collective on the data path)
     query = query_leg(store, dev, peak_gbs, with_cpu=(world == 1 and rank == 0))
     if world > 1:
@@ -378,7 +397,7 @@ def run_ours(args):
                        "l2": f"inputs larger than L2: {B * 2 * H * W * 4 / 1e6:.0f} MB of frames per step, pool of {P} frames",
                        "sharding": "one scene per rank, no data-path collective" if world > 1 else "single GPU"},
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "vit_tflops": cfg.flops_per_frame() * B * K / (ms / 1e3) / 1e12, "query": query}
+            "vit_tflops": cfg.flops_per_frame() * B * K / (ms / 1e3) / 1e12, "query": query, "merge": merge}
     if world == 1:
         v, detail = cpu_reference_rate(1, args.ref_points, os.cpu_count() or 1)
         line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": detail}

@@ -269,7 +269,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # engine + memory (the reference-facing object)
-    cfg = pkg.CLIP_L14
+    cfg = pkg.CLIP_L14 if args.model == "clip" else pkg.DINOV2_L14_REG
     eng = pkg.ViTEngine(cfg, pkg.random_weights(cfg, seed=0), max_batch=B, device=dev)
     margs = synth.Args(height=H, width=W, grid_size=GS, depth_sample_rate=1)
     mem = pkg.VoxelTokenMemory(margs, preload_dino=eng, need_diffusion=False, cache_size=1, bev=True, max_batch=B)
@@ -393,7 +393,8 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 operands / f32 accumulate (ViT), f64 (cell index), f32 (tokens)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_frames_per_gpu": B, "frames_per_step": world * B,
+            "config": {"workload": WORKLOAD if args.model == "clip" else WORKLOAD.replace("CLIP ViT-L/14", "DINOv2 ViT-L/14-reg"),
+                       "batch_frames_per_gpu": B, "frames_per_step": world * B,
                        "l2": f"inputs larger than L2: {B * 2 * H * W * 4 / 1e6:.0f} MB of frames per step, pool of {P} frames",
                        "sharding": "one scene per rank, no data-path collective" if world > 1 else "single GPU"},
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
@@ -415,12 +416,17 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=54,
+    ap.add_argument("--batch", type=int, default=None,
                     help="frames per step per GPU (54 x 257 tokens = 109 row tiles = 55 CTA-pair tiles: with 74 CTA pairs every GEMM "
-                         "of the layer is within 1-3 %% of a whole number of waves)")
+                         "of the layer is within 1-3 %% of a whole number of waves); default 54 for clip, 53 for dinov2 (53 x 261 tokens -> 55 pair tiles)")
+    ap.add_argument("--model", default="clip", choices=["clip", "dinov2"],
+                    help="clip: CLIP ViT-L/14 (BASELINE.json's configuration, default); dinov2: DINOv2 ViT-L/14 with 4 registers, the "
+                         "feature extractor the reference itself loads (args.py:50)")
     ap.add_argument("--pool-batches", type=int, default=3, help="distinct batches of synthetic frames cycled through")
     ap.add_argument("--ref-points", type=int, default=20000, help="points of each frame the CPU reference loop visits")
     a = ap.parse_args()
+    if a.batch is None:
+        a.batch = 54 if a.model == "clip" else 53
     if a.impl == "reference":
         run_reference(a)
     else:

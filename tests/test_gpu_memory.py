@@ -235,3 +235,65 @@ def test_query_planted_topk_full_size(pkg):
         assert got == set(top.indices.cpu().tolist())
         torch.testing.assert_close(sims[i], top.values, rtol=1e-3, atol=1e-5)
         assert (pos[i][:, 2] == 100).all()
+
+
+def test_capacity_overflow_is_reported(pkg):
+    """More new cells than slots: the batch sets the overflow flag, count() raises (the reference raises IndexError at
+    memory_2.py:891 when max_id passes gs*gs)."""
+    H, W, gs = 96, 128, 64
+    cfg = pkg.StoreConfig(height=H, width=W, grid_size=gs, floor_height=-2.0, map_height=2.0, token_dim=128, cache_size=1, bev=False,
+                          max_slots=50)
+    st = pkg.SpatialStore(cfg)
+    chain = pkg.PoseChain([0, 0, -1], [-1, 0, 0], [0, 1, 0], [1, 0, 0, 0, -1, 0, 0, 0, -1], 1.5)
+    _rgb, depth, pose = mp.synthetic_frame(0, H, W, n_frames=8)
+    st.fuse(torch.from_numpy(depth[None]).cuda(), chain(pose)[None], torch.zeros(1, 256, 128, device="cuda"))
+    lib_mod = importlib.import_module("bsc-nav_b200._lib")
+    with pytest.raises(lib_mod.BscnavError):
+        st.count()
+
+
+def test_frames_without_valid_depth_leave_the_store_unchanged(pkg):
+    """Depth outside (min_depth, max_depth) everywhere (utils.py:174-176): no point survives, nothing is stored; a following
+    regular frame fuses as if the empty ones had never been offered."""
+    H, W, gs = 96, 128, 64
+    cfg = pkg.StoreConfig(height=H, width=W, grid_size=gs, floor_height=-2.0, map_height=2.0, token_dim=128, cache_size=2, bev=False)
+    chain = pkg.PoseChain([0, 0, -1], [-1, 0, 0], [0, 1, 0], [1, 0, 0, 0, -1, 0, 0, 0, -1], 1.5)
+    _rgb, depth, pose = mp.synthetic_frame(0, H, W, n_frames=8)
+    T = chain(pose)[None]
+    tok = torch.randn(1, 256, 128, device="cuda", generator=torch.Generator("cuda").manual_seed(0))
+    a, b = pkg.SpatialStore(cfg), pkg.SpatialStore(cfg)
+    for bad in (np.zeros((1, H, W), np.float32), np.full((1, H, W), 10.0, np.float32), np.full((1, H, W), 0.05, np.float32)):   # (float32(0.1) is > 0.1 in float64: valid)
+        a.fuse(torch.from_numpy(bad).cuda(), T, tok, ord_base=np.array([0]))
+        assert a.count() == 0
+    a.fuse(torch.from_numpy(depth[None]).cuda(), T, tok, ord_base=np.array([H * W]))
+    b.fuse(torch.from_numpy(depth[None]).cuda(), T, tok, ord_base=np.array([H * W]))
+    assert a.count() == b.count() > 0
+    assert torch.equal(a.slot_cell[: a.count()], b.slot_cell[: b.count()])
+    sa, sb = a.snapshot(), b.snapshot()          # (unused physical rows of a cell are uninitialised: compare the kept tokens)
+    assert sa.keys() == sb.keys()
+    for k in sa:
+        assert [(t[0], t[1], t[2]) for t in sa[k]] == [(t[0], t[1], t[2]) for t in sb[k]]
+        assert all(np.array_equal(x[3], y[3]) for x, y in zip(sa[k], sb[k]))
+
+
+def test_ragged_batches_equal_one_batch(pkg):
+    """7 frames fused as 3 + 3 + 1 (ragged tail) give the store of a single 7-frame batch."""
+    H, W, gs = 96, 128, 64
+    cfg = pkg.StoreConfig(height=H, width=W, grid_size=gs, floor_height=-2.0, map_height=2.0, token_dim=128, cache_size=3, bev=False)
+    chain = pkg.PoseChain([0, 0, -1], [-1, 0, 0], [0, 1, 0], [1, 0, 0, 0, -1, 0, 0, 0, -1], 1.5)
+    frames = [mp.synthetic_frame(f, H, W, n_frames=10) for f in range(7)]
+    depth = torch.from_numpy(np.stack([f[1] for f in frames])).cuda()
+    poses = np.stack([chain(f[2]) for f in frames])
+    tok = torch.randn(7, 256, 128, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    one, parts = pkg.SpatialStore(cfg), pkg.SpatialStore(cfg)
+    one.fuse(depth, poses, tok)
+    for lo, hi in ((0, 3), (3, 6), (6, 7)):
+        parts.fuse(depth[lo:hi].contiguous(), poses[lo:hi], tok[lo:hi].contiguous())
+    n = one.count()
+    assert n == parts.count()
+    assert torch.equal(one.slot_cell[:n], parts.slot_cell[:n]) and torch.equal(one.slot_keys[: n * 3], parts.slot_keys[: n * 3])
+    sa, sb = one.snapshot(), parts.snapshot()
+    assert sa.keys() == sb.keys()
+    for k in sa:
+        assert [(t[0], t[1], t[2]) for t in sa[k]] == [(t[0], t[1], t[2]) for t in sb[k]]
+        assert all(np.array_equal(x[3], y[3]) for x, y in zip(sa[k], sb[k]))

@@ -82,10 +82,10 @@ k_preprocess_frames(const uint8_t* __restrict__ rgb, int batch, int H, int W, in
 
 // Tiled form of the same computation for scale factors <= 4 (640x480, 680x680 -> 224): a block produces a 32 x 8 tile of output
 // pixels from a source window staged once in shared memory with coalesced loads (the per-pixel kernel above issues ~130 byte
-// loads and as many divisions per thread: 276 us for 54 frames, 0.24 TB/s).  Same weights, same summation order, and i/255
-// taken from a 256-entry table holding the very quotients the per-pixel kernel computes: results are bit-identical.
+// loads and as many divisions per thread: 276 us for 54 frames, 0.24 TB/s).  Same weights and summation order; the /255 is
+// folded into the horizontal weights.
 static constexpr int kPreTX = 32, kPreTY = 8, kPreTaps = 10, kPreWinW = 140, kPreWinH = 44;
-static constexpr int kPreTabStride = kPreTaps + 2;       // per output coordinate: 10 weights, tap count, first source index
+static constexpr int kPreTabStride = kPreTaps + 3;       // per output coordinate: 10 weights, tap count, first source index; odd stride: lanes read their own row conflict-free
 
 // tap tables of one (H, W) -> S resize: tab[0 .. S) for x, tab[S .. 2S) for y (the per-thread tap computation, with its
 // float divisions, was 3/4 of the tiled kernel's time: ncu SM 76 %, 189 us per 54 frames)
@@ -98,8 +98,9 @@ __global__ void k_aa_tables(int H, int W, int S, float* __restrict__ tab) {
   int start;
   const int n = aa_taps<kPreTaps>(o, isy ? (float)H / (float)S : (float)W / (float)S, isy ? H : W, w, &start);
   float* t = tab + (long long)i * kPreTabStride;
+  // x weights carry the /255 of memory_2.py:733 (w * (b / 255) == (w / 255) * b up to one rounding, far inside the 2e-6 parity bound)
 #pragma unroll
-  for (int j = 0; j < kPreTaps; ++j) t[j] = j < n ? w[j] : 0.f;
+  for (int j = 0; j < kPreTaps; ++j) t[j] = j < n ? (isy ? w[j] : w[j] / 255.f) : 0.f;
   t[kPreTaps] = __int_as_float(n);
   t[kPreTaps + 1] = __int_as_float(start);
 }
@@ -108,11 +109,9 @@ __global__ void __launch_bounds__(kPreTX * kPreTY)
 k_preprocess_tiled(const uint8_t* __restrict__ rgb, int batch, int H, int W, int ch, int S, int P, int k_pad,
                    const float* __restrict__ tab, __half* __restrict__ a0, float* __restrict__ out_pre) {
   __shared__ uint32_t win[kPreWinH * kPreWinW];
-  __shared__ float lut[256];
   __shared__ float s_tx[kPreTX * kPreTabStride], s_ty[kPreTY * kPreTabStride];
   const int tid = threadIdx.x, tx = tid & (kPreTX - 1), ty = tid / kPreTX;
   const int b = blockIdx.z, ox0 = blockIdx.x * kPreTX, oy0 = blockIdx.y * kPreTY;
-  lut[tid] = (float)tid / 255.f;
   for (int i = tid; i < kPreTX * kPreTabStride; i += kPreTX * kPreTY) {
     const int o = ox0 + i / kPreTabStride;
     s_tx[i] = o < S ? tab[(long long)o * kPreTabStride + i % kPreTabStride] : 0.f;
@@ -153,9 +152,11 @@ k_preprocess_tiled(const uint8_t* __restrict__ rgb, int batch, int H, int W, int
         if (jx < nx) {
           const float w = wxs[jx];
           const uint32_t v = rowp[jx];
-          r[0] += w * lut[v & 255];
-          r[1] += w * lut[(v >> 8) & 255];
-          r[2] += w * lut[(v >> 16) & 255];
+          // byte -> float on the FMA pipe: 0x4B000000 | b is the float 2^23 + b (I2F runs on the XU pipe, a 256-entry table
+          // in shared memory bank-conflicts: both measured slower)
+          r[0] = fmaf(w, __uint_as_float(0x4B000000u | (v & 255u)) - 8388608.f, r[0]);
+          r[1] = fmaf(w, __uint_as_float(0x4B000000u | ((v >> 8) & 255u)) - 8388608.f, r[1]);
+          r[2] = fmaf(w, __uint_as_float(0x4B000000u | ((v >> 16) & 255u)) - 8388608.f, r[2]);
         }
       }
       acc[0] += wys[jy] * r[0]; acc[1] += wys[jy] * r[1]; acc[2] += wys[jy] * r[2];

@@ -1,7 +1,11 @@
 """Memory directory reader/writer: the reference's .npy set (memory_2.py:1136-1145, 185-200) plus the token store.
 
-The reference keeps tokens in an HDF5 file (`feat.h5df`, group per voxel); h5py is not part of this image, so the
-device store is persisted as flat arrays next to the reference's files (HDF5 interchange is a "next" row).
+The reference keeps tokens in an HDF5 file (`feat.h5df`, one group `grid_{row}_{col}_{h}` per voxel with datasets
+`features (M, D) f32` and `distances (M,) f32`, memory_2.py:335-354).  The device store is persisted natively as flat arrays
+next to the reference's files; `export_h5` / `import_h5` write and read the reference's HDF5 layout through `h5py` when that
+module is importable (it is not part of this image: the functions take the module as an argument, the tests pass the oracle's
+in-memory stand-in), so memories built by either side can be loaded by the other.  `load_single_floor` floor detection
+(memory_2.py:202-256) is host logic over a handful of heights and lives here too.
 """
 from __future__ import annotations
 
@@ -25,6 +29,17 @@ def save_memory(mem, path: str):
     np.save(path + "/original_pos.npy", np.asarray(orig))
     np.save(path + "/map_height.npy", np.array([mem.minh, mem.maxh]))
     np.save(path + "/base_height.npy", np.array(mem.base_height))
+    # colour side channels of the reference's set (memory_2.py:1138-1139); zeros when the memory was built without them
+    if getattr(mem, "colour", False):
+        grid_rgb, weight, cv_map, _mh = st.colour_views()
+        np.save(path + "/cv_map.npy", cv_map)
+    else:
+        grid_rgb, weight = np.zeros((n, 3), np.uint8), np.zeros(n, np.float32)
+    np.save(path + "/grid_rgb.npy", grid_rgb)
+    np.save(path + "/weight.npy", weight)
+    h5 = _h5py()
+    if h5 is not None and g.levels > 1:
+        export_h5(mem, path, h5)
     with open(path + "/long_memory.json", "w") as f:
         json.dump(mem.long_memory_dict, f, indent=4)
     rows = n * g.cache
@@ -35,9 +50,164 @@ def save_memory(mem, path: str):
     np.save(path + "/bscnav_meta.npy", np.array([g.gs, g.levels, g.cache, g.dim, st.next_ordinal], dtype=np.int64))
 
 
+def _h5py():
+    try:
+        import h5py
+        return h5py
+    except ImportError:
+        return None
+
+
+def export_h5(mem, path: str, h5):
+    """Write the kept tokens as the reference's `feat.h5df` (memory_2.py:335-354): per voxel the tokens best first."""
+    st = mem.store
+    g = st.g
+    if g.levels == 1:
+        raise ValueError("the HDF5 layout is keyed by voxel (row, col, h): not defined for a BEV-keyed store")
+    with h5.File(os.path.join(path, "feat.h5df"), "a") as f:
+        for key, items in st.snapshot().items():
+            name = f"grid_{key[0]}_{key[1]}_{key[2]}"
+            feats = np.stack([t[3] for t in items]).astype(np.float32)
+            dist = np.array([t[0] for t in items], dtype=np.float32)
+            grp = f.create_group(name)
+            grp.create_dataset("features", data=feats, maxshape=(None, feats.shape[1]), chunks=True)
+            grp.create_dataset("distances", data=dist, maxshape=(None,), chunks=True)
+
+
+def import_h5(mem, path: str, h5):
+    """Fill the device store from a reference-format directory: `feat.h5df` + `occupied_ids.npy` / `grid_rgb_pos.npy` (slot
+    numbering as the reference assigned it; sequential in group order when those files are absent).  Per voxel the `cache_size`
+    tokens with the smallest distances are kept (the store rule); ordinals follow group order."""
+    st = mem.store
+    g = st.g
+    if g.levels == 1:
+        raise ValueError("the HDF5 layout is keyed by voxel (row, col, h): load it into a voxel-keyed store (bev=False)")
+    st.reset()
+    occ = None
+    if os.path.exists(path + "/occupied_ids.npy"):
+        occ = np.load(path + "/occupied_ids.npy").reshape(g.gs, g.gs, g.levels)
+    C_, D = g.cache, g.dim
+    cells, rows_feat, rows_key, rows_h, slots = [], [], [], [], []
+    ordinal = 0
+    with h5.File(os.path.join(path, "feat.h5df"), "r") as f:
+        names = list(f.keys())
+        n = len(names)
+        feat = np.zeros((n * C_, D), np.float32)
+        row_key = np.full(n * C_, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)
+        tok_h = np.zeros(n * C_, np.int32)
+        slot_cell = np.zeros(n, np.int32)
+        next_slot = 0
+        for name in names:
+            row, col, h = (int(v) for v in name.split("_")[1:4])
+            feats = np.asarray(f[name]["features"][:], dtype=np.float32)
+            dist = np.asarray(f[name]["distances"][:], dtype=np.float32)
+            if feats.shape[1] != D:
+                raise ValueError(f"{name}: token dimension {feats.shape[1]} != store dimension {D}")
+            slot = int(occ[row, col, h]) if occ is not None and occ[row, col, h] >= 0 else next_slot
+            next_slot = max(next_slot, slot + 1)
+            if slot >= n and occ is None:
+                raise ValueError("slot numbering out of range")
+            order = np.argsort(dist, kind="stable")[:C_]
+            for j, i in enumerate(order):
+                r = slot * C_ + j
+                feat[r] = feats[i]
+                row_key[r] = (np.uint64(np.float32(dist[i]).view(np.uint32)) << np.uint64(32)) | np.uint64(ordinal + int(i))
+                tok_h[r] = h
+            ordinal += len(dist)
+            slot_cell[slot] = (row * g.gs + col) * g.levels + h
+    n_slots = next_slot
+    if n_slots > g.max_slots:
+        raise ValueError(f"{n_slots} voxels exceed the store capacity {g.max_slots}")
+    dev = st.device
+    rows = n_slots * C_
+    st.slot_cell[:n_slots] = torch.from_numpy(slot_cell[:n_slots]).to(dev)
+    st.occupied_ids[torch.from_numpy(slot_cell[:n_slots].astype(np.int64)).to(dev)] = torch.arange(n_slots, dtype=torch.int32, device=dev)
+    keys = torch.from_numpy(row_key[:rows].view(np.int64)).to(dev)
+    st.row_key[:rows] = keys
+    flip = keys.view(-1, C_) ^ torch.tensor(-2 ** 63, dtype=torch.int64, device=dev)
+    st.slot_keys[:rows] = (torch.sort(flip, dim=1).values ^ torch.tensor(-2 ** 63, dtype=torch.int64, device=dev)).reshape(-1)
+    st.tok_h[:rows] = torch.from_numpy(tok_h[:rows]).to(dev)
+    st.feat[:rows] = torch.from_numpy(feat[:rows]).to(dev)
+    st.row_norms(rows)
+    st.counters[0] = n_slots
+    st.next_ordinal = ordinal
+
+
+def dbscan_labels(points: np.ndarray, eps: float, min_samples: int) -> np.ndarray:
+    """scikit-learn's DBSCAN labelling on a small point set (host; used for the handful of base heights of load_single_floor):
+    clusters = components of the core-core graph numbered by smallest core index, a border point joins the lowest-numbered
+    cluster that reaches it, noise = -1 (the device kernel csrc/cluster.cu states the same rule for the top-K positions)."""
+    p = np.asarray(points, dtype=np.float64).reshape(len(points), -1)
+    n = len(p)
+    d = np.sqrt(((p[:, None, :] - p[None, :, :]) ** 2).sum(-1))
+    near = d <= eps
+    core = near.sum(1) >= min_samples
+    labels = np.full(n, -1, dtype=np.int64)
+    cur = 0
+    for i in range(n):
+        if labels[i] != -1 or not core[i]:
+            continue
+        stack = [i]
+        while stack:
+            j = stack.pop()
+            if labels[j] == -1:
+                labels[j] = cur
+                if core[j]:
+                    stack.extend(k for k in np.nonzero(near[j])[0] if labels[k] == -1)
+        cur += 1
+    return labels
+
+
+def detect_floor(mem, path: str | None = None):
+    """memory_2.py:202-256: floors = DBSCAN(eps 0.4, min_samples n//5) clusters of the recorded base heights; the current floor's
+    height range (in cells) becomes floor_min_height / floor_max_height, which voxel_localized and long_memory_filter apply."""
+    base = np.asarray(mem.base_height, dtype=np.float64).reshape(-1, 1)
+    if len(base) == 0:
+        return
+    min_samples = len(base) // 5 if len(base) // 5 > 0 else 1
+    labels = dbscan_labels(base, 0.4, min_samples)
+    mem.floor_heights = sorted(float(np.mean(base[labels == l])) for l in set(labels.tolist()) if l != -1)
+    mem.num_floors = len(mem.floor_heights)
+    if mem.num_floors == 0:
+        return
+    agent = getattr(mem.Env, "agent", None)
+    current_height = agent.get_state().position[1] if agent is not None else mem.floor_heights[0]
+    current_floor = int(np.argmin(np.abs(np.array(mem.floor_heights) - current_height)))
+    pos = mem.grid_rgb_pos
+    pos_range = [int(pos[:, 2].min()), int(pos[:, 2].max())]
+    if mem.num_floors == 1:
+        rng = pos_range
+    else:
+        fh, cs, ranges = mem.floor_heights, mem.cs, []
+        for i in range(mem.num_floors):
+            if i == 0:
+                lo, hi = pos_range[0], pos_range[0] + (fh[1] - fh[0]) / cs
+            elif i == mem.num_floors - 1:
+                lo, hi = pos_range[0] + (fh[i] - fh[0]) / cs, pos_range[1]
+            else:
+                lo, hi = pos_range[0] + (fh[i] - fh[0]) / cs, pos_range[0] + (fh[i + 1] - fh[0]) / cs
+            ranges.append([int(lo) + 1, int(hi) - 1])
+        rng = ranges[current_floor]
+    mem.floor_min_height, mem.floor_max_height = int(rng[0]), int(rng[1])
+    if path is not None:
+        mask = (pos[:, 2] >= mem.floor_min_height) & (pos[:, 2] <= mem.floor_max_height)
+        np.save(path + f"/grid_rgb_pos_floor_{current_floor}.npy", pos[mask])
+        if getattr(mem, "colour", False):
+            np.save(path + f"/grid_rgb_floor_{current_floor}.npy", mem.grid_rgb[mask])
+
+
 def load_memory(mem, path: str):
     st = mem.store
     g = st.g
+    if not os.path.exists(path + "/bscnav_meta.npy"):
+        # a directory written by the reference: tokens live in feat.h5df
+        h5 = _h5py()
+        if h5 is None or not os.path.exists(path + "/feat.h5df"):
+            raise FileNotFoundError(f"{path}: neither the native token arrays (bscnav_*.npy) nor a readable feat.h5df "
+                                    "(h5py is needed to read a memory written by the reference)")
+        import_h5(mem, path, h5)
+        _load_side_files(mem, path)
+        return
     meta = np.load(path + "/bscnav_meta.npy")
     if tuple(meta[:4]) != (g.gs, g.levels, g.cache, g.dim):
         raise ValueError(f"memory at {path} was built with (gs, levels, C, D) = {tuple(meta[:4])}, store is "
@@ -59,6 +229,10 @@ def load_memory(mem, path: str):
     st.row_norms(rows)
     st.counters[0] = n
     st.next_ordinal = int(meta[4])
+    _load_side_files(mem, path)
+
+
+def _load_side_files(mem, path: str):
     mem.minh, mem.maxh = [int(v) for v in np.load(path + "/map_height.npy")]
     if os.path.exists(path + "/long_memory.json"):
         with open(path + "/long_memory.json") as f:
@@ -67,3 +241,5 @@ def load_memory(mem, path: str):
         mem.Env.original_state.position = np.load(path + "/original_pos.npy")
     if os.path.exists(path + "/base_height.npy"):
         mem.base_height = list(np.load(path + "/base_height.npy"))
+    if getattr(mem.args, "load_single_floor", False):
+        detect_floor(mem, path)

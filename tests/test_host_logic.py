@@ -33,3 +33,39 @@ def test_geom_struct_matches_oracle_params():
         assert np.array_equal(np.array(g.kimg[:]).reshape(3, 3), p.calib_mat)
         assert np.array_equal(np.array(g.kinv[:]).reshape(3, 3), np.linalg.inv(p.calib_mat))
         assert np.array_equal(np.array(g.kpatch[:]).reshape(3, 3), p.patch_intr)
+
+
+def test_dbscan_labels_match_sklearn():
+    """Host DBSCAN labelling (floor detection, memory_2.py:205-207) == scikit-learn, the reference's dependency."""
+    import importlib
+
+    import numpy as np
+    from sklearn.cluster import DBSCAN
+    io = importlib.import_module("bsc-nav_b200.io")
+    rng = np.random.default_rng(0)
+    for _ in range(100):
+        pts = np.concatenate([rng.normal(c, 0.15, size=rng.integers(0, 12)) for c in (0.0, 3.1, 6.0)]).reshape(-1, 1)
+        if len(pts) == 0:
+            continue
+        ms = max(len(pts) // 5, 1)
+        assert np.array_equal(io.dbscan_labels(pts, 0.4, ms), DBSCAN(eps=0.4, min_samples=ms).fit(pts).labels_)
+    for _ in range(30):
+        pts = rng.integers(0, 60, size=(80, 3)).astype(float)
+        assert np.array_equal(io.dbscan_labels(pts, 10, 5), DBSCAN(eps=10, min_samples=5).fit(pts).labels_)
+
+
+def test_detect_floor_ranges():
+    """Two floors 3 m apart, agent on the upper one: the upper floor's cell range (memory_2.py:222-241)."""
+    import importlib
+    import types
+
+    import numpy as np
+    io = importlib.import_module("bsc-nav_b200.io")
+    pos = np.array([[1, 1, h] for h in range(95, 160)], dtype=np.int32)
+    agent = types.SimpleNamespace(get_state=lambda: types.SimpleNamespace(position=np.array([0.0, 3.05, 0.0])))
+    mem = types.SimpleNamespace(base_height=[0.0, 0.02, 0.01, 3.0, 3.02, 3.05, 0.03, 2.98, 0.0, 3.01], cs=0.1, grid_rgb_pos=pos,
+                                Env=types.SimpleNamespace(agent=agent), colour=False, floor_min_height=None, floor_max_height=None)
+    io.detect_floor(mem)
+    assert mem.num_floors == 2 and abs(mem.floor_heights[0] - 0.012) < 1e-9 and abs(mem.floor_heights[1] - 3.012) < 1e-9
+    lo = 95 + (mem.floor_heights[1] - mem.floor_heights[0]) / 0.1
+    assert (mem.floor_min_height, mem.floor_max_height) == (int(lo) + 1, 159 - 1)

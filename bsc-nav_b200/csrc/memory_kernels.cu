@@ -522,10 +522,11 @@ k_query_slots(const bscnav_geom_t g, const float* __restrict__ feat, const float
 static constexpr int kChunk = kTopkChunk;
 __global__ void __launch_bounds__(1024)
 k_topk_chunks(const unsigned long long* __restrict__ in, long long in_stride, const int32_t* __restrict__ n_dev, int n_host,
-              unsigned long long* __restrict__ out, long long out_stride, int k) {
+              unsigned long long* __restrict__ out, long long out_stride, int k, const int32_t* __restrict__ run_flag) {
   __shared__ unsigned long long s[kChunk];
   const int n = n_dev ? *n_dev : n_host;
   const int qi = blockIdx.y;
+  if (run_flag && !run_flag[qi]) return;        // fall-back sorter: only for queries the histogram select handed over
   const long long base = (long long)blockIdx.x * kChunk;
   for (int i = threadIdx.x; i < kChunk; i += 1024) {
     const long long idx = base + i;
@@ -597,6 +598,14 @@ k_topk_decode(const bscnav_geom_t g, const unsigned long long* __restrict__ keys
 
 int mem_num_sms();
 static int num_sms() { return mem_num_sms(); }
+
+// queries flagged by the histogram select take the chunked sorter's result
+__global__ void k_pick_fallback(const int32_t* __restrict__ overflow, const unsigned long long* __restrict__ fallback,
+                                long long fb_stride, unsigned long long* __restrict__ sorted, int k) {
+  const int qi = blockIdx.x;
+  if (!overflow[qi]) return;
+  for (int i = threadIdx.x; i < k; i += blockDim.x) sorted[(long long)qi * k + i] = fallback[(long long)qi * fb_stride + i];
+}
 int mem_num_sms() {
   static int n = 0;
   if (!n) {
@@ -660,7 +669,7 @@ static int run_store_update(const bscnav_geom_t* g, const bscnav_store_t* st, co
 int launch_topk_chunks(const unsigned long long* in, long long in_stride, const int32_t* n_dev, int n_host, int n_chunks,
                        int n_query, unsigned long long* out, long long out_stride, int k, cudaStream_t stream) {
   BSC_LAUNCH(k_topk_chunks, dim3((unsigned)n_chunks, (unsigned)n_query), 1024, 0, stream, in, in_stride, n_dev, n_host, out,
-             out_stride, k);
+             out_stride, k, (const int32_t*)nullptr);
   return BSCNAV_OK;
 }
 
@@ -779,7 +788,7 @@ int64_t bscnav_query_scratch_bytes(const bscnav_geom_t* g, int32_t n_query, int3
   const long long lvl0 = (long long)kQ * g->max_slots;
   const long long chunks = (g->max_slots + kChunk - 1) / kChunk;
   const long long cand = (long long)kQ * chunks * k;
-  return align_up(lvl0 * 8, 256) + 2 * align_up(cand * 8, 256) + 256;
+  return align_up(lvl0 * 8, 256) + 2 * align_up(cand * 8, 256) + 256 + exact_select_scratch_bytes(kQ) + align_up((long long)kQ * k * 8, 256);
 }
 
 int bscnav_query_topk(const bscnav_geom_t* g, const bscnav_store_t* st, const float* q, int32_t n_query, int32_t k,
@@ -817,22 +826,30 @@ int bscnav_query_topk(const bscnav_geom_t* g, const bscnav_store_t* st, const fl
       default: return BSCNAV_EINVAL;
     }
 #undef BSC_QUERY_CASE
+    // top-K: histogram select over the exact keys + one small sort (three launches of a few microseconds); a query with more
+    // than 4096 keys in its k-th bin (massive ties) is handed to the chunked bitonic sorter below, which otherwise exits at once
+    char* sel = base + align_up(lvl0 * 8, 256) + 2 * align_up(cand * 8, 256) + 256;
+    unsigned long long* sorted = reinterpret_cast<unsigned long long*>(sel + exact_select_scratch_bytes(kQ));
+    int32_t* overflow = nullptr;
+    if (int e = launch_exact_select(keys0, (long long)g->max_slots, st->counters, g->max_slots, nq, k, sel, sorted, &overflow, stream)) return e;
     // level 0: n is the device-side slot count, but the grid covers the capacity
     long long n_chunks = chunks0;
     BSC_LAUNCH(k_topk_chunks, dim3((unsigned)n_chunks, (unsigned)nq), 1024, 0, stream, keys0, (long long)g->max_slots,
-               st->counters, 0, bufA, n_chunks * k, k);
+               st->counters, 0, bufA, n_chunks * k, k, (const int32_t*)overflow);
     unsigned long long* in = bufA;
     unsigned long long* out = bufB;
     long long n_in = n_chunks * k, in_stride = n_chunks * k;
     while (n_in > k) {
       n_chunks = (n_in + kChunk - 1) / kChunk;
       BSC_LAUNCH(k_topk_chunks, dim3((unsigned)n_chunks, (unsigned)nq), 1024, 0, stream, in, in_stride, nullptr, (int)n_in,
-                 out, n_chunks * k, k);
+                 out, n_chunks * k, k, (const int32_t*)overflow);
       in_stride = n_chunks * k;
       n_in = n_chunks * k;
       unsigned long long* t = in; in = out; out = t;
       if (n_chunks == 1) break;
     }
+    BSC_LAUNCH(k_pick_fallback, (unsigned)nq, 128, 0, stream, overflow, in, in_stride, sorted, k);
+    in = sorted; in_stride = k;
     BSC_CUDA(cudaMemsetAsync(out_count + q0, 0, sizeof(int32_t) * nq, stream));
     BSC_LAUNCH(k_topk_decode, dim3((unsigned)nq, (unsigned)((k + kThreads / 32 - 1) / (kThreads / 32))), kThreads, 0, stream, *g, in, in_stride, k, st->occupied_ids,
                reinterpret_cast<const unsigned long long*>(st->row_key), st->tok_h, st->feat, st->norm2, q, q0,

@@ -34,6 +34,10 @@ int launch_topk_chunks(const unsigned long long* in, long long in_stride, const 
                        int n_query, unsigned long long* out, long long out_stride, int k, cudaStream_t stream);
 int launch_topk_decode(const bscnav_geom_t* g, const bscnav_store_t* st, const unsigned long long* keys, long long key_stride, int k,
                        const float* q, int n_query, float* out_sim, int32_t* out_pos, int32_t* out_count, cudaStream_t stream);
+// histogram-select + sort of exact composite keys (query_batch.cu), used by the single-query path
+int64_t exact_select_scratch_bytes(int n_query);
+int launch_exact_select(const unsigned long long* keys, long long stride, const int32_t* counters, int max_slots, int n_query, int k,
+                        void* scratch, unsigned long long* sorted, int32_t** overflow_out, cudaStream_t stream);
 int mem_num_sms();
 int mem_check_geom(const bscnav_geom_t* g);
 

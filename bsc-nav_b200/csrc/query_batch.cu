@@ -177,22 +177,17 @@ k_batch_hist(const float* __restrict__ sims, long long ld, const uint8_t* __rest
     if (h[b]) atomicAdd(&hist[(long long)qi * kBins + b], h[b]);
 }
 
-__global__ void __launch_bounds__(kMemThreads)
-k_batch_select(const float* __restrict__ sims, long long ld, const uint8_t* __restrict__ row_ok, const int32_t* __restrict__ counters,
-               int C, const uint32_t* __restrict__ hist, int k, int32_t* __restrict__ cand, int32_t* __restrict__ cand_count,
-               int32_t* __restrict__ overflow) {
+// Block-wide (kMemThreads threads, all must call): the bin that holds the k-th largest entry counted in hist_q (0 when fewer
+// than k entries exist), lowered by `margin` bins; *n_sel = number of entries in bins >= the returned bin.
+__device__ __forceinline__ int threshold_bin(const uint32_t* __restrict__ hist_q, int k, int margin, uint32_t* n_sel) {
   static_assert(kBins == 8 * kMemThreads, "one thread owns eight bins");
   __shared__ uint32_t part[kMemThreads], above_of[kMemThreads];
   __shared__ int s_tb;
   __shared__ uint32_t s_ncand;
-  const int qi = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
-  const int n_slots = counters[0];
-  const int slot0 = blockIdx.x * kSelSlots;
-  if (slot0 >= n_slots) return;
-  // threshold bin: the bin that holds the k-th largest value (0 when fewer than k cells take part)
+  const int tid = threadIdx.x, lane = tid & 31;
   uint32_t local[8], sum = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { local[i] = hist[(long long)qi * kBins + tid * 8 + i]; sum += local[i]; }
+  for (int i = 0; i < 8; ++i) { local[i] = hist_q[tid * 8 + i]; sum += local[i]; }
   part[tid] = sum;
   if (tid == 0) { s_tb = 0; s_ncand = 0; }
   __syncthreads();
@@ -221,15 +216,29 @@ k_batch_select(const float* __restrict__ sims, long long ld, const uint8_t* __re
     }
   }
   __syncthreads();
-  const int t = s_tb > kMarginBins ? s_tb - kMarginBins : 0;
+  const int t = s_tb > margin ? s_tb - margin : 0;
   if (t >= tid * 8 && t < tid * 8 + 8) {
     uint32_t n = above_of[tid];
     for (int i = t - tid * 8; i < 8; ++i) n += local[i];
     s_ncand = n;
   }
   __syncthreads();
-  if (s_ncand > (uint32_t)kCandCap) {
-    if (blockIdx.x == 0 && tid == 0) overflow[qi] = (int32_t)s_ncand;
+  *n_sel = s_ncand;
+  return t;
+}
+
+__global__ void __launch_bounds__(kMemThreads)
+k_batch_select(const float* __restrict__ sims, long long ld, const uint8_t* __restrict__ row_ok, const int32_t* __restrict__ counters,
+               int C, const uint32_t* __restrict__ hist, int k, int32_t* __restrict__ cand, int32_t* __restrict__ cand_count,
+               int32_t* __restrict__ overflow) {
+  const int qi = blockIdx.y, tid = threadIdx.x;
+  const int n_slots = counters[0];
+  const int slot0 = blockIdx.x * kSelSlots;
+  if (slot0 >= n_slots) return;
+  uint32_t n_sel;
+  const int t = threshold_bin(hist + (long long)qi * kBins, k, kMarginBins, &n_sel);
+  if (n_sel > (uint32_t)kCandCap) {
+    if (blockIdx.x == 0 && tid == 0) overflow[qi] = (int32_t)n_sel;
     return;
   }
   visit_chunk(sims + (long long)qi * ld, row_ok, slot0, n_slots, C, [&](int slot, float sv) {
@@ -238,6 +247,60 @@ k_batch_select(const float* __restrict__ sims, long long ld, const uint8_t* __re
       if (pos < kCandCap) cand[(long long)qi * kCandCap + pos] = slot;
     }
   });
+}
+
+// ---- the same two stages over exact composite keys (single-query path, bscnav_query_topk): the bins are a monotone function of
+// the similarity, so every key in a bin at or above the k-th key's bin is kept and the sort of those few keys is exact
+__device__ __forceinline__ int key_bin(unsigned long long key) { return sim_bin(from_orderable(~(uint32_t)(key >> 32))); }
+
+__global__ void __launch_bounds__(kMemThreads)
+k_keys_hist(const unsigned long long* __restrict__ keys, long long stride, const int32_t* __restrict__ counters,
+            uint32_t* __restrict__ hist) {
+  __shared__ uint32_t h[kBins];
+  const int qi = blockIdx.y;
+  const int n_slots = counters[0];
+  const int slot0 = blockIdx.x * kSelSlots;
+  if (slot0 >= n_slots) return;
+  for (int b = threadIdx.x; b < kBins; b += kMemThreads) h[b] = 0;
+  __syncthreads();
+  const unsigned long long* kq = keys + (long long)qi * stride;
+  for (int i = threadIdx.x; i < kSelSlots; i += kMemThreads) {
+    const int slot = slot0 + i;
+    if (slot < n_slots) {
+      const unsigned long long key = kq[slot];
+      if (key != BSCNAV_KEY_EMPTY) atomicAdd(&h[key_bin(key)], 1u);
+    }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < kBins; b += kMemThreads)
+    if (h[b]) atomicAdd(&hist[(long long)qi * kBins + b], h[b]);
+}
+
+__global__ void __launch_bounds__(kMemThreads)
+k_keys_select(const unsigned long long* __restrict__ keys, long long stride, const int32_t* __restrict__ counters,
+              const uint32_t* __restrict__ hist, int k, unsigned long long* __restrict__ cand_keys, int32_t* __restrict__ cand_count,
+              int32_t* __restrict__ overflow) {
+  const int qi = blockIdx.y, tid = threadIdx.x;
+  const int n_slots = counters[0];
+  const int slot0 = blockIdx.x * kSelSlots;
+  if (slot0 >= n_slots) return;
+  uint32_t n_sel;
+  const int t = threshold_bin(hist + (long long)qi * kBins, k, 0, &n_sel);
+  if (n_sel > (uint32_t)kCandCap) {                      // thousands of ties in the k-th key's bin: the chunked sorter takes over
+    if (blockIdx.x == 0 && tid == 0) overflow[qi] = 1;
+    return;
+  }
+  const unsigned long long* kq = keys + (long long)qi * stride;
+  for (int i = tid; i < kSelSlots; i += kMemThreads) {
+    const int slot = slot0 + i;
+    if (slot < n_slots) {
+      const unsigned long long key = kq[slot];
+      if (key != BSCNAV_KEY_EMPTY && key_bin(key) >= t) {
+        const int pos = atomicAdd(&cand_count[qi], 1);
+        if (pos < kCandCap) cand_keys[(long long)qi * kCandCap + pos] = key;
+      }
+    }
+  }
 }
 
 // exact fp32 cosine of every candidate cell, arithmetic identical to k_query_slots; one warp per candidate
@@ -330,6 +393,35 @@ static int64_t batch_layout(const bscnav_geom_t* g, int n_query, int k, long lon
   p = take(P * kCandCap * 8); if (s) s->keys = reinterpret_cast<unsigned long long*>(p);
   p = take(P * (long long)k * 8); if (s) s->sorted = reinterpret_cast<unsigned long long*>(p);
   return off;
+}
+
+int64_t exact_select_scratch_bytes(int n_query) {
+  return align_up((long long)n_query * kBins * 4, 256) + 2 * align_up((long long)n_query * 4, 256) +
+         align_up((long long)n_query * kCandCap * 8, 256);
+}
+
+// keys [n_query][stride] (composite keys, BSCNAV_KEY_EMPTY = not a candidate) -> sorted [n_query][k] ascending; queries whose
+// k-th bin holds more than kCandCap keys are flagged in *overflow_out (device int32[n_query]) and left to the caller
+int launch_exact_select(const unsigned long long* keys, long long stride, const int32_t* counters, int max_slots, int n_query, int k,
+                        void* scratch, unsigned long long* sorted, int32_t** overflow_out, cudaStream_t stream) {
+  char* base = static_cast<char*>(scratch);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(base);
+  base += align_up((long long)n_query * kBins * 4, 256);
+  int32_t* cand_count = reinterpret_cast<int32_t*>(base);
+  base += align_up((long long)n_query * 4, 256);
+  int32_t* overflow = reinterpret_cast<int32_t*>(base);
+  base += align_up((long long)n_query * 4, 256);
+  unsigned long long* cand_keys = reinterpret_cast<unsigned long long*>(base);
+  BSC_CUDA(cudaMemsetAsync(hist, 0, (size_t)n_query * kBins * 4, stream));
+  BSC_CUDA(cudaMemsetAsync(cand_count, 0, (size_t)n_query * 4, stream));
+  BSC_CUDA(cudaMemsetAsync(overflow, 0, (size_t)n_query * 4, stream));
+  const unsigned blocks = (unsigned)((max_slots + kSelSlots - 1) / kSelSlots);
+  BSC_LAUNCH(k_keys_hist, dim3(blocks, (unsigned)n_query), kMemThreads, 0, stream, keys, stride, counters, hist);
+  BSC_LAUNCH(k_keys_select, dim3(blocks, (unsigned)n_query), kMemThreads, 0, stream, keys, stride, counters, hist, k, cand_keys,
+             cand_count, overflow);
+  BSC_LAUNCH(k_sort_candidates, (unsigned)n_query, 1024, 0, stream, cand_keys, cand_count, overflow, k, sorted);
+  *overflow_out = overflow;
+  return BSCNAV_OK;
 }
 
 }  // namespace bscnav

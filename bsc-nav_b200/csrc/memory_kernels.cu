@@ -478,17 +478,18 @@ k_query_slots(const bscnav_geom_t g, const float* __restrict__ feat, const float
     bool cand = true;
     for (int j = 0; j < C; ++j) {
       const long long r = (long long)slot * C + j;
-      if (row_key[r] == BSCNAV_KEY_EMPTY) continue;
-      if (g.levels == 1) {            // BEV keys: the token's own height takes part in the filter
-        h = tok_h[r];
-      }
-      const bool ok = filter_pass(flt, row, col, h);
-      if (!ok) { if (g.levels != 1) { cand = false; break; } else continue; }
+      // the row's 128-bit loads go out before its metadata is looked at (the row always exists in the buffer; an empty or
+      // filtered row costs one wasted read): the scan is bound by loads in flight, not by bytes
       float4 v[NV];
       const float4* fr = reinterpret_cast<const float4*>(feat + r * D);
 #pragma unroll
       for (int c = 0; c < NV; ++c) v[c] = ld_stream_f4(fr + lane + 32 * c);
+      const unsigned long long rk = row_key[r];
       const float n2 = norm2[r];
+      if (g.levels == 1) h = tok_h[r];            // BEV keys: the token's own height takes part in the filter
+      if (rk == BSCNAV_KEY_EMPTY) continue;
+      const bool ok = filter_pass(flt, row, col, h);
+      if (!ok) { if (g.levels != 1) { cand = false; break; } else continue; }
 #pragma unroll
       for (int k = 0; k < kQ; ++k) {
         if (k < nq) {

@@ -255,16 +255,16 @@ __device__ __forceinline__ int key_bin(unsigned long long key) { return sim_bin(
 
 __global__ void __launch_bounds__(kMemThreads)
 k_keys_hist(const unsigned long long* __restrict__ keys, long long stride, const int32_t* __restrict__ counters,
-            uint32_t* __restrict__ hist) {
+            uint32_t* __restrict__ hist, int chunk) {
   __shared__ uint32_t h[kBins];
   const int qi = blockIdx.y;
   const int n_slots = counters[0];
-  const int slot0 = blockIdx.x * kSelSlots;
+  const int slot0 = blockIdx.x * chunk;
   if (slot0 >= n_slots) return;
   for (int b = threadIdx.x; b < kBins; b += kMemThreads) h[b] = 0;
   __syncthreads();
   const unsigned long long* kq = keys + (long long)qi * stride;
-  for (int i = threadIdx.x; i < kSelSlots; i += kMemThreads) {
+  for (int i = threadIdx.x; i < chunk; i += kMemThreads) {
     const int slot = slot0 + i;
     if (slot < n_slots) {
       const unsigned long long key = kq[slot];
@@ -279,10 +279,10 @@ k_keys_hist(const unsigned long long* __restrict__ keys, long long stride, const
 __global__ void __launch_bounds__(kMemThreads)
 k_keys_select(const unsigned long long* __restrict__ keys, long long stride, const int32_t* __restrict__ counters,
               const uint32_t* __restrict__ hist, int k, unsigned long long* __restrict__ cand_keys, int32_t* __restrict__ cand_count,
-              int32_t* __restrict__ overflow) {
+              int32_t* __restrict__ overflow, int chunk) {
   const int qi = blockIdx.y, tid = threadIdx.x;
   const int n_slots = counters[0];
-  const int slot0 = blockIdx.x * kSelSlots;
+  const int slot0 = blockIdx.x * chunk;
   if (slot0 >= n_slots) return;
   uint32_t n_sel;
   const int t = threshold_bin(hist + (long long)qi * kBins, k, 0, &n_sel);
@@ -291,7 +291,7 @@ k_keys_select(const unsigned long long* __restrict__ keys, long long stride, con
     return;
   }
   const unsigned long long* kq = keys + (long long)qi * stride;
-  for (int i = tid; i < kSelSlots; i += kMemThreads) {
+  for (int i = tid; i < chunk; i += kMemThreads) {
     const int slot = slot0 + i;
     if (slot < n_slots) {
       const unsigned long long key = kq[slot];
@@ -415,10 +415,13 @@ int launch_exact_select(const unsigned long long* keys, long long stride, const 
   BSC_CUDA(cudaMemsetAsync(hist, 0, (size_t)n_query * kBins * 4, stream));
   BSC_CUDA(cudaMemsetAsync(cand_count, 0, (size_t)n_query * 4, stream));
   BSC_CUDA(cudaMemsetAsync(overflow, 0, (size_t)n_query * 4, stream));
-  const unsigned blocks = (unsigned)((max_slots + kSelSlots - 1) / kSelSlots);
-  BSC_LAUNCH(k_keys_hist, dim3(blocks, (unsigned)n_query), kMemThreads, 0, stream, keys, stride, counters, hist);
+  // at most eight queries per call: small chunks, so that a few hundred blocks share the 2 MB of keys per query (with the batch
+  // path's 8192-cell chunks the two stages were latency-bound at ~21 us each)
+  const int chunk = 1024;
+  const unsigned blocks = (unsigned)((max_slots + chunk - 1) / chunk);
+  BSC_LAUNCH(k_keys_hist, dim3(blocks, (unsigned)n_query), kMemThreads, 0, stream, keys, stride, counters, hist, chunk);
   BSC_LAUNCH(k_keys_select, dim3(blocks, (unsigned)n_query), kMemThreads, 0, stream, keys, stride, counters, hist, k, cand_keys,
-             cand_count, overflow);
+             cand_count, overflow, chunk);
   BSC_LAUNCH(k_sort_candidates, (unsigned)n_query, 1024, 0, stream, cand_keys, cand_count, overflow, k, sorted);
   *overflow_out = overflow;
   return BSCNAV_OK;

@@ -33,12 +33,48 @@ WORKLOAD = ("BASELINE configs[1]: HM3D single scene, synthetic 640x480 RGB-D fra
             "CLIP ViT-L/14 seeded random weights, 512x512 BEV grid, C=1, dense sampling (rate=1)")
 
 
+def _flatten(d, prefix=""):
+    if isinstance(d, dict):
+        for k, v in d.items():
+            yield from _flatten(v, prefix + "." + str(k).lower())
+    elif isinstance(d, (int, float)) and not isinstance(d, bool):
+        yield prefix, float(d)
+
+
+def parse_peaks(d):
+    """(bf16 TFLOP/s, HBM GB/s) from a MEASURED_PEAKS.json-like dict, whatever its exact key names: the sustained bf16 figure
+    is preferred over the burst one (the GEMM is timed inside a long step); values are range-checked. None where not found."""
+    flat = list(_flatten(d))
+
+    def pick(words, lo, hi, raw_scale, prefer=(), avoid=()):
+        best = None
+        for k, v in flat:
+            if v > 1e9:                      # bytes/s or FLOP/s rather than GB/s or TFLOP/s
+                v = v / raw_scale
+            if not any(w in k for w in words) or not lo <= v <= hi:
+                continue
+            score = sum(w in k for w in prefer) - sum(w in k for w in avoid)
+            if best is None or score > best[0]:
+                best = (score, v)
+        return None if best is None else best[1]
+
+    tf = pick(("bf16", "tflop", "tensor", "gemm", "cublas"), 200.0, 3000.0, 1e12, prefer=("sustain", "bf16"), avoid=("burst", "fp8", "fp4"))
+    gbs = pick(("hbm", "copy", "bandwidth", "dram", "gbs", "gb_s"), 2000.0, 9000.0, 1e9, prefer=("hbm", "sustain"), avoid=("burst", "l2"))
+    return tf, gbs
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        with open(p) as f:
-            d = json.load(f)
-        return d.get("bf16_tflops_sustained", 1386.8), d.get("hbm_gbs", 6445.3), "measured (MEASURED_PEAKS.json, sustained bf16)"
+        try:
+            with open(p) as f:
+                tf, gbs = parse_peaks(json.load(f))
+        except (OSError, ValueError):
+            tf = gbs = None
+        if tf is not None and gbs is not None:
+            return tf, gbs, "measured (MEASURED_PEAKS.json, sustained bf16)"
+        if tf is not None or gbs is not None:
+            return tf or 1400.0, gbs or 6650.0, "MEASURED_PEAKS.json where present, else fallback (B200_PROFILING.md)"
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 

@@ -2,7 +2,8 @@
 
 GESObjectNavRobot.working_memory_retrival / weighted_cluster_centers / _grid2loc / _loc2grid (BSCAgent.py:454-497,
 587-664; twin in objnav_benchmark.py:440-495) and LocalizeAgent (agent_localize.py:11-37).  LLM prompt expansion,
-CLIP view verification and motion execution are out-of-scope collaborators: `prompt_expander` is injectable.
+Motion execution and the LLM are out-of-scope collaborators: `prompt_expander` is injectable.  The CLIP view check of
+check_around (BSCAgent.py:700-748) is `ViewChecker`: image tower + scoring on the device, text tower supplied by the caller.
 """
 from __future__ import annotations
 
@@ -98,3 +99,37 @@ class LocalizeAgent(GESObjectNavRobot):
         centers, _, _ = self.weighted_cluster_centers(top_pos, top_sim)
         np.save(f"{self.save_dir}/best_pos_topK_img_input.npy", np.array(top_pos))
         return centers
+
+
+class ViewChecker:
+    """The scoring half of check_around (BSCAgent.py:700-748): after a full turn the agent encodes every view with CLIP
+    ViT-H/14, scores them against the goal (text or image embedding), takes the soft-max arg-max and turns back to that view.
+
+    `clip` is a ViTEngine built from vit_config.OPENCLIP_H14 weights (image tower, `encode_image`).  Views and image goals are
+    pre-processed tensors (N, 3, 224, 224) -- open_clip's PIL transform stays with the caller, as does the text tower: pass
+    `encode_text` (str -> (1, E) tensor) for text goals."""
+
+    def __init__(self, clip, turn_left: float, encode_text=None):
+        self.clip, self.turn_left, self.encode_text = clip, turn_left, encode_text
+
+    def goal_features(self, prompt):
+        if isinstance(prompt, str):
+            if self.encode_text is None:
+                raise ValueError("text goal needs an `encode_text` collaborator (open_clip's text tower)")
+            return self.encode_text(prompt).reshape(-1)
+        return self.clip.encode_image(prompt.reshape(1, *prompt.shape[-3:]))[0]
+
+    def best_view(self, views, prompt):
+        """-> (index of the matching view, soft-max probabilities (N,) on the device)."""
+        from .vit import score_views
+        prob, best = score_views(self.clip.encode_image(views), self.goal_features(prompt))
+        return int(best), prob
+
+    def turn_actions(self, max_idx: int):
+        """BSCAgent.py:735-745: the turn that faces the best view again."""
+        num_turns = int(360 / self.turn_left)
+        if max_idx >= num_turns:
+            max_idx -= num_turns
+        if max_idx * self.turn_left <= 180:
+            return ["turn_left"] * max_idx
+        return ["turn_right"] * (num_turns - max_idx)

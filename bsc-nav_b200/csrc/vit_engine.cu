@@ -23,7 +23,9 @@ struct VitLayout {
 };
 
 static int vit_layout(const bscnav_vit_cfg_t* c, VitLayout* L) {
-  if (!c || c->depth <= 0 || c->depth > 64 || c->dim % 128 || c->mlp % 128 || c->heads <= 0 || c->dim != c->heads * 64) return BSCNAV_EINVAL;
+  if (!c || c->depth <= 0 || c->depth > 64 || c->dim % 128 || c->mlp % 128 || c->heads <= 0) return BSCNAV_EINVAL;
+  const int hd = c->head_dim ? c->head_dim : 64;
+  if ((hd != 64 && hd != 80) || c->dim != c->heads * hd) return BSCNAV_EINVAL;
   if (c->image % c->patch || c->patch_k_pad % 64 || c->patch_k_pad < 3 * c->patch * c->patch) return BSCNAV_EINVAL;
   const long long D = c->dim, M = c->mlp, Np = (long long)(c->image / c->patch) * (c->image / c->patch);
   long long h = 0, f = 0;
@@ -115,7 +117,9 @@ struct ProfScope {
   ~ProfScope() { if (idx) cudaEventRecord(e->spans[idx - 1].e1, s); }
 };
 
-static int vit_run(VitEngine* e, int batch, float* out_tokens, cudaStream_t stream) {
+// out_tokens: LayerNorm(post) patch tokens [batch, Np, D]; or (proj != null) out_embed: the cls token's image embedding [batch, E]
+static int vit_run(VitEngine* e, int batch, float* out_tokens, cudaStream_t stream, const float* proj = nullptr, int embed_dim = 0,
+                   float* out_embed = nullptr) {
   const bscnav_vit_cfg_t& c = e->cfg;
   const int D = c.dim, M = c.mlp, T = e->T, Np = e->Np;
   const int rows = batch * T;
@@ -142,7 +146,7 @@ static int vit_run(VitEngine* e, int batch, float* out_tokens, cudaStream_t stre
         // the 3-D map's frame extent is the engine's max_batch: frames >= batch are simply never addressed
         if (int r = attention_ws_launch(&e->qkv3d128, &e->qkv3d16, e->ws.ao, batch, T, c.heads, stream)) return r;
       } else if (e->attn_impl == 1) { if (int r = attention_tc_launch(&e->qkv128, &e->qkv16, e->ws.ao, batch, T, c.heads, stream)) return r; }
-      else if (int r = attention_f16(e->ws.qkv, e->ws.ao, batch, T, c.heads, stream)) return r; }
+      else if (int r = attention_f16(e->ws.qkv, e->ws.ao, batch, T, c.heads, c.head_dim ? c.head_dim : 64, stream)) return r; }
     GemmEpilogue e2{};
     e2.out = e->ws.x; e2.bias = wf + o.proj_b; e2.ld_out = D; e2.mode = kOutResidual;
     { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * (double)D * D);
@@ -158,6 +162,7 @@ static int vit_run(VitEngine* e, int batch, float* out_tokens, cudaStream_t stre
     { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * (double)M * D);
       if (int r = gemm_f16_launch(&e->map_h, &e->map_fc2[i], &e->out_x, rows, D, M, e4, stream, e->has_half[3] ? &e->half_fc2[i] : nullptr)) return r; }
   }
+  if (proj) return cls_embed(e->ws.x, wf + e->L.ln_post_w, wf + e->L.ln_post_b, c.ln_eps, batch, T, D, proj, embed_dim, out_embed, stream);
   return layernorm_patch_tokens(e->ws.x, wf + e->L.ln_post_w, wf + e->L.ln_post_b, c.ln_eps, batch, T, 1 + c.n_reg, D,
                                 out_tokens, stream);
 }
@@ -210,6 +215,7 @@ int bscnav_vit_create(const bscnav_vit_cfg_t* c, const void* w_half, const float
   // BSCNAV_ATTENTION=0|1|2 selects mma.sync / tcgen05 v1 / tcgen05 warp-specialised (tests exercise all three)
   const char* impl_env = getenv("BSCNAV_ATTENTION");
   e->attn_impl = impl_env ? atoi(impl_env) : 2;
+  if (c->head_dim && c->head_dim != 64) e->attn_impl = 0;          // the tcgen05 kernels are specialised to head dim 64
   if (e->attn_impl == 2 && !attention_ws_supported(e->T)) e->attn_impl = 0;
   if (e->attn_impl == 1 && !attention_tc_supported(e->T)) e->attn_impl = 0;
   r = r ? r : make_qkv_map3d(&e->qkv3d128, e->ws.qkv, max_batch, e->T, 3 * D, 128);
@@ -290,6 +296,16 @@ int bscnav_vit_forward_images(void* engine, const float* images, int32_t batch, 
   if (int r = clear_a0_once(e, stream)) return r;
   if (int r = im2col_images(images, batch, e->cfg.image, e->cfg.patch, e->cfg.patch_k_pad, e->ws.a0, stream)) return r;
   return vit_run(e, batch, out_tokens, stream);
+}
+
+int bscnav_vit_encode_images(void* engine, const float* images, int32_t batch, const float* proj, int32_t embed_dim,
+                             float* out_embed, void* stream_) {
+  VitEngine* e = static_cast<VitEngine*>(engine);
+  if (!e || !images || !proj || !out_embed || embed_dim <= 0 || batch <= 0 || batch > e->max_batch) return BSCNAV_EINVAL;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int r = clear_a0_once(e, stream)) return r;
+  if (int r = im2col_images(images, batch, e->cfg.image, e->cfg.patch, e->cfg.patch_k_pad, e->ws.a0, stream)) return r;
+  return vit_run(e, batch, nullptr, stream, proj, embed_dim, out_embed);
 }
 
 }  // extern "C"

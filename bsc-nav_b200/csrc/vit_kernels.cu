@@ -287,12 +287,11 @@ int layernorm_patch_tokens(const float* x, const float* g, const float* b, float
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Multi-head self-attention, head dim 64, fp16 operands, fp32 softmax / accumulation.
+// Multi-head self-attention, head dim 64 or 80 (ViT-H/14), fp16 operands, fp32 softmax / accumulation.
 // One CTA = one (frame, head): K and V are staged once in shared memory with cp.async (16-byte chunks XOR-swizzled
 // by row so ldmatrix is conflict-free) and shared by all query rows; each of the 6 warps owns 16-row query groups
 // and runs a flash-style online softmax over 64-key blocks with mma.sync.m16n8k16, no block-level barriers in the loop.
 // 4% of the ViT's FLOPs; the GEMMs carry the tcgen05 work.
-static constexpr int kHd = 64;
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
@@ -316,6 +315,14 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 }
 // byte offset of (row, 16-byte chunk) in a [rows][64] fp16 tile with the chunk index XOR-swizzled by row
 __device__ __forceinline__ uint32_t sw_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+// K / V row layout in shared memory by head dim: 64 -> 128-byte rows, 16-byte chunks XOR-swizzled by row;
+// 80 (ViT-H/14) -> 160-byte rows padded to 176 (44 words: eight consecutive rows start 12 banks apart, so the 8 x 16-byte
+// reads of one ldmatrix phase cover all 32 banks once), no swizzle.
+template <int HD> __device__ __forceinline__ uint32_t kv_off(int row, int chunk) {
+  if (HD == 64) return sw_off(row, chunk);
+  return (uint32_t)(row * (HD * 2 + 16) + (chunk << 4));
+}
+template <int HD> constexpr int kv_row_bytes() { return HD == 64 ? 128 : HD * 2 + 16; }
 
 // 16-byte async copy global -> shared; src_bytes == 0 zero-fills (rows past the sequence end)
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
@@ -327,22 +334,24 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 static constexpr int kAttnWarps = 6;        // 257 (261) tokens = 17 row groups of 16 -> 3 rounds of 6 warps, 94% of lanes busy
 static constexpr int kAttnThreads = kAttnWarps * 32;
 
+template <int HD>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 k_attention(const __half* __restrict__ qkv, __half* __restrict__ out, int T, int heads, int t_pad) {
   extern __shared__ __align__(128) uint8_t smem_attn[];
+  constexpr int kHd = HD, KS = HD / 16, NT = HD / 8, CH = HD / 8;     // k-steps of QK^T, 8-wide output tiles, 16-byte chunks per row
   const int D = heads * kHd;
   const int head = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const __half* base = qkv + (long long)b * T * 3 * D + head * kHd;
   const uint32_t sKa = (uint32_t)__cvta_generic_to_shared(smem_attn);
-  const uint32_t sVa = sKa + t_pad * 128;
+  const uint32_t sVa = sKa + t_pad * kv_row_bytes<HD>();
   // K and V of this (frame, head): staged once, shared by every query row of the head
-  for (int i = tid; i < t_pad * 8; i += kAttnThreads) {
-    const int r = i >> 3, c = i & 7;
+  for (int i = tid; i < t_pad * CH; i += kAttnThreads) {
+    const int r = i / CH, c = i - r * CH;
     const __half* src = base + (long long)(r < T ? r : 0) * 3 * D + c * 8;
     const int nb = r < T ? 16 : 0;
-    cp_async16(sKa + sw_off(r, c), src + D, nb);
-    cp_async16(sVa + sw_off(r, c), src + 2 * D, nb);
+    cp_async16(sKa + kv_off<HD>(r, c), src + D, nb);
+    cp_async16(sVa + kv_off<HD>(r, c), src + 2 * D, nb);
   }
   cp_async_commit();
   cp_async_wait<0>();
@@ -354,21 +363,21 @@ k_attention(const __half* __restrict__ qkv, __half* __restrict__ out, int T, int
   for (int g = warp; g < n_groups; g += kAttnWarps) {
     // Q fragments (m16k16 A operand, 4 k-steps) straight from global memory: rows r0 and r0+8 of this group
     const int r0 = g * 16 + (lane >> 2), r1 = r0 + 8;
-    uint32_t qf[4][4];
+    uint32_t qf[KS][4];
     {
       const __half* q0 = base + (long long)r0 * 3 * D + 2 * (lane & 3);
       const __half* q1 = base + (long long)r1 * 3 * D + 2 * (lane & 3);
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
+      for (int ks = 0; ks < KS; ++ks) {
         qf[ks][0] = r0 < T ? *reinterpret_cast<const uint32_t*>(q0 + ks * 16) : 0u;
         qf[ks][1] = r1 < T ? *reinterpret_cast<const uint32_t*>(q1 + ks * 16) : 0u;
         qf[ks][2] = r0 < T ? *reinterpret_cast<const uint32_t*>(q0 + ks * 16 + 8) : 0u;
         qf[ks][3] = r1 < T ? *reinterpret_cast<const uint32_t*>(q1 + ks * 16 + 8) : 0u;
       }
     }
-    float o[8][4];
+    float o[NT][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+    for (int i = 0; i < NT; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // running max / sum of rows r0 and r1
 
     for (int kb = 0; kb < n_kb; ++kb) {
@@ -380,13 +389,13 @@ k_attention(const __half* __restrict__ qkv, __half* __restrict__ out, int T, int
       // S = Q K^T for 64 keys: B fragments straight from K rows (key-major, head dim contiguous).
       // k-step outermost: the eight 8-key accumulator tiles form eight independent mma chains.
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
+      for (int ks = 0; ks < KS; ++ks) {
         uint32_t kf[4][4];
 #pragma unroll
         for (int np = 0; np < 4; ++np) {     // pairs of 8-key tiles
           if (np < ng) {
             const int key = kb * 64 + np * 16 + (lane & 7) + ((lane >> 4) << 3);
-            ldsm_x4(sKa + sw_off(key, ks * 2 + ((lane >> 3) & 1)), kf[np][0], kf[np][1], kf[np][2], kf[np][3]);
+            ldsm_x4(sKa + kv_off<HD>(key, ks * 2 + ((lane >> 3) & 1)), kf[np][0], kf[np][1], kf[np][2], kf[np][3]);
           }
         }
 #pragma unroll
@@ -429,20 +438,20 @@ k_attention(const __half* __restrict__ qkv, __half* __restrict__ out, int T, int
       l0 = l0 * sc0 + ps0;
       l1 = l1 * sc1 + ps1;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { o[i][0] *= sc0; o[i][1] *= sc0; o[i][2] *= sc1; o[i][3] *= sc1; }
+      for (int i = 0; i < NT; ++i) { o[i][0] *= sc0; o[i][1] *= sc0; o[i][2] *= sc1; o[i][3] *= sc1; }
       // O += P V : P from the S accumulators (fp16), V fragments via transposing ldmatrix
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {       // 16 keys per step
         if (ks < ng) {
           const uint32_t a0 = pack_half2(s[2 * ks][0], s[2 * ks][1]), a1 = pack_half2(s[2 * ks][2], s[2 * ks][3]);
           const uint32_t a2 = pack_half2(s[2 * ks + 1][0], s[2 * ks + 1][1]), a3 = pack_half2(s[2 * ks + 1][2], s[2 * ks + 1][3]);
-          uint32_t vf[4][4];
+          uint32_t vf[KS][4];
           const int key = kb * 64 + ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
 #pragma unroll
-          for (int np = 0; np < 4; ++np)       // pairs of 8-wide head-dim tiles
-            ldsm_x4_t(sVa + sw_off(key, np * 2 + (lane >> 4)), vf[np][0], vf[np][1], vf[np][2], vf[np][3]);
+          for (int np = 0; np < KS; ++np)      // pairs of 8-wide head-dim tiles
+            ldsm_x4_t(sVa + kv_off<HD>(key, np * 2 + (lane >> 4)), vf[np][0], vf[np][1], vf[np][2], vf[np][3]);
 #pragma unroll
-          for (int np = 0; np < 4; ++np) {
+          for (int np = 0; np < KS; ++np) {
             mma_16816(o[2 * np], a0, a1, a2, a3, vf[np][0], vf[np][1]);
             mma_16816(o[2 * np + 1], a0, a1, a2, a3, vf[np][2], vf[np][3]);
           }
@@ -454,25 +463,32 @@ k_attention(const __half* __restrict__ qkv, __half* __restrict__ out, int T, int
     const float i0 = 1.f / l0, i1 = 1.f / l1;
     __half* ob = out + (long long)b * T * D + head * kHd + 2 * (lane & 3);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < NT; ++i) {
       if (r0 < T) *reinterpret_cast<uint32_t*>(ob + (long long)r0 * D + i * 8) = pack_half2(o[i][0] * i0, o[i][1] * i0);
       if (r1 < T) *reinterpret_cast<uint32_t*>(ob + (long long)r1 * D + i * 8) = pack_half2(o[i][2] * i1, o[i][3] * i1);
     }
   }
 }
 
-int attention_f16(const __half* qkv, __half* out, int batch, int T, int heads, cudaStream_t stream) {
-  if (batch <= 0 || T <= 0 || heads <= 0) return BSCNAV_EINVAL;
+template <int HD>
+static int attention_launch(const __half* qkv, __half* out, int batch, int T, int heads, cudaStream_t stream) {
   const int t_pad = (T + 15) / 16 * 16;      // only whole 16-key groups are ever read (see `ng` in the kernel)
-  const int smem = 2 * t_pad * 128;
+  const int smem = 2 * t_pad * kv_row_bytes<HD>();
   if (smem > 200 * 1024) return BSCNAV_EINVAL;
   static int attr_smem = 0;
   if (smem > attr_smem) {
-    BSC_CUDA(cudaFuncSetAttribute(k_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    BSC_CUDA(cudaFuncSetAttribute(k_attention<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem = smem;
   }
-  BSC_LAUNCH(k_attention, dim3((unsigned)heads, (unsigned)batch), kAttnThreads, smem, stream, qkv, out, T, heads, t_pad);
+  BSC_LAUNCH(k_attention<HD>, dim3((unsigned)heads, (unsigned)batch), kAttnThreads, smem, stream, qkv, out, T, heads, t_pad);
   return BSCNAV_OK;
+}
+
+int attention_f16(const __half* qkv, __half* out, int batch, int T, int heads, int head_dim, cudaStream_t stream) {
+  if (batch <= 0 || T <= 0 || heads <= 0) return BSCNAV_EINVAL;
+  if (head_dim == 64) return attention_launch<64>(qkv, out, batch, T, heads, stream);
+  if (head_dim == 80) return attention_launch<80>(qkv, out, batch, T, heads, stream);
+  return BSCNAV_EINVAL;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -503,6 +519,87 @@ __global__ void k_gaussian_pool(const float* __restrict__ tokens, int batch, int
     acc_b += acc;
   }
   out[c] = acc_b / (float)batch;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Image-embedding head (open_clip VisionTransformer: pooled = ln_post(x[:, 0]); pooled @ proj): one block per frame.
+// LayerNorm in two passes (mean, centred variance) like k_layernorm; the D x E product in fp32, proj read coalesced.
+__global__ void __launch_bounds__(256)
+k_cls_embed(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int tokens,
+            int D, const float* __restrict__ proj, int E, float* __restrict__ out) {
+  extern __shared__ float cls_row[];
+  __shared__ float red[8];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* xr = x + (long long)b * tokens * D;
+  auto block_sum = [&](float v) {
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    return t;
+  };
+  float s = 0.f;
+  for (int i = tid; i < D; i += 256) { cls_row[i] = xr[i]; s += cls_row[i]; }
+  const float mean = block_sum(s) / (float)D;
+  float q = 0.f;
+  for (int i = tid; i < D; i += 256) { const float d = cls_row[i] - mean; q += d * d; }
+  const float rstd = rsqrtf(block_sum(q) / (float)D + eps);
+  for (int i = tid; i < D; i += 256) cls_row[i] = (cls_row[i] - mean) * rstd * gamma[i] + beta[i];
+  __syncthreads();
+  for (int e = tid; e < E; e += 256) {
+    float acc = 0.f;
+    for (int d = 0; d < D; ++d) acc = fmaf(cls_row[d], proj[(long long)d * E + e], acc);
+    out[(long long)b * E + e] = acc;
+  }
+}
+
+int cls_embed(const float* x, const float* g, const float* b, float eps, int batch, int tokens, int D, const float* proj, int E,
+              float* out, cudaStream_t stream) {
+  if (batch <= 0 || D <= 0 || E <= 0 || D * 4 > 48 * 1024) return BSCNAV_EINVAL;
+  BSC_LAUNCH(k_cls_embed, (unsigned)batch, 256, D * sizeof(float), stream, x, g, b, eps, tokens, D, proj, E, out);
+  return BSCNAV_OK;
+}
+
+// View scoring (check_around, BSCAgent.py:713-718): cosine of each view embedding with the goal, softmax over the views, argmax.
+__global__ void __launch_bounds__(256)
+k_score_views(const float* __restrict__ embeds, const float* __restrict__ goal, int n, int D, float* __restrict__ prob,
+              int32_t* __restrict__ best) {
+  __shared__ float sim[1024];
+  __shared__ float g_norm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (warp == 0) {
+    float q = 0.f;
+    for (int d = lane; d < D; d += 32) q += goal[d] * goal[d];
+    q = warp_sum(q);
+    if (lane == 0) g_norm = fmaxf(sqrtf(q), 1e-12f);      // F.normalize: x / max(|x|, eps), eps = 1e-12
+  }
+  __syncthreads();
+  for (int i = warp; i < n; i += 8) {
+    const float* v = embeds + (long long)i * D;
+    float dot = 0.f, q = 0.f;
+    for (int d = lane; d < D; d += 32) { dot = fmaf(v[d], goal[d], dot); q = fmaf(v[d], v[d], q); }
+    dot = warp_sum(dot); q = warp_sum(q);
+    if (lane == 0) sim[i] = dot / (fmaxf(sqrtf(q), 1e-12f) * g_norm);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float m = -INFINITY;
+    int arg = 0x7fffffff;
+    for (int i = lane; i < n; i += 32)
+      if (sim[i] > m) { m = sim[i]; arg = i; }
+    for (int o = 16; o; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, m, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (om > m || (om == m && oa < arg)) { m = om; arg = oa; }
+    }
+    float z = 0.f;
+    for (int i = lane; i < n; i += 32) z += expf(sim[i] - m);
+    z = warp_sum(z);
+    for (int i = lane; i < n; i += 32) prob[i] = expf(sim[i] - m) / z;
+    if (lane == 0) { best[0] = arg; best[1] = 0; }
+  }
 }
 
 int64_t preprocess_table_bytes(int S) { return (int64_t)2 * S * kPreTabStride * sizeof(float); }
@@ -538,6 +635,13 @@ int fill_prefix_tokens(float* x, const float* cls_pos, const float* reg, int bat
 }  // namespace bscnav
 
 using namespace bscnav;
+
+extern "C" int bscnav_score_views(const float* embeds, const float* goal, int32_t n, int32_t dim, float* out_prob, int32_t* out_best,
+                                  void* stream) {
+  if (!embeds || !goal || !out_prob || !out_best || n <= 0 || n > 1024 || dim <= 0) return BSCNAV_EINVAL;
+  BSC_LAUNCH(k_score_views, 1, 256, 0, (cudaStream_t)stream, embeds, goal, n, dim, out_prob, out_best);
+  return BSCNAV_OK;
+}
 
 extern "C" int bscnav_gaussian_pool(const float* tokens, int32_t batch, int32_t grid, int32_t dim, float* out, void* stream) {
   if (!tokens || !out || batch <= 0 || grid <= 0 || grid > 64 || dim <= 0) return BSCNAV_EINVAL;

@@ -14,6 +14,9 @@ int layernorm_half(const float* x, const float* g, const float* b, float eps, lo
 int layernorm_inplace(float* x, const float* g, const float* b, float eps, long long rows, int D, cudaStream_t s);
 int layernorm_patch_tokens(const float* x, const float* g, const float* b, float eps, int batch, int tokens, int skip, int D,
                            float* out, cudaStream_t s);
-int attention_f16(const __half* qkv, __half* out, int batch, int T, int heads, cudaStream_t stream);   // mma.sync kernel
+int attention_f16(const __half* qkv, __half* out, int batch, int T, int heads, int head_dim, cudaStream_t stream);   // mma.sync kernel, head dim 64 | 80
+// image-embedding head (CLIP encode_image): LayerNorm of each frame's cls row, times proj [D, E] (fp32) -> out [batch, E]
+int cls_embed(const float* x, const float* g, const float* b, float eps, int batch, int tokens, int D, const float* proj, int E,
+              float* out, cudaStream_t stream);
 
 }  // namespace bscnav

@@ -20,20 +20,21 @@ def _cfg_struct(cfg: ViTConfig) -> _lib.VitCfg:
     k_pad = (cfg.patch_k + 63) // 64 * 64
     return _lib.VitCfg(image=cfg.image, patch=cfg.patch, dim=cfg.dim, depth=cfg.depth, heads=cfg.heads, mlp=cfg.mlp,
                        n_reg=cfg.n_reg, act=0 if cfg.act == "gelu" else 1, ln_pre=1 if cfg.ln_pre else 0,
-                       patch_k_pad=k_pad, ln_eps=cfg.ln_eps, reserved=0)
+                       patch_k_pad=k_pad, ln_eps=cfg.ln_eps, head_dim=cfg.dim // cfg.heads)
 
 
 def pack_weights(cfg: ViTConfig, w: dict):
     """fp32 weight dict (vit_config.random_weights layout) -> (half blob, float blob), CPU tensors.
 
     Folded on the host (exact in real arithmetic): 1/sqrt(head_dim) into the q rows of qkv (a power of two for
-    head_dim 64, so also exact in fp16), LayerScale gamma into proj / fc2 weights and biases, cls + pos[0].
+    head_dim 64, so also exact in fp16; for head_dim 80 the scaled fp32 weight is rounded to fp16 once), LayerScale gamma
+    into proj / fc2 weights and biases, cls + pos[0].
     Layout must match csrc/vit_engine.cu:vit_layout.
     """
     D, M = cfg.dim, cfg.mlp
     dh = D // cfg.heads
-    if dh != 64:
-        raise ValueError("engine supports head_dim 64")
+    if dh not in (64, 80):
+        raise ValueError("engine supports head_dim 64 (tcgen05 attention) and 80 (ViT-H/14, mma.sync attention)")
     k_pad = (cfg.patch_k + 63) // 64 * 64
     half, flt = [], []
     pw = torch.zeros(D, k_pad)
@@ -77,6 +78,7 @@ class ViTEngine:
             raise _lib.BscnavError("weight blob layout mismatch between vit.py and vit_engine.cu")
         self.w_half = hb.to(self.device)
         self.w_float = fb.to(self.device)
+        self.proj = weights["proj"].to(self.device, torch.float32).contiguous() if "proj" in weights else None
         nbytes = _lib.check(self.lib.bscnav_vit_workspace_bytes(C.byref(self._c), self.max_batch), "vit_workspace_bytes")
         self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         h = C.c_void_p()
@@ -116,6 +118,21 @@ class ViTEngine:
             _lib.check(self.lib.bscnav_vit_forward_images(self._h, _lib.ptr(x[b0:]), nb, _lib.ptr(out[b0:]), _lib.stream_ptr()),
                        "vit_forward_images")
         return {"x_norm_patchtokens": out}
+
+    # -- open_clip `encode_image` (BSCAgent.py:710, 721-724): normalised float images -> (B, embed) image embeddings
+    @torch.no_grad()
+    def encode_image(self, x: torch.Tensor) -> torch.Tensor:
+        if self.proj is None:
+            raise _lib.BscnavError("this ViT has no image-embedding head (weights['proj'])")
+        x = x.to(self.device, torch.float32).contiguous()
+        B, E = x.shape[0], self.proj.shape[1]
+        assert x.shape[1:] == (3, self.cfg.image, self.cfg.image) and self.proj.shape[0] == self.cfg.dim, x.shape
+        out = torch.empty(B, E, dtype=torch.float32, device=self.device)
+        for b0 in range(0, B, self.max_batch):
+            nb = min(self.max_batch, B - b0)
+            _lib.check(self.lib.bscnav_vit_encode_images(self._h, _lib.ptr(x[b0:]), nb, _lib.ptr(self.proj), E, _lib.ptr(out[b0:]),
+                                                         _lib.stream_ptr()), "vit_encode_images")
+        return out
 
     def profile(self, enable: bool):
         _lib.check(self.lib.bscnav_vit_profile(self._h, 1 if enable else 0), "vit_profile")
@@ -157,8 +174,29 @@ def gemm_f16(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None,
     return out
 
 
-def attention_f16(qkv: torch.Tensor, batch: int, T: int, heads: int, impl: int = 1) -> torch.Tensor:
-    """Self-attention over a packed fp16 qkv tensor [batch*T, 3*heads*64] (q pre-scaled); impl 0 = mma.sync, 1 = tcgen05."""
-    out = torch.empty(batch * T, heads * 64, dtype=torch.float16, device=qkv.device)
+def score_views(embeds: torch.Tensor, goal: torch.Tensor):
+    """check_around's scoring (BSCAgent.py:713-718, 726-731): cosine of every view embedding (n, E) with the goal embedding
+    (E,), softmax over the views -> (probabilities (n,) float32, index of the best view as a 0-d int64 tensor), on the device."""
+    embeds = embeds.to(torch.float32).contiguous()
+    goal = goal.to(embeds.device, torch.float32).reshape(-1).contiguous()
+    n, E = embeds.shape
+    assert goal.numel() == E
+    prob = torch.empty(n, dtype=torch.float32, device=embeds.device)
+    best = torch.empty(2, dtype=torch.int32, device=embeds.device)
+    _lib.check(_lib.lib().bscnav_score_views(_lib.ptr(embeds), _lib.ptr(goal), n, E, _lib.ptr(prob), _lib.ptr(best), _lib.stream_ptr()),
+               "score_views")
+    return prob, best[0].long()
+
+
+def attention_f16(qkv: torch.Tensor, batch: int, T: int, heads: int, impl: int = 1, head_dim: int = 64) -> torch.Tensor:
+    """Self-attention over a packed fp16 qkv tensor [batch*T, 3*heads*head_dim] (q pre-scaled); impl 0 = mma.sync (head_dim 64
+    or 80), 1 / 2 = tcgen05 kernels (head_dim 64)."""
+    out = torch.empty(batch * T, heads * head_dim, dtype=torch.float16, device=qkv.device)
+    if head_dim != 64:
+        if impl != 0:
+            raise ValueError("head_dim != 64 runs on the mma.sync kernel only (impl=0)")
+        _lib.check(_lib.lib().bscnav_attention_f16_hd(_lib.ptr(qkv), _lib.ptr(out), batch, T, heads, head_dim, _lib.stream_ptr()),
+                   "attention_f16_hd")
+        return out
     _lib.check(_lib.lib().bscnav_attention_f16(_lib.ptr(qkv), _lib.ptr(out), batch, T, heads, impl, _lib.stream_ptr()), "attention_f16")
     return out

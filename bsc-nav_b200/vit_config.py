@@ -27,6 +27,11 @@ class ViTConfig:
     ln_pre: bool = False      # CLIP pre-LayerNorm
     ln_eps: float = 1e-6
     patch_bias: bool = True
+    embed: int = 0            # image-embedding width of the cls head (CLIP `proj`, D x embed, no bias); 0 = no head
+
+    @property
+    def head_dim(self) -> int:
+        return self.dim // self.heads
 
     @property
     def grid(self) -> int:
@@ -55,7 +60,12 @@ DINOV2_L14_REG = ViTConfig("dinov2-vitl14-reg", n_reg=4, layerscale=True, act="g
 CLIP_B32 = ViTConfig("clip-vit-b32", patch=32, dim=768, depth=12, heads=12, mlp=3072, act="quick_gelu",
                      ln_pre=True, ln_eps=1e-5, patch_bias=False)
 
-CONFIGS = {c.name: c for c in (CLIP_L14, DINOV2_L14_REG, CLIP_B32)}
+# the agent's view-check encoder (BSCAgent.py:309: open_clip 'ViT-H/14' -> config ViT-H-14: 32 layers, width 1280, 16 heads of
+# dimension 80, MLP 5120, GELU(erf), 1024-d embedding); image tower only
+OPENCLIP_H14 = ViTConfig("openclip-vit-h14", dim=1280, depth=32, heads=16, mlp=5120, act="gelu", ln_pre=True, ln_eps=1e-5,
+                         patch_bias=False, embed=1024)
+
+CONFIGS = {c.name: c for c in (CLIP_L14, DINOV2_L14_REG, CLIP_B32, OPENCLIP_H14)}
 # torch.hub entry names the reference passes as --dino_size (args.py:50)
 CONFIGS["dinov2_vitl14_reg"] = DINOV2_L14_REG
 
@@ -103,4 +113,6 @@ def random_weights(cfg: ViTConfig, seed: int = 0, perturb: bool = False, std: fl
             w[p + "ls1"] = 1.0 + n(D, s=0.1) if perturb else torch.ones(D)
             w[p + "ls2"] = 1.0 + n(D, s=0.1) if perturb else torch.ones(D)
     w["ln_post_w"], w["ln_post_b"] = ln_pair()
+    if cfg.embed:
+        w["proj"] = n(D, cfg.embed, s=D ** -0.5)
     return w

@@ -195,7 +195,7 @@ typedef struct {
   int32_t ln_pre;                 /* 1 = CLIP pre-LayerNorm                            */
   int32_t patch_k_pad;            /* 3*patch*patch rounded up to a multiple of 64      */
   float   ln_eps;
-  int32_t reserved;
+  int32_t head_dim;               /* 0 or 64: dim == heads*64; 80: ViT-H/14 (mma.sync attention) */
 } bscnav_vit_cfg_t;
 
 /* Element counts of the two packed weight blobs (layout documented in DESIGN.md / vit.py:pack_weights). */
@@ -224,6 +224,18 @@ int bscnav_vit_forward_frames(void* engine, const uint8_t* rgb, int32_t batch, i
 /* Query-image path (voxel_localized, memory_2.py:577-592): already normalised float[batch*3*image*image]. */
 int bscnav_vit_forward_images(void* engine, const float* images, int32_t batch, float* out_tokens, void* stream);
 
+/* Image-embedding path of the agent's view check (check_around, BSCAgent.py:700-731: clip_model.encode_image):
+ * already normalised float[batch*3*image*image] -> ViT -> LayerNorm(post) of the cls token -> x proj (float[dim*embed_dim],
+ * row-major [dim][embed_dim], no bias) -> out_embed float[batch*embed_dim]. */
+int bscnav_vit_encode_images(void* engine, const float* images, int32_t batch, const float* proj, int32_t embed_dim,
+                             float* out_embed, void* stream);
+
+/* View scoring of check_around (BSCAgent.py:713-718, 726-731): L2-normalise the n view embeddings and the goal embedding,
+ * similarities = views . goal, softmax over the n views -> out_prob float[n]; out_best int32[2] = {argmax (lowest index on
+ * ties), 0}.  n <= 1024. */
+int bscnav_score_views(const float* embeds, const float* goal, int32_t n, int32_t dim, float* out_prob, int32_t* out_best,
+                       void* stream);
+
 /* Gaussian centre-weighted pooling of query tokens (memory_2.py:596-608): float[batch*n_patch*dim] -> float[dim]. */
 int bscnav_gaussian_pool(const float* tokens, int32_t batch, int32_t grid, int32_t dim, float* out, void* stream);
 
@@ -235,6 +247,8 @@ int bscnav_gemm_f16(const void* a, const void* w, const float* bias, void* out, 
 /* Stand-alone attention entry (tests/bench): qkv fp16 [batch*T, 3*heads*64] (q pre-scaled by 1/sqrt(64)) ->
  * out fp16 [batch*T, heads*64].  impl 0: mma.sync kernel (any T); impl 1: tcgen05 kernel (T <= 272). */
 int bscnav_attention_f16(const void* qkv, void* out, int32_t batch, int32_t T, int32_t heads, int32_t impl, void* stream);
+/* The mma.sync kernel with an explicit head dim (64 | 80): qkv fp16 [batch*T, 3*heads*head_dim], q pre-scaled. */
+int bscnav_attention_f16_hd(const void* qkv, void* out, int32_t batch, int32_t T, int32_t heads, int32_t head_dim, void* stream);
 
 /* Number of kernels launched by this library since load (bench.py's gpu_launches). */
 int64_t bscnav_launch_count(void);

@@ -91,6 +91,22 @@ def vit_forward(x: torch.Tensor, w: dict, cfg, quant=None, return_all: bool = Fa
     return h[:, 1 + cfg.n_reg:]
 
 
+@torch.no_grad()
+def encode_image(x: torch.Tensor, w: dict, cfg, quant=None) -> torch.Tensor:
+    """open_clip / CLIP `encode_image` (the agent's view-check encoder, BSCAgent.py:309, 710, 721-724; third-party, restated
+    and cross-checked against transformers.CLIPVisionModelWithProjection in tests/test_vit_oracle.py): the post-LayerNorm'd
+    cls token times the bias-free projection `proj` (D, E)."""
+    return vit_forward(x, w, cfg, quant, return_all=True)[:, 0] @ w["proj"]
+
+
+def score_views(image_features: torch.Tensor, goal_features: torch.Tensor):
+    """check_around, BSCAgent.py:713-718 / 726-731: normalise, similarities, softmax over the views, argmax."""
+    a = F.normalize(image_features, p=2, dim=-1)
+    g = F.normalize(goal_features.reshape(1, -1), p=2, dim=-1)
+    sims = torch.softmax(torch.matmul(a, g.T).squeeze(1), dim=0)
+    return sims, torch.max(sims, dim=0)[1]
+
+
 class TorchViT(torch.nn.Module):
     """Adapter with the reference's plug-point signature (`preload_dino`, memory_2.py:43-46)."""
 

@@ -17,7 +17,7 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 256, 128), (1000, 1024, 1024), (257 * 3, 3072, 1024), (515, 4096, 1024),
-                                   (200, 1024, 4096), (4112, 2304, 768)])
+                                   (200, 1024, 4096), (4112, 2304, 768), (514, 3840, 1280), (300, 1280, 5120)])
 def test_gemm_modes(pkg, M, N, K):
     g = torch.Generator("cuda").manual_seed(M + N + K)
     a = (torch.randn(M, K, device="cuda", generator=g)).half()
@@ -113,3 +113,61 @@ def test_attention_ws_many_items_matches_mma(pkg):
     for _ in range(3):
         b = pkg.attention_f16(qkv, B, T, heads, impl=2).float()
         torch.testing.assert_close(b, a, rtol=2e-3, atol=2e-3)
+
+
+# ---- the agent's view-check encoder: open_clip ViT-H/14 image tower, heads of dimension 80 (BSCAgent.py:309, 700-731)
+@pytest.mark.parametrize("T,heads,batch", [(257, 16, 2), (50, 3, 3), (17, 1, 1), (261, 2, 2)])
+def test_attention_head_dim_80(pkg, T, heads, batch):
+    g = torch.Generator("cuda").manual_seed(T + heads)
+    D = heads * 80
+    qkv = (torch.randn(batch * T, 3 * D, device="cuda", generator=g) * 0.8).half()
+    out = pkg.attention_f16(qkv, batch, T, heads, impl=0, head_dim=80).float().view(batch, T, heads, 80)
+    q, k, v = qkv.float().view(batch, T, 3, heads, 80).permute(2, 0, 3, 1, 4)
+    ref = (torch.softmax(q @ k.transpose(-1, -2), dim=-1) @ v).permute(0, 2, 1, 3)
+    torch.testing.assert_close(out, ref, rtol=2e-3, atol=2e-3)
+
+
+def test_tiny_h14_image_embedding_matches_oracle(pkg):
+    import dataclasses
+    cfg = dataclasses.replace(pkg.tiny(pkg.OPENCLIP_H14, dim=640, depth=2, heads=8, mlp=1280), embed=96)
+    w = pkg.random_weights(cfg, seed=8, perturb=True)
+    eng = pkg.ViTEngine(cfg, w, max_batch=3)
+    x = torch.randn(5, 3, 224, 224, generator=torch.Generator().manual_seed(3))
+    got = eng.encode_image(x.cuda()).cpu()
+    ref = vit_ref.encode_image(x, w, cfg)
+    assert got.shape == ref.shape == (5, 96)
+    assert _rel(got, ref) < 1e-3
+    # the patch-token output of the same engine (head dim 80 through forward_features)
+    tok = eng.forward_features(x.cuda())["x_norm_patchtokens"].cpu()
+    assert _rel(tok, vit_ref.vit_forward(x, w, cfg)) < 1e-3
+
+
+def test_full_h14_image_embedding_and_view_scores(pkg):
+    cfg = pkg.OPENCLIP_H14
+    w = pkg.random_weights(cfg, seed=0)
+    eng = pkg.ViTEngine(cfg, w, max_batch=4)
+    x = torch.randn(3, 3, 224, 224, generator=torch.Generator().manual_seed(4))
+    got = eng.encode_image(x.cuda())
+    ref = vit_ref.encode_image(x, w, cfg)
+    rel = _rel(got.cpu(), ref)
+    print("ViT-H/14 image embedding, max relative L2 error", rel)
+    assert got.shape == (3, 1024) and rel < 1e-3
+    # check_around: the views against an image goal (BSCAgent.py:721-731)
+    checker = pkg.ViewChecker(eng, turn_left=30)
+    best, prob = checker.best_view(x.cuda(), x[2])
+    ref_prob, ref_best = vit_ref.score_views(ref, ref[2])
+    assert best == int(ref_best) == 2
+    torch.testing.assert_close(prob.cpu(), ref_prob, rtol=1e-3, atol=1e-5)
+    assert checker.turn_actions(2) == ["turn_left"] * 2 and checker.turn_actions(9) == ["turn_right"] * 3
+    assert checker.turn_actions(14) == ["turn_left"] * 2          # second lap of views (BSCAgent.py:736-737)
+
+
+@pytest.mark.parametrize("n,E", [(12, 1024), (24, 1024), (1, 16), (37, 100)])
+def test_score_views_matches_torch(pkg, n, E):
+    g = torch.Generator().manual_seed(n + E)
+    emb, goal = torch.randn(n, E, generator=g), torch.randn(E, generator=g)
+    emb[n // 2] = goal * 3 + 0.2 * torch.randn(E, generator=g)
+    prob, best = pkg.score_views(emb.cuda(), goal.cuda())
+    ref_prob, ref_best = vit_ref.score_views(emb, goal)
+    assert int(best) == int(ref_best) == n // 2
+    torch.testing.assert_close(prob.cpu(), ref_prob, rtol=1e-5, atol=1e-7)

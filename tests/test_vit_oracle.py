@@ -62,6 +62,44 @@ def test_clip_oracle_matches_transformers():
     torch.testing.assert_close(got, ref, rtol=2e-4, atol=2e-4)
 
 
+def test_clip_image_embedding_head_dim_80_matches_transformers():
+    """The agent's view-check encoder (BSCAgent.py:309, open_clip ViT-H/14: heads of dimension 80, GELU(erf), bias-free
+    projection of the post-LayerNorm'd cls token) at test size against transformers.CLIPVisionModelWithProjection."""
+    from transformers import CLIPVisionConfig, CLIPVisionModelWithProjection
+    cfg = vc.tiny(vc.OPENCLIP_H14, dim=160, depth=2, heads=2, mlp=256)
+    cfg = vc.replace(cfg, embed=48)
+    assert cfg.head_dim == 80
+    w = vc.random_weights(cfg, seed=6, perturb=True)
+    hf = CLIPVisionModelWithProjection(CLIPVisionConfig(
+        hidden_size=cfg.dim, intermediate_size=cfg.mlp, num_hidden_layers=cfg.depth, num_attention_heads=cfg.heads,
+        image_size=cfg.image, patch_size=cfg.patch, hidden_act="gelu", layer_norm_eps=cfg.ln_eps, projection_dim=cfg.embed)).eval()
+    vm = hf.vision_model
+    with torch.no_grad():
+        vm.embeddings.patch_embedding.weight.copy_(w["patch_w"].view(cfg.dim, 3, cfg.patch, cfg.patch))
+        vm.embeddings.class_embedding.copy_(w["cls"])
+        vm.embeddings.position_embedding.weight.copy_(w["pos"])
+        vm.pre_layrnorm.weight.copy_(w["ln_pre_w"]); vm.pre_layrnorm.bias.copy_(w["ln_pre_b"])
+        vm.post_layernorm.weight.copy_(w["ln_post_w"]); vm.post_layernorm.bias.copy_(w["ln_post_b"])
+        hf.visual_projection.weight.copy_(w["proj"].T)
+
+    def get(i):
+        L = vm.encoder.layers[i]
+        a = L.self_attn
+        return {"ln1_w": L.layer_norm1.weight, "ln1_b": L.layer_norm1.bias, "ln2_w": L.layer_norm2.weight, "ln2_b": L.layer_norm2.bias,
+                "q_w": a.q_proj.weight, "q_b": a.q_proj.bias, "k_w": a.k_proj.weight, "k_b": a.k_proj.bias, "v_w": a.v_proj.weight,
+                "v_b": a.v_proj.bias, "proj_w": a.out_proj.weight, "proj_b": a.out_proj.bias, "fc1_w": L.mlp.fc1.weight,
+                "fc1_b": L.mlp.fc1.bias, "fc2_w": L.mlp.fc2.weight, "fc2_b": L.mlp.fc2.bias}
+    _copy_layers(cfg, w, get)
+    x = torch.randn(3, 3, cfg.image, cfg.image, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        ref = hf(pixel_values=x).image_embeds
+    got = vit_ref.encode_image(x, w, cfg)
+    torch.testing.assert_close(got, ref, rtol=2e-4, atol=2e-4)
+    # check_around's scoring on those embeddings (BSCAgent.py:713-718): literal torch restatement
+    prob, best = vit_ref.score_views(got, got[1])
+    assert int(best) == 1 and abs(float(prob.sum()) - 1.0) < 1e-6
+
+
 def test_dinov2_reg_oracle_matches_transformers():
     try:
         from transformers import Dinov2WithRegistersConfig, Dinov2WithRegistersModel

@@ -46,7 +46,7 @@ class Filter(C.Structure):
 class VitCfg(C.Structure):
     _fields_ = [("image", C.c_int32), ("patch", C.c_int32), ("dim", C.c_int32), ("depth", C.c_int32), ("heads", C.c_int32),
                 ("mlp", C.c_int32), ("n_reg", C.c_int32), ("act", C.c_int32), ("ln_pre", C.c_int32),
-                ("patch_k_pad", C.c_int32), ("ln_eps", C.c_float), ("head_dim", C.c_int32)]
+                ("patch_k_pad", C.c_int32), ("ln_eps", C.c_float), ("head_dim", C.c_int32), ("text_context", C.c_int32)]
 
 
 _P = C.c_void_p
@@ -87,7 +87,8 @@ _SIGS = {
     "bscnav_vit_forward_images": (C.c_int, [_P, _P, C.c_int32, _P, _P]),
     "bscnav_vit_encode_images": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, _P, _P]),
     "bscnav_score_views": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
-    "bscnav_attention_f16_hd": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "bscnav_attention_f16_hd": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "bscnav_text_encode": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P, _P]),
     "bscnav_gaussian_pool": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "bscnav_attention_f16": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "bscnav_gemm_f16": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),

@@ -133,3 +133,11 @@ class ViewChecker:
         if max_idx * self.turn_left <= 180:
             return ["turn_left"] * max_idx
         return ["turn_right"] * (num_turns - max_idx)
+
+
+def match_long_memory_label(text_features, label_features) -> int:
+    """Long-term label matching (BSCAgent.py:541-557): the stored label whose CLIP text embedding is closest (cosine) to the
+    prompt's; embeddings from a text-tower ViTEngine (`encode_text`), arg-max on the device."""
+    from .vit import score_views
+    _prob, best = score_views(label_features, text_features.reshape(-1))
+    return int(best)

@@ -257,7 +257,7 @@ using namespace bscnav;
 // impl 0 = mma.sync kernel, 1 = tcgen05 kernel.
 extern "C" int bscnav_attention_f16(const void* qkv, void* out, int32_t batch, int32_t T, int32_t heads, int32_t impl, void* stream) {
   if (!qkv || !out || batch <= 0 || T <= 0 || heads <= 0) return BSCNAV_EINVAL;
-  if (impl == 0) return attention_f16(static_cast<const __half*>(qkv), static_cast<__half*>(out), batch, T, heads, 64, (cudaStream_t)stream);
+  if (impl == 0) return attention_f16(static_cast<const __half*>(qkv), static_cast<__half*>(out), batch, T, heads, 64, false, (cudaStream_t)stream);
   CUtensorMap m128, m16;
   if (impl == 2) {
     if (int e = make_qkv_map3d(&m128, qkv, batch, T, 3LL * heads * 64, 128)) return e;
@@ -269,9 +269,10 @@ extern "C" int bscnav_attention_f16(const void* qkv, void* out, int32_t batch, i
   return attention_tc_launch(&m128, &m16, static_cast<__half*>(out), batch, T, heads, (cudaStream_t)stream);
 }
 
-// The same with an explicit head dim (64 | 80; 80 = ViT-H/14, mma.sync kernel only): qkv [batch*T, 3*heads*head_dim].
+// The mma.sync kernel with an explicit head dim (64 | 80; 80 = ViT-H/14) and optional causal mask (head dim 64, text tower).
 extern "C" int bscnav_attention_f16_hd(const void* qkv, void* out, int32_t batch, int32_t T, int32_t heads, int32_t head_dim,
-                                       void* stream) {
+                                       int32_t causal, void* stream) {
   if (!qkv || !out || batch <= 0 || T <= 0 || heads <= 0) return BSCNAV_EINVAL;
-  return attention_f16(static_cast<const __half*>(qkv), static_cast<__half*>(out), batch, T, heads, head_dim, (cudaStream_t)stream);
+  return attention_f16(static_cast<const __half*>(qkv), static_cast<__half*>(out), batch, T, heads, head_dim, causal != 0,
+                       (cudaStream_t)stream);
 }

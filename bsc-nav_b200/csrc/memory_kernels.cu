@@ -689,7 +689,7 @@ using namespace bscnav;
 
 extern "C" {
 
-int bscnav_abi_version(void) { return 1; }
+int bscnav_abi_version(void) { return 2; }
 const char* bscnav_last_error(void) { return g_last_error; }
 int64_t bscnav_launch_count(void) { return g_launches.load(); }
 

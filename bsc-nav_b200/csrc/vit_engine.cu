@@ -4,6 +4,9 @@
 //               fc1_w [M, D], fc2_w [D, M] (LayerScale folded) }
 //   float blob: patch_b [D] | cls_pos [D] | reg [n_reg, D] | pos [Np, D] | ln_pre_w, ln_pre_b [D] (if ln_pre) |
 //               per layer { ln1_w, ln1_b [D], qkv_b [3D], proj_b [D], ln2_w, ln2_b [D], fc1_b [M], fc2_b [D] } | ln_post_w, ln_post_b [D]
+// Text tower (cfg.text_context > 0, open_clip encode_text for the agent's goal / label matching, BSCAgent.py:541-557, 708-711):
+//   half blob : per layer { qkv_w, proj_w, fc1_w, fc2_w };  float blob: pos [ctx, D] | per layer { ... } | ln_final_w, ln_final_b
+//   causal attention, no patch embedding / cls / registers / pre-LN; the token-embedding table is passed per call.
 #include <cstdlib>
 #include <vector>
 #include "gemm_tcgen05.cuh"
@@ -26,13 +29,18 @@ static int vit_layout(const bscnav_vit_cfg_t* c, VitLayout* L) {
   if (!c || c->depth <= 0 || c->depth > 64 || c->dim % 128 || c->mlp % 128 || c->heads <= 0) return BSCNAV_EINVAL;
   const int hd = c->head_dim ? c->head_dim : 64;
   if ((hd != 64 && hd != 80) || c->dim != c->heads * hd) return BSCNAV_EINVAL;
-  if (c->image % c->patch || c->patch_k_pad % 64 || c->patch_k_pad < 3 * c->patch * c->patch) return BSCNAV_EINVAL;
-  const long long D = c->dim, M = c->mlp, Np = (long long)(c->image / c->patch) * (c->image / c->patch);
+  const bool text = c->text_context > 0;
+  if (c->text_context < 0 || (text && (hd != 64 || c->n_reg || c->ln_pre))) return BSCNAV_EINVAL;
+  if (!text && (c->patch <= 0 || c->image % c->patch || c->patch_k_pad % 64 || c->patch_k_pad < 3 * c->patch * c->patch)) return BSCNAV_EINVAL;
+  const long long D = c->dim, M = c->mlp;
+  const long long Np = text ? c->text_context : (long long)(c->image / c->patch) * (c->image / c->patch);
   long long h = 0, f = 0;
-  L->patch_w = h; h += D * c->patch_k_pad;
-  L->patch_b = f; f += D;
-  L->cls_pos = f; f += D;
-  L->reg = f; f += (long long)c->n_reg * D;
+  if (!text) {
+    L->patch_w = h; h += D * c->patch_k_pad;
+    L->patch_b = f; f += D;
+    L->cls_pos = f; f += D;
+    L->reg = f; f += (long long)c->n_reg * D;
+  }
   L->pos = f; f += Np * D;
   if (c->ln_pre) { L->ln_pre_w = f; f += D; L->ln_pre_b = f; f += D; }
   for (int i = 0; i < c->depth; ++i) {
@@ -66,16 +74,18 @@ struct Workspace {
   long long total;
 };
 static void workspace_layout(const bscnav_vit_cfg_t* c, int max_batch, Workspace* w, char* base) {
-  const long long D = c->dim, M = c->mlp, G = c->image / c->patch, Np = G * G, T = 1 + c->n_reg + Np, B = max_batch;
+  const bool text = c->text_context > 0;
+  const long long D = c->dim, M = c->mlp, G = text ? 0 : c->image / c->patch, Np = G * G, B = max_batch;
+  const long long T = text ? c->text_context : 1 + c->n_reg + Np;
   long long off = 0;
   auto take = [&](long long bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes, 1024); return p; };
-  w->a0 = reinterpret_cast<__half*>(take(B * Np * c->patch_k_pad * 2));
+  w->a0 = reinterpret_cast<__half*>(take(text ? 0 : B * Np * c->patch_k_pad * 2));
   w->x = reinterpret_cast<float*>(take(B * T * D * 4));
   w->y = reinterpret_cast<__half*>(take(B * T * D * 2));
   w->qkv = reinterpret_cast<__half*>(take(B * T * 3 * D * 2));
   w->ao = reinterpret_cast<__half*>(take(B * T * D * 2));
   w->hmid = reinterpret_cast<__half*>(take(B * T * M * 2));
-  w->pre_tab = reinterpret_cast<float*>(take(preprocess_table_bytes(c->image)));
+  w->pre_tab = reinterpret_cast<float*>(take(text ? 0 : preprocess_table_bytes(c->image)));
   w->total = off;
 }
 
@@ -117,11 +127,14 @@ struct ProfScope {
   ~ProfScope() { if (idx) cudaEventRecord(e->spans[idx - 1].e1, s); }
 };
 
+static int run_layers(VitEngine* e, int batch, cudaStream_t stream);
+
 // out_tokens: LayerNorm(post) patch tokens [batch, Np, D]; or (proj != null) out_embed: the cls token's image embedding [batch, E]
 static int vit_run(VitEngine* e, int batch, float* out_tokens, cudaStream_t stream, const float* proj = nullptr, int embed_dim = 0,
                    float* out_embed = nullptr) {
   const bscnav_vit_cfg_t& c = e->cfg;
-  const int D = c.dim, M = c.mlp, T = e->T, Np = e->Np;
+  if (c.text_context > 0) return BSCNAV_EINVAL;        // a text engine has no image path
+  const int D = c.dim, T = e->T, Np = e->Np;
   const int rows = batch * T;
   const float* wf = e->wf;
   // patch embedding + position embedding, written straight into the residual stream at the patch rows
@@ -133,6 +146,19 @@ static int vit_run(VitEngine* e, int batch, float* out_tokens, cudaStream_t stre
   if (int r = fill_prefix_tokens(e->ws.x, wf + e->L.cls_pos, wf + e->L.reg, batch, T, c.n_reg, D, stream)) return r;
   if (c.ln_pre)
     if (int r = layernorm_inplace(e->ws.x, wf + e->L.ln_pre_w, wf + e->L.ln_pre_b, c.ln_eps, rows, D, stream)) return r;
+  if (int r = run_layers(e, batch, stream)) return r;
+  if (proj) return cls_embed(e->ws.x, wf + e->L.ln_post_w, wf + e->L.ln_post_b, c.ln_eps, batch, T, D, proj, embed_dim, out_embed, nullptr, stream);
+  return layernorm_patch_tokens(e->ws.x, wf + e->L.ln_post_w, wf + e->L.ln_post_b, c.ln_eps, batch, T, 1 + c.n_reg, D,
+                                out_tokens, stream);
+}
+
+// the transformer blocks over the residual stream ws.x [batch*T, D] (image and text towers)
+static int run_layers(VitEngine* e, int batch, cudaStream_t stream) {
+  const bscnav_vit_cfg_t& c = e->cfg;
+  const int D = c.dim, M = c.mlp, T = e->T;
+  const int rows = batch * T;
+  const float* wf = e->wf;
+  const bool causal = c.text_context > 0;
   for (int i = 0; i < c.depth; ++i) {
     const LayerOff& o = e->L.layer[i];
     { ProfScope ps(e, stream, kCatLayerNorm, (double)rows * D * 6);
@@ -146,7 +172,7 @@ static int vit_run(VitEngine* e, int batch, float* out_tokens, cudaStream_t stre
         // the 3-D map's frame extent is the engine's max_batch: frames >= batch are simply never addressed
         if (int r = attention_ws_launch(&e->qkv3d128, &e->qkv3d16, e->ws.ao, batch, T, c.heads, stream)) return r;
       } else if (e->attn_impl == 1) { if (int r = attention_tc_launch(&e->qkv128, &e->qkv16, e->ws.ao, batch, T, c.heads, stream)) return r; }
-      else if (int r = attention_f16(e->ws.qkv, e->ws.ao, batch, T, c.heads, c.head_dim ? c.head_dim : 64, stream)) return r; }
+      else if (int r = attention_f16(e->ws.qkv, e->ws.ao, batch, T, c.heads, c.head_dim ? c.head_dim : 64, causal, stream)) return r; }
     GemmEpilogue e2{};
     e2.out = e->ws.x; e2.bias = wf + o.proj_b; e2.ld_out = D; e2.mode = kOutResidual;
     { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * (double)D * D);
@@ -162,9 +188,7 @@ static int vit_run(VitEngine* e, int batch, float* out_tokens, cudaStream_t stre
     { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * (double)M * D);
       if (int r = gemm_f16_launch(&e->map_h, &e->map_fc2[i], &e->out_x, rows, D, M, e4, stream, e->has_half[3] ? &e->half_fc2[i] : nullptr)) return r; }
   }
-  if (proj) return cls_embed(e->ws.x, wf + e->L.ln_post_w, wf + e->L.ln_post_b, c.ln_eps, batch, T, D, proj, embed_dim, out_embed, stream);
-  return layernorm_patch_tokens(e->ws.x, wf + e->L.ln_post_w, wf + e->L.ln_post_b, c.ln_eps, batch, T, 1 + c.n_reg, D,
-                                out_tokens, stream);
+  return BSCNAV_OK;
 }
 
 }  // namespace bscnav
@@ -202,12 +226,13 @@ int bscnav_vit_create(const bscnav_vit_cfg_t* c, const void* w_half, const float
   e->wh = static_cast<const __half*>(w_half);
   e->wf = w_float;
   e->max_batch = max_batch;
-  const int G = c->image / c->patch;
+  const bool text = c->text_context > 0;
+  const int G = text ? 0 : c->image / c->patch;
   e->Np = G * G;
-  e->T = 1 + c->n_reg + e->Np;
+  e->T = text ? c->text_context : 1 + c->n_reg + e->Np;
   const long long D = c->dim, M = c->mlp, rows = (long long)max_batch * e->T;
   int r = 0;
-  r = r ? r : make_operand_map(&e->map_a0, e->ws.a0, (long long)max_batch * e->Np, c->patch_k_pad, 128);
+  if (!text) r = r ? r : make_operand_map(&e->map_a0, e->ws.a0, (long long)max_batch * e->Np, c->patch_k_pad, 128);
   r = r ? r : make_operand_map(&e->map_y, e->ws.y, rows, D, 128);
   r = r ? r : make_operand_map(&e->map_ao, e->ws.ao, rows, D, 128);
   r = r ? r : make_operand_map(&e->map_h, e->ws.hmid, rows, M, 128);
@@ -215,7 +240,7 @@ int bscnav_vit_create(const bscnav_vit_cfg_t* c, const void* w_half, const float
   // BSCNAV_ATTENTION=0|1|2 selects mma.sync / tcgen05 v1 / tcgen05 warp-specialised (tests exercise all three)
   const char* impl_env = getenv("BSCNAV_ATTENTION");
   e->attn_impl = impl_env ? atoi(impl_env) : 2;
-  if (c->head_dim && c->head_dim != 64) e->attn_impl = 0;          // the tcgen05 kernels are specialised to head dim 64
+  if ((c->head_dim && c->head_dim != 64) || text) e->attn_impl = 0;  // the tcgen05 kernels: head dim 64, no causal mask
   if (e->attn_impl == 2 && !attention_ws_supported(e->T)) e->attn_impl = 0;
   if (e->attn_impl == 1 && !attention_tc_supported(e->T)) e->attn_impl = 0;
   r = r ? r : make_qkv_map3d(&e->qkv3d128, e->ws.qkv, max_batch, e->T, 3 * D, 128);
@@ -225,7 +250,7 @@ int bscnav_vit_create(const bscnav_vit_cfg_t* c, const void* w_half, const float
   r = r ? r : make_store_map(&e->out_qkv, e->ws.qkv, rows, 3 * D, false);
   r = r ? r : make_store_map(&e->out_h, e->ws.hmid, rows, M, false);
   r = r ? r : make_store_map(&e->out_x, e->ws.x, rows, D, true);
-  r = r ? r : make_operand_map(&e->map_patch_w, e->wh + e->L.patch_w, D, c->patch_k_pad, gemm_block_n((int)D));
+  if (!text) r = r ? r : make_operand_map(&e->map_patch_w, e->wh + e->L.patch_w, D, c->patch_k_pad, gemm_block_n((int)D));
   for (int i = 0; i < c->depth && !r; ++i) {
     const LayerOff& o = e->L.layer[i];
     r = r ? r : make_operand_map(&e->map_qkv[i], e->wh + o.qkv_w, 3 * D, D, gemm_block_n((int)(3 * D)));
@@ -269,6 +294,7 @@ int bscnav_vit_profile_read(void* engine, double* out_ms, double* out_work, int3
 }
 
 static int clear_a0_once(VitEngine* e, cudaStream_t stream) {
+  if (e->cfg.text_context > 0) return BSCNAV_EINVAL;     // text engine: image entry points do not apply
   // the K padding columns of the patch rows are never written by im2col: zero them once
   if (!e->a0_cleared) {
     BSC_CUDA(cudaMemsetAsync(e->ws.a0, 0, (size_t)e->max_batch * e->Np * e->cfg.patch_k_pad * 2, stream));
@@ -306,6 +332,19 @@ int bscnav_vit_encode_images(void* engine, const float* images, int32_t batch, c
   if (int r = clear_a0_once(e, stream)) return r;
   if (int r = im2col_images(images, batch, e->cfg.image, e->cfg.patch, e->cfg.patch_k_pad, e->ws.a0, stream)) return r;
   return vit_run(e, batch, nullptr, stream, proj, embed_dim, out_embed);
+}
+
+int bscnav_text_encode(void* engine, const int32_t* token_ids, int32_t batch, const float* token_embedding, int32_t vocab,
+                       const float* proj, int32_t embed_dim, float* out_embed, void* stream_) {
+  VitEngine* e = static_cast<VitEngine*>(engine);
+  if (!e || !token_ids || !token_embedding || !proj || !out_embed || vocab <= 0 || embed_dim <= 0) return BSCNAV_EINVAL;
+  if (e->cfg.text_context <= 0 || batch <= 0 || batch > e->max_batch) return BSCNAV_EINVAL;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bscnav_vit_cfg_t& c = e->cfg;
+  if (int r = text_embed(token_ids, token_embedding, vocab, e->wf + e->L.pos, batch, e->T, c.dim, e->ws.x, stream)) return r;
+  if (int r = run_layers(e, batch, stream)) return r;
+  return cls_embed(e->ws.x, e->wf + e->L.ln_post_w, e->wf + e->L.ln_post_b, c.ln_eps, batch, e->T, c.dim, proj, embed_dim, out_embed,
+                   token_ids, stream);
 }
 
 }  // extern "C"

@@ -334,7 +334,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 static constexpr int kAttnWarps = 6;        // 257 (261) tokens = 17 row groups of 16 -> 3 rounds of 6 warps, 94% of lanes busy
 static constexpr int kAttnThreads = kAttnWarps * 32;
 
-template <int HD>
+template <int HD, bool CAUSAL>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 k_attention(const __half* __restrict__ qkv, __half* __restrict__ out, int T, int heads, int t_pad) {
   extern __shared__ __align__(128) uint8_t smem_attn[];
@@ -380,7 +380,10 @@ k_attention(const __half* __restrict__ qkv, __half* __restrict__ out, int T, int
     for (int i = 0; i < NT; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // running max / sum of rows r0 and r1
 
-    for (int kb = 0; kb < n_kb; ++kb) {
+    // causal (text tower): keys <= query row only, so key blocks past this row group are skipped; a visited block starts at
+    // or before the group's first row (kb*64 <= g*16), hence still holds a valid key for every row of the group
+    const int n_kb_g = CAUSAL ? min(n_kb, (g * 16 + 15) / 64 + 1) : n_kb;
+    for (int kb = 0; kb < n_kb_g; ++kb) {
       // 16-key groups of this block that hold at least one real key (T = 257: the last block has one of four)
       const int ng = (kb == n_kb - 1) ? (T - kb * 64 + 15) >> 4 : 4;
       float s[8][4];
@@ -413,6 +416,16 @@ k_attention(const __half* __restrict__ qkv, __half* __restrict__ out, int T, int
           const int key = kb * 64 + i * 8 + 2 * (lane & 3);
           if (key >= T) { s[i][0] = -INFINITY; s[i][2] = -INFINITY; }
           if (key + 1 >= T) { s[i][1] = -INFINITY; s[i][3] = -INFINITY; }
+        }
+      }
+      if (CAUSAL && kb * 64 + 63 > g * 16) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int key = kb * 64 + i * 8 + 2 * (lane & 3);
+          if (key > r0) s[i][0] = -INFINITY;
+          if (key + 1 > r0) s[i][1] = -INFINITY;
+          if (key > r1) s[i][2] = -INFINITY;
+          if (key + 1 > r1) s[i][3] = -INFINITY;
         }
       }
       float bm0 = -INFINITY, bm1 = -INFINITY;
@@ -470,24 +483,25 @@ k_attention(const __half* __restrict__ qkv, __half* __restrict__ out, int T, int
   }
 }
 
-template <int HD>
+template <int HD, bool CAUSAL>
 static int attention_launch(const __half* qkv, __half* out, int batch, int T, int heads, cudaStream_t stream) {
   const int t_pad = (T + 15) / 16 * 16;      // only whole 16-key groups are ever read (see `ng` in the kernel)
   const int smem = 2 * t_pad * kv_row_bytes<HD>();
   if (smem > 200 * 1024) return BSCNAV_EINVAL;
   static int attr_smem = 0;
   if (smem > attr_smem) {
-    BSC_CUDA(cudaFuncSetAttribute(k_attention<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    BSC_CUDA(cudaFuncSetAttribute((k_attention<HD, CAUSAL>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem = smem;
   }
-  BSC_LAUNCH(k_attention<HD>, dim3((unsigned)heads, (unsigned)batch), kAttnThreads, smem, stream, qkv, out, T, heads, t_pad);
+  BSC_LAUNCH((k_attention<HD, CAUSAL>), dim3((unsigned)heads, (unsigned)batch), kAttnThreads, smem, stream, qkv, out, T, heads, t_pad);
   return BSCNAV_OK;
 }
 
-int attention_f16(const __half* qkv, __half* out, int batch, int T, int heads, int head_dim, cudaStream_t stream) {
+int attention_f16(const __half* qkv, __half* out, int batch, int T, int heads, int head_dim, bool causal, cudaStream_t stream) {
   if (batch <= 0 || T <= 0 || heads <= 0) return BSCNAV_EINVAL;
-  if (head_dim == 64) return attention_launch<64>(qkv, out, batch, T, heads, stream);
-  if (head_dim == 80) return attention_launch<80>(qkv, out, batch, T, heads, stream);
+  if (head_dim == 64) return causal ? attention_launch<64, true>(qkv, out, batch, T, heads, stream)
+                                    : attention_launch<64, false>(qkv, out, batch, T, heads, stream);
+  if (head_dim == 80 && !causal) return attention_launch<80, false>(qkv, out, batch, T, heads, stream);
   return BSCNAV_EINVAL;
 }
 
@@ -524,13 +538,28 @@ __global__ void k_gaussian_pool(const float* __restrict__ tokens, int batch, int
 // ---------------------------------------------------------------------------------------------------------
 // Image-embedding head (open_clip VisionTransformer: pooled = ln_post(x[:, 0]); pooled @ proj): one block per frame.
 // LayerNorm in two passes (mean, centred variance) like k_layernorm; the D x E product in fp32, proj read coalesced.
+// ids != null (text tower, open_clip encode_text): the pooled row is the end-of-text position = argmax of the token ids
+// (first position of the largest id), instead of row 0.
 __global__ void __launch_bounds__(256)
 k_cls_embed(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int tokens,
-            int D, const float* __restrict__ proj, int E, float* __restrict__ out) {
+            int D, const float* __restrict__ proj, int E, float* __restrict__ out, const int32_t* __restrict__ ids) {
   extern __shared__ float cls_row[];
   __shared__ float red[8];
+  __shared__ int pooled_row;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* xr = x + (long long)b * tokens * D;
+  if (tid == 0) {
+    int row = 0;
+    if (ids) {
+      int best = ids[(long long)b * tokens];
+      for (int t = 1; t < tokens; ++t) {
+        const int v = ids[(long long)b * tokens + t];
+        if (v > best) { best = v; row = t; }
+      }
+    }
+    pooled_row = row;
+  }
+  __syncthreads();
+  const float* xr = x + ((long long)b * tokens + pooled_row) * D;
   auto block_sum = [&](float v) {
     v = warp_sum(v);
     __syncthreads();
@@ -556,9 +585,32 @@ k_cls_embed(const float* __restrict__ x, const float* __restrict__ gamma, const 
 }
 
 int cls_embed(const float* x, const float* g, const float* b, float eps, int batch, int tokens, int D, const float* proj, int E,
-              float* out, cudaStream_t stream) {
+              float* out, const int32_t* ids, cudaStream_t stream) {
   if (batch <= 0 || D <= 0 || E <= 0 || D * 4 > 48 * 1024) return BSCNAV_EINVAL;
-  BSC_LAUNCH(k_cls_embed, (unsigned)batch, 256, D * sizeof(float), stream, x, g, b, eps, tokens, D, proj, E, out);
+  BSC_LAUNCH(k_cls_embed, (unsigned)batch, 256, D * sizeof(float), stream, x, g, b, eps, tokens, D, proj, E, out, ids);
+  return BSCNAV_OK;
+}
+
+// Text tower input (open_clip encode_text): x[b, t, :] = token_embedding[ids[b, t]] + positional_embedding[t]
+__global__ void k_text_embed(const int32_t* __restrict__ ids, const float* __restrict__ tok_emb, int vocab, const float* __restrict__ pos,
+                             int batch, int ctx, int D, float* __restrict__ x) {
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // one float4 per thread
+  const int d4 = D >> 2;
+  if (i4 >= (long long)batch * ctx * d4) return;
+  const int c = (int)(i4 % d4);
+  const long long bt = i4 / d4;
+  const int t = (int)(bt % ctx);
+  int id = ids[bt];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  const float4 a = reinterpret_cast<const float4*>(tok_emb + (long long)id * D)[c];
+  const float4 p = reinterpret_cast<const float4*>(pos + (long long)t * D)[c];
+  reinterpret_cast<float4*>(x)[i4] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+}
+int text_embed(const int32_t* ids, const float* tok_emb, int vocab, const float* pos, int batch, int ctx, int D, float* x,
+               cudaStream_t stream) {
+  if (batch <= 0 || ctx <= 0 || vocab <= 0 || D % 4) return BSCNAV_EINVAL;
+  const long long total = (long long)batch * ctx * (D / 4);
+  BSC_LAUNCH(k_text_embed, (unsigned)((total + 255) / 256), 256, 0, stream, ids, tok_emb, vocab, pos, batch, ctx, D, x);
   return BSCNAV_OK;
 }
 

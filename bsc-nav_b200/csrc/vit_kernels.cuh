@@ -14,9 +14,14 @@ int layernorm_half(const float* x, const float* g, const float* b, float eps, lo
 int layernorm_inplace(float* x, const float* g, const float* b, float eps, long long rows, int D, cudaStream_t s);
 int layernorm_patch_tokens(const float* x, const float* g, const float* b, float eps, int batch, int tokens, int skip, int D,
                            float* out, cudaStream_t s);
-int attention_f16(const __half* qkv, __half* out, int batch, int T, int heads, int head_dim, cudaStream_t stream);   // mma.sync kernel, head dim 64 | 80
+// mma.sync kernel, head dim 64 | 80; causal (keys <= query row, text tower): head dim 64
+int attention_f16(const __half* qkv, __half* out, int batch, int T, int heads, int head_dim, bool causal, cudaStream_t stream);
 // image-embedding head (CLIP encode_image): LayerNorm of each frame's cls row, times proj [D, E] (fp32) -> out [batch, E]
+// ids != null: pool the row at argmax(ids[b, :]) (end-of-text token of the text tower) instead of row 0
 int cls_embed(const float* x, const float* g, const float* b, float eps, int batch, int tokens, int D, const float* proj, int E,
-              float* out, cudaStream_t stream);
+              float* out, const int32_t* ids, cudaStream_t stream);
+// text tower input: x[b, t, :] = tok_emb[ids[b, t]] + pos[t]
+int text_embed(const int32_t* ids, const float* tok_emb, int vocab, const float* pos, int batch, int ctx, int D, float* x,
+               cudaStream_t stream);
 
 }  // namespace bscnav

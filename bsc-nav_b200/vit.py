@@ -20,7 +20,7 @@ def _cfg_struct(cfg: ViTConfig) -> _lib.VitCfg:
     k_pad = (cfg.patch_k + 63) // 64 * 64
     return _lib.VitCfg(image=cfg.image, patch=cfg.patch, dim=cfg.dim, depth=cfg.depth, heads=cfg.heads, mlp=cfg.mlp,
                        n_reg=cfg.n_reg, act=0 if cfg.act == "gelu" else 1, ln_pre=1 if cfg.ln_pre else 0,
-                       patch_k_pad=k_pad, ln_eps=cfg.ln_eps, head_dim=cfg.dim // cfg.heads)
+                       patch_k_pad=k_pad, ln_eps=cfg.ln_eps, head_dim=cfg.dim // cfg.heads, text_context=cfg.text_context)
 
 
 def pack_weights(cfg: ViTConfig, w: dict):
@@ -37,13 +37,16 @@ def pack_weights(cfg: ViTConfig, w: dict):
         raise ValueError("engine supports head_dim 64 (tcgen05 attention) and 80 (ViT-H/14, mma.sync attention)")
     k_pad = (cfg.patch_k + 63) // 64 * 64
     half, flt = [], []
-    pw = torch.zeros(D, k_pad)
-    pw[:, : cfg.patch_k] = w["patch_w"]
-    half.append(pw)
-    flt += [w["patch_b"] if cfg.patch_bias else torch.zeros(D), w["cls"] + w["pos"][0]]
-    if cfg.n_reg:
-        flt.append(w["reg"].reshape(-1))
-    flt.append(w["pos"][1:].reshape(-1))
+    if cfg.text_context:                      # text tower: no patch embedding / cls; the token table stays a separate tensor
+        flt.append(w["pos"].reshape(-1))
+    else:
+        pw = torch.zeros(D, k_pad)
+        pw[:, : cfg.patch_k] = w["patch_w"]
+        half.append(pw)
+        flt += [w["patch_b"] if cfg.patch_bias else torch.zeros(D), w["cls"] + w["pos"][0]]
+        if cfg.n_reg:
+            flt.append(w["reg"].reshape(-1))
+        flt.append(w["pos"][1:].reshape(-1))
     if cfg.ln_pre:
         flt += [w["ln_pre_w"], w["ln_pre_b"]]
     qs = 1.0 / math.sqrt(dh)
@@ -79,6 +82,7 @@ class ViTEngine:
         self.w_half = hb.to(self.device)
         self.w_float = fb.to(self.device)
         self.proj = weights["proj"].to(self.device, torch.float32).contiguous() if "proj" in weights else None
+        self.tok_emb = weights["tok_emb"].to(self.device, torch.float32).contiguous() if cfg.text_context else None
         nbytes = _lib.check(self.lib.bscnav_vit_workspace_bytes(C.byref(self._c), self.max_batch), "vit_workspace_bytes")
         self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         h = C.c_void_p()
@@ -132,6 +136,21 @@ class ViTEngine:
             nb = min(self.max_batch, B - b0)
             _lib.check(self.lib.bscnav_vit_encode_images(self._h, _lib.ptr(x[b0:]), nb, _lib.ptr(self.proj), E, _lib.ptr(out[b0:]),
                                                          _lib.stream_ptr()), "vit_encode_images")
+        return out
+
+    # -- open_clip `encode_text` (BSCAgent.py:545-546, 711): token ids (B, context) from the caller's tokenizer -> (B, embed)
+    @torch.no_grad()
+    def encode_text(self, token_ids: torch.Tensor) -> torch.Tensor:
+        if not self.cfg.text_context or self.proj is None:
+            raise _lib.BscnavError("not a text tower (cfg.text_context, weights['tok_emb'], weights['proj'])")
+        ids = token_ids.to(self.device, torch.int32).contiguous()
+        assert ids.dim() == 2 and ids.shape[1] == self.cfg.text_context, ids.shape
+        B, E = ids.shape[0], self.proj.shape[1]
+        out = torch.empty(B, E, dtype=torch.float32, device=self.device)
+        for b0 in range(0, B, self.max_batch):
+            nb = min(self.max_batch, B - b0)
+            _lib.check(self.lib.bscnav_text_encode(self._h, _lib.ptr(ids[b0:]), nb, _lib.ptr(self.tok_emb), self.tok_emb.shape[0],
+                                                   _lib.ptr(self.proj), E, _lib.ptr(out[b0:]), _lib.stream_ptr()), "text_encode")
         return out
 
     def profile(self, enable: bool):
@@ -188,15 +207,16 @@ def score_views(embeds: torch.Tensor, goal: torch.Tensor):
     return prob, best[0].long()
 
 
-def attention_f16(qkv: torch.Tensor, batch: int, T: int, heads: int, impl: int = 1, head_dim: int = 64) -> torch.Tensor:
+def attention_f16(qkv: torch.Tensor, batch: int, T: int, heads: int, impl: int = 1, head_dim: int = 64,
+                  causal: bool = False) -> torch.Tensor:
     """Self-attention over a packed fp16 qkv tensor [batch*T, 3*heads*head_dim] (q pre-scaled); impl 0 = mma.sync (head_dim 64
-    or 80), 1 / 2 = tcgen05 kernels (head_dim 64)."""
+    or 80, optional causal mask at head_dim 64), 1 / 2 = tcgen05 kernels (head_dim 64, no mask)."""
     out = torch.empty(batch * T, heads * head_dim, dtype=torch.float16, device=qkv.device)
-    if head_dim != 64:
+    if head_dim != 64 or causal:
         if impl != 0:
-            raise ValueError("head_dim != 64 runs on the mma.sync kernel only (impl=0)")
-        _lib.check(_lib.lib().bscnav_attention_f16_hd(_lib.ptr(qkv), _lib.ptr(out), batch, T, heads, head_dim, _lib.stream_ptr()),
-                   "attention_f16_hd")
+            raise ValueError("head_dim != 64 and causal masks run on the mma.sync kernel only (impl=0)")
+        _lib.check(_lib.lib().bscnav_attention_f16_hd(_lib.ptr(qkv), _lib.ptr(out), batch, T, heads, head_dim, 1 if causal else 0,
+                                                      _lib.stream_ptr()), "attention_f16_hd")
         return out
     _lib.check(_lib.lib().bscnav_attention_f16(_lib.ptr(qkv), _lib.ptr(out), batch, T, heads, impl, _lib.stream_ptr()), "attention_f16")
     return out

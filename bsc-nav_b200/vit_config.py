@@ -28,6 +28,8 @@ class ViTConfig:
     ln_eps: float = 1e-6
     patch_bias: bool = True
     embed: int = 0            # image-embedding width of the cls head (CLIP `proj`, D x embed, no bias); 0 = no head
+    text_context: int = 0     # > 0: CLIP text tower over this many positions (causal attention, pooled at the end-of-text token)
+    vocab: int = 0            # text tower: rows of the token-embedding table
 
     @property
     def head_dim(self) -> int:
@@ -43,7 +45,7 @@ class ViTConfig:
 
     @property
     def tokens(self) -> int:
-        return 1 + self.n_reg + self.n_patch
+        return self.text_context if self.text_context else 1 + self.n_reg + self.n_patch
 
     @property
     def patch_k(self) -> int:
@@ -64,8 +66,12 @@ CLIP_B32 = ViTConfig("clip-vit-b32", patch=32, dim=768, depth=12, heads=12, mlp=
 # dimension 80, MLP 5120, GELU(erf), 1024-d embedding); image tower only
 OPENCLIP_H14 = ViTConfig("openclip-vit-h14", dim=1280, depth=32, heads=16, mlp=5120, act="gelu", ln_pre=True, ln_eps=1e-5,
                          patch_bias=False, embed=1024)
+# its text tower (encode_text: goal text and long-term labels, BSCAgent.py:541-546, 708-711): width 1024, 24 layers, 16 heads,
+# context 77, vocabulary 49 408, causal attention, pooled at the end-of-text token; the BPE tokenizer stays with the caller
+OPENCLIP_H14_TEXT = ViTConfig("openclip-vit-h14-text", dim=1024, depth=24, heads=16, mlp=4096, act="gelu", ln_eps=1e-5,
+                              patch_bias=False, embed=1024, text_context=77, vocab=49408)
 
-CONFIGS = {c.name: c for c in (CLIP_L14, DINOV2_L14_REG, CLIP_B32, OPENCLIP_H14)}
+CONFIGS = {c.name: c for c in (CLIP_L14, DINOV2_L14_REG, CLIP_B32, OPENCLIP_H14, OPENCLIP_H14_TEXT)}
 # torch.hub entry names the reference passes as --dino_size (args.py:50)
 CONFIGS["dinov2_vitl14_reg"] = DINOV2_L14_REG
 
@@ -92,13 +98,16 @@ def random_weights(cfg: ViTConfig, seed: int = 0, perturb: bool = False, std: fl
             return 1.0 + n(D, s=0.1), n(D, s=0.1)
         return torch.ones(D), torch.zeros(D)
 
-    w = {
-        "patch_w": n(D, cfg.patch_k),
-        "patch_b": n(D) if cfg.patch_bias else torch.zeros(D),
-        "cls": n(D),
-        "reg": n(max(cfg.n_reg, 1), D)[: cfg.n_reg] if cfg.n_reg else torch.zeros(0, D),
-        "pos": n(1 + cfg.n_patch, D),
-    }
+    if cfg.text_context:
+        w = {"tok_emb": n(cfg.vocab, D), "pos": n(cfg.text_context, D, s=0.01)}
+    else:
+        w = {
+            "patch_w": n(D, cfg.patch_k),
+            "patch_b": n(D) if cfg.patch_bias else torch.zeros(D),
+            "cls": n(D),
+            "reg": n(max(cfg.n_reg, 1), D)[: cfg.n_reg] if cfg.n_reg else torch.zeros(0, D),
+            "pos": n(1 + cfg.n_patch, D),
+        }
     if cfg.ln_pre:
         w["ln_pre_w"], w["ln_pre_b"] = ln_pair()
     for i in range(cfg.depth):

@@ -196,6 +196,8 @@ typedef struct {
   int32_t patch_k_pad;            /* 3*patch*patch rounded up to a multiple of 64      */
   float   ln_eps;
   int32_t head_dim;               /* 0 or 64: dim == heads*64; 80: ViT-H/14 (mma.sync attention) */
+  int32_t text_context;           /* 0: image tower; > 0: text tower over this many positions (causal attention,
+                                     no patch embedding / cls / registers / pre-LN; image, patch, patch_k_pad unused) */
 } bscnav_vit_cfg_t;
 
 /* Element counts of the two packed weight blobs (layout documented in DESIGN.md / vit.py:pack_weights). */
@@ -230,6 +232,14 @@ int bscnav_vit_forward_images(void* engine, const float* images, int32_t batch, 
 int bscnav_vit_encode_images(void* engine, const float* images, int32_t batch, const float* proj, int32_t embed_dim,
                              float* out_embed, void* stream);
 
+/* Text tower of the same CLIP (open_clip encode_text; goal text in check_around, BSCAgent.py:708-711, and long-term label
+ * matching, :541-546): engine created from a cfg with text_context > 0.  token_ids int32[batch*context] (the caller's
+ * tokenizer; ids outside [0, vocab) are clamped), token_embedding float[vocab*dim] -> + positional embedding -> causal
+ * transformer -> LayerNorm(final) of the row at argmax(token_ids) (end-of-text) -> x proj float[dim*embed_dim]
+ * -> out_embed float[batch*embed_dim]. */
+int bscnav_text_encode(void* engine, const int32_t* token_ids, int32_t batch, const float* token_embedding, int32_t vocab,
+                       const float* proj, int32_t embed_dim, float* out_embed, void* stream);
+
 /* View scoring of check_around (BSCAgent.py:713-718, 726-731): L2-normalise the n view embeddings and the goal embedding,
  * similarities = views . goal, softmax over the n views -> out_prob float[n]; out_best int32[2] = {argmax (lowest index on
  * ties), 0}.  n <= 1024. */
@@ -247,8 +257,10 @@ int bscnav_gemm_f16(const void* a, const void* w, const float* bias, void* out, 
 /* Stand-alone attention entry (tests/bench): qkv fp16 [batch*T, 3*heads*64] (q pre-scaled by 1/sqrt(64)) ->
  * out fp16 [batch*T, heads*64].  impl 0: mma.sync kernel (any T); impl 1: tcgen05 kernel (T <= 272). */
 int bscnav_attention_f16(const void* qkv, void* out, int32_t batch, int32_t T, int32_t heads, int32_t impl, void* stream);
-/* The mma.sync kernel with an explicit head dim (64 | 80): qkv fp16 [batch*T, 3*heads*head_dim], q pre-scaled. */
-int bscnav_attention_f16_hd(const void* qkv, void* out, int32_t batch, int32_t T, int32_t heads, int32_t head_dim, void* stream);
+/* The mma.sync kernel with an explicit head dim (64 | 80) and optional causal mask (keys <= query row; head dim 64):
+ * qkv fp16 [batch*T, 3*heads*head_dim], q pre-scaled. */
+int bscnav_attention_f16_hd(const void* qkv, void* out, int32_t batch, int32_t T, int32_t heads, int32_t head_dim, int32_t causal,
+                            void* stream);
 
 /* Number of kernels launched by this library since load (bench.py's gpu_launches). */
 int64_t bscnav_launch_count(void);

@@ -41,6 +41,40 @@ def patchify(x: torch.Tensor, patch: int) -> torch.Tensor:
     return x.reshape(B, nh * nw, C * patch * patch)
 
 
+def _blocks(h, w, cfg, quant=None, causal=False):
+    """The transformer blocks (pre-norm residual attention + MLP); causal: keys <= query position (CLIP text tower)."""
+    D, Hh = cfg.dim, cfg.heads
+    dh = D // Hh
+    B, T = h.shape[0], h.shape[1]
+    mask = torch.full((T, T), float("-inf")).triu(1) if causal else None
+    for i in range(cfg.depth):
+        p = f"l{i}."
+        y = _ln(h, w[p + "ln1_w"], w[p + "ln1_b"], cfg.ln_eps)
+        qkv = _lin(y, w[p + "qkv_w"], w[p + "qkv_b"], quant).reshape(B, T, 3, Hh, dh).permute(2, 0, 3, 1, 4)
+        q, k, v = qkv[0], qkv[1], qkv[2]
+        if quant is not None:
+            q, k, v = quant(q), quant(k), quant(v)
+        s = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(dh)
+        if mask is not None:
+            s = s + mask
+        a = torch.softmax(s, dim=-1)
+        if quant is not None:
+            a = quant(a)
+        o = torch.matmul(a, v).permute(0, 2, 1, 3).reshape(B, T, D)
+        o = _lin(o, w[p + "proj_w"], w[p + "proj_b"], quant)
+        if cfg.layerscale:
+            o = o * w[p + "ls1"]
+        h = h + o
+        y = _ln(h, w[p + "ln2_w"], w[p + "ln2_b"], cfg.ln_eps)
+        y = _lin(y, w[p + "fc1_w"], w[p + "fc1_b"], quant)
+        y = F.gelu(y) if cfg.act == "gelu" else y * torch.sigmoid(1.702 * y)
+        y = _lin(y, w[p + "fc2_w"], w[p + "fc2_b"], quant)
+        if cfg.layerscale:
+            y = y * w[p + "ls2"]
+        h = h + y
+    return h
+
+
 @torch.no_grad()
 def vit_forward(x: torch.Tensor, w: dict, cfg, quant=None, return_all: bool = False) -> torch.Tensor:
     """fp32 forward.  x (B,3,S,S) normalised image -> patch tokens (B, Np, D).
@@ -61,30 +95,7 @@ def vit_forward(x: torch.Tensor, w: dict, cfg, quant=None, return_all: bool = Fa
     h = torch.cat(parts, dim=1)
     if cfg.ln_pre:
         h = _ln(h, w["ln_pre_w"], w["ln_pre_b"], cfg.ln_eps)
-    T = h.shape[1]
-    for i in range(cfg.depth):
-        p = f"l{i}."
-        y = _ln(h, w[p + "ln1_w"], w[p + "ln1_b"], cfg.ln_eps)
-        qkv = _lin(y, w[p + "qkv_w"], w[p + "qkv_b"], quant).reshape(B, T, 3, Hh, dh).permute(2, 0, 3, 1, 4)
-        q, k, v = qkv[0], qkv[1], qkv[2]
-        if quant is not None:
-            q, k, v = quant(q), quant(k), quant(v)
-        s = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(dh)
-        a = torch.softmax(s, dim=-1)
-        if quant is not None:
-            a = quant(a)
-        o = torch.matmul(a, v).permute(0, 2, 1, 3).reshape(B, T, D)
-        o = _lin(o, w[p + "proj_w"], w[p + "proj_b"], quant)
-        if cfg.layerscale:
-            o = o * w[p + "ls1"]
-        h = h + o
-        y = _ln(h, w[p + "ln2_w"], w[p + "ln2_b"], cfg.ln_eps)
-        y = _lin(y, w[p + "fc1_w"], w[p + "fc1_b"], quant)
-        y = F.gelu(y) if cfg.act == "gelu" else y * torch.sigmoid(1.702 * y)
-        y = _lin(y, w[p + "fc2_w"], w[p + "fc2_b"], quant)
-        if cfg.layerscale:
-            y = y * w[p + "ls2"]
-        h = h + y
+    h = _blocks(h, w, cfg, quant)
     h = _ln(h, w["ln_post_w"], w["ln_post_b"], cfg.ln_eps)
     if return_all:
         return h
@@ -97,6 +108,17 @@ def encode_image(x: torch.Tensor, w: dict, cfg, quant=None) -> torch.Tensor:
     and cross-checked against transformers.CLIPVisionModelWithProjection in tests/test_vit_oracle.py): the post-LayerNorm'd
     cls token times the bias-free projection `proj` (D, E)."""
     return vit_forward(x, w, cfg, quant, return_all=True)[:, 0] @ w["proj"]
+
+
+@torch.no_grad()
+def encode_text(token_ids: torch.Tensor, w: dict, cfg, quant=None) -> torch.Tensor:
+    """open_clip `encode_text` (BSCAgent.py:545-546, 711; third-party, restated and cross-checked against
+    transformers.CLIPTextModelWithProjection): token + positional embedding, causal transformer, final LayerNorm, the row at
+    argmax(token_ids) (end-of-text has the largest id) times the bias-free text projection (D, E)."""
+    ids = token_ids.long()
+    h = w["tok_emb"][ids] + w["pos"]
+    h = _ln(_blocks(h, w, cfg, quant, causal=True), w["ln_post_w"], w["ln_post_b"], cfg.ln_eps)
+    return h[torch.arange(h.shape[0]), ids.argmax(dim=-1)] @ w["proj"]
 
 
 def score_views(image_features: torch.Tensor, goal_features: torch.Tensor):

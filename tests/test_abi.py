@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
-    assert lib.bscnav_abi_version() == 1
+    assert lib.bscnav_abi_version() == 2
 
 
 def test_struct_sizes_match_header():
@@ -26,7 +26,7 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(_lib.Geom) == 12 * 4 + 3 * 8 + 27 * 8
     assert ctypes.sizeof(_lib.Store) == 9 * 8
     assert ctypes.sizeof(_lib.Filter) == 8 + 12 + 8 + 4
-    assert ctypes.sizeof(_lib.VitCfg) == 12 * 4
+    assert ctypes.sizeof(_lib.VitCfg) == 13 * 4
 
 
 def test_weight_blob_layout_matches_engine():

@@ -17,7 +17,7 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 256, 128), (1000, 1024, 1024), (257 * 3, 3072, 1024), (515, 4096, 1024),
-                                   (200, 1024, 4096), (4112, 2304, 768), (514, 3840, 1280), (300, 1280, 5120)])
+                                   (200, 1024, 4096), (4112, 2304, 768), (514, 3840, 1280), (300, 1280, 5120), (77, 3072, 1024), (50, 1024, 4096)])
 def test_gemm_modes(pkg, M, N, K):
     g = torch.Generator("cuda").manual_seed(M + N + K)
     a = (torch.randn(M, K, device="cuda", generator=g)).half()
@@ -171,3 +171,58 @@ def test_score_views_matches_torch(pkg, n, E):
     ref_prob, ref_best = vit_ref.score_views(emb, goal)
     assert int(best) == int(ref_best) == n // 2
     torch.testing.assert_close(prob.cpu(), ref_prob, rtol=1e-5, atol=1e-7)
+
+
+# ---- the same CLIP's text tower (encode_text: goal text, long-term labels; BSCAgent.py:541-557, 708-711)
+@pytest.mark.parametrize("T,heads,batch", [(77, 16, 3), (20, 2, 2), (130, 3, 2), (64, 1, 1), (257, 2, 1)])
+def test_attention_causal(pkg, T, heads, batch):
+    g = torch.Generator("cuda").manual_seed(T * 3 + heads)
+    D = heads * 64
+    qkv = (torch.randn(batch * T, 3 * D, device="cuda", generator=g) * 0.8).half()
+    out = pkg.attention_f16(qkv, batch, T, heads, impl=0, causal=True).float().view(batch, T, heads, 64)
+    q, k, v = qkv.float().view(batch, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    mask = torch.full((T, T), float("-inf"), device="cuda").triu(1)
+    ref = (torch.softmax(q @ k.transpose(-1, -2) + mask, dim=-1) @ v).permute(0, 2, 1, 3)
+    torch.testing.assert_close(out, ref, rtol=2e-3, atol=2e-3)
+
+
+def _token_rows(cfg, lengths, seed):
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.zeros(len(lengths), cfg.text_context, dtype=torch.long)
+    for r, n in enumerate(lengths):
+        n = min(n, cfg.text_context - 2)
+        ids[r, 0] = cfg.vocab - 2
+        ids[r, 1:1 + n] = torch.randint(1, cfg.vocab - 2, (n,), generator=g)
+        ids[r, 1 + n] = cfg.vocab - 1
+    return ids
+
+
+def test_tiny_text_tower_matches_oracle(pkg):
+    import dataclasses
+    cfg = dataclasses.replace(pkg.tiny(pkg.OPENCLIP_H14_TEXT, dim=128, depth=2, heads=2, mlp=256), embed=64, vocab=1000)
+    w = pkg.random_weights(cfg, seed=9, perturb=True)
+    eng = pkg.ViTEngine(cfg, w, max_batch=2)
+    ids = _token_rows(cfg, [3, 75, 1, 40, 12], seed=1)          # more rows than max_batch: chunked
+    got = eng.encode_text(ids.cuda()).cpu()
+    ref = vit_ref.encode_text(ids, w, cfg)
+    assert got.shape == ref.shape == (5, 64)
+    assert _rel(got, ref) < 1e-3
+    with pytest.raises(Exception):
+        eng.forward_features(torch.zeros(1, 3, 224, 224))      # a text engine has no image path
+
+
+def test_full_text_tower_and_label_matching(pkg):
+    cfg = pkg.OPENCLIP_H14_TEXT
+    w = pkg.random_weights(cfg, seed=0)
+    eng = pkg.ViTEngine(cfg, w, max_batch=8)
+    ids = _token_rows(cfg, [4, 9, 2, 30, 6, 4], seed=2)
+    ids[5] = ids[0]                                             # the prompt repeats label 0
+    got = eng.encode_text(ids.cuda())
+    ref = vit_ref.encode_text(ids, w, cfg)
+    rel = _rel(got.cpu(), ref)
+    print("CLIP text tower (24 x 1024, context 77), max relative L2 error", rel)
+    assert got.shape == (6, 1024) and rel < 1e-3
+    # BSCAgent.py:548-557: the prompt against the stored labels
+    assert pkg.match_long_memory_label(got[5], got[:5]) == 0
+    a, b = torch.nn.functional.normalize(ref[5:6], dim=-1), torch.nn.functional.normalize(ref[:5], dim=-1)
+    assert int(torch.argmax((a @ b.T).squeeze(0))) == 0

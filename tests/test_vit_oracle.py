@@ -100,6 +100,52 @@ def test_clip_image_embedding_head_dim_80_matches_transformers():
     assert int(best) == 1 and abs(float(prob.sum()) - 1.0) < 1e-6
 
 
+def test_clip_text_tower_matches_transformers():
+    """encode_text of the agent's CLIP (BSCAgent.py:545-546, 711): causal transformer, end-of-text pooling (argmax of the ids),
+    bias-free projection -- against transformers.CLIPTextModelWithProjection at test size."""
+    from transformers import CLIPTextConfig, CLIPTextModelWithProjection
+    cfg = vc.replace(vc.tiny(vc.OPENCLIP_H14_TEXT, dim=64, depth=2, heads=1, mlp=128), embed=40, text_context=20, vocab=300)
+    w = vc.random_weights(cfg, seed=7, perturb=True)
+    # eos_token_id=2 selects transformers' argmax pooling (what open_clip does: text.argmax(dim=-1))
+    hf = CLIPTextModelWithProjection(CLIPTextConfig(
+        vocab_size=cfg.vocab, hidden_size=cfg.dim, intermediate_size=cfg.mlp, projection_dim=cfg.embed, num_hidden_layers=cfg.depth,
+        num_attention_heads=cfg.heads, max_position_embeddings=cfg.text_context, hidden_act="gelu", layer_norm_eps=cfg.ln_eps,
+        eos_token_id=2, bos_token_id=0, pad_token_id=1)).eval()
+    tm = hf.text_model
+    with torch.no_grad():
+        tm.embeddings.token_embedding.weight.copy_(w["tok_emb"])
+        tm.embeddings.position_embedding.weight.copy_(w["pos"])
+        tm.final_layer_norm.weight.copy_(w["ln_post_w"]); tm.final_layer_norm.bias.copy_(w["ln_post_b"])
+        hf.text_projection.weight.copy_(w["proj"].T)
+
+    def get(i):
+        L = tm.encoder.layers[i]
+        a = L.self_attn
+        return {"ln1_w": L.layer_norm1.weight, "ln1_b": L.layer_norm1.bias, "ln2_w": L.layer_norm2.weight, "ln2_b": L.layer_norm2.bias,
+                "q_w": a.q_proj.weight, "q_b": a.q_proj.bias, "k_w": a.k_proj.weight, "k_b": a.k_proj.bias, "v_w": a.v_proj.weight,
+                "v_b": a.v_proj.bias, "proj_w": a.out_proj.weight, "proj_b": a.out_proj.bias, "fc1_w": L.mlp.fc1.weight,
+                "fc1_b": L.mlp.fc1.bias, "fc2_w": L.mlp.fc2.weight, "fc2_b": L.mlp.fc2.bias}
+    _copy_layers(cfg, w, get)
+    ids = _token_rows(cfg, [5, 11, 19, 1], seed=3)
+    with torch.no_grad():
+        ref = hf(input_ids=ids).text_embeds
+    got = vit_ref.encode_text(ids, w, cfg)
+    torch.testing.assert_close(got, ref, rtol=2e-4, atol=2e-4)
+
+
+def _token_rows(cfg, lengths, seed):
+    """Token rows the way open_clip.tokenize lays them out: <start> words... <end> then zero padding; <end> = vocab - 1 is the
+    largest id, so argmax finds it."""
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.zeros(len(lengths), cfg.text_context, dtype=torch.long)
+    for r, n in enumerate(lengths):
+        n = min(n, cfg.text_context - 2)
+        ids[r, 0] = cfg.vocab - 2
+        ids[r, 1:1 + n] = torch.randint(1, cfg.vocab - 2, (n,), generator=g)
+        ids[r, 1 + n] = cfg.vocab - 1
+    return ids
+
+
 def test_dinov2_reg_oracle_matches_transformers():
     try:
         from transformers import Dinov2WithRegistersConfig, Dinov2WithRegistersModel

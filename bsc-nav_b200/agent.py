@@ -121,8 +121,16 @@ class ViewChecker:
 
     def best_view(self, views, prompt):
         """-> (index of the matching view, soft-max probabilities (N,) on the device)."""
+        import torch
         from .vit import score_views
-        prob, best = score_views(self.clip.encode_image(views), self.goal_features(prompt))
+        if isinstance(prompt, str):
+            feats, goal = self.clip.encode_image(views), self.goal_features(prompt)
+        else:
+            # an image goal rides in the views' batch: one pass of the tower instead of two (a lone image is launch-bound)
+            goal_img = prompt.reshape(1, *prompt.shape[-3:]).to(views.device, views.dtype)
+            both = self.clip.encode_image(torch.cat([views, goal_img], dim=0))
+            feats, goal = both[:-1], both[-1]
+        prob, best = score_views(feats, goal)
         return int(best), prob
 
     def turn_actions(self, max_idx: int):

@@ -6,6 +6,9 @@ The path shards two ways:
     own store, then ONE all-gather of the compacted per-rank deltas {cell, key, h, token row} and every rank applies
     the same winner rule (bscnav_merge_delta).  The rule is a min over (float32 r^2, ordinal) -- commutative and
     associative -- so the merged store does not depend on the number of ranks or on arrival order.
+  * queries over a grid whose cells are spread over ranks (tile-sharded scene, or un-merged frame shards with C large
+    enough): local top-K per rank, ONE all-gather of K x (similarity, position) per query, K-way merge on every rank
+    (`query_sharded`, `merge_topk`) -- 1.6 KB per query and rank at K = 100.
 The reference has none of this (CUDA_VISIBLE_DEVICES='0', create_memory_for_dataset.py:38).
 """
 from __future__ import annotations
@@ -76,3 +79,50 @@ def merge_rule_host(cells: np.ndarray, keys: np.ndarray, cache: int) -> dict:
         if c >= 0:
             out.setdefault(c, []).append(k)
     return {c: sorted(v)[:cache] for c, v in out.items()}
+
+
+def merge_topk(sims: torch.Tensor, pos: torch.Tensor, counts: torch.Tensor, k: int):
+    """K-way merge of per-rank query results for ONE query batch: sims (R, Q, K) f32, pos (R, Q, K, 3) i32, counts (R, Q) i32
+    -> (sims (Q, k), pos (Q, k, 3), counts (Q,)) with the layout of SpatialStore.query (entries past the count: -inf / -1).
+    A cell reported by several ranks keeps its largest similarity (the reference's per-voxel max, memory_2.py:655-662);
+    order: similarity descending, ties by (row, col, h) ascending -- independent of the rank count and order."""
+    R, Q, K = sims.shape
+    dev = sims.device
+    s = sims.permute(1, 0, 2).reshape(Q, R * K)
+    p = pos.permute(1, 0, 2, 3).reshape(Q, R * K, 3).long()
+    valid = (torch.arange(K, device=dev)[None, None, :] < counts.permute(1, 0)[:, :, None].long()).reshape(Q, R * K)
+    cell = (p[..., 0] << 42) | (p[..., 1] << 21) | p[..., 2]               # grid coordinates are < 2^21
+    cell = torch.where(valid, cell, torch.full_like(cell, torch.iinfo(torch.int64).max))
+    s = torch.where(valid, s, torch.full_like(s, float("-inf")))
+    # order by (similarity desc, cell asc): stable sort by the minor key first
+    o1 = torch.argsort(cell, dim=1, stable=True)
+    s, cell, p, valid = s.gather(1, o1), cell.gather(1, o1), p.gather(1, o1[..., None].expand(-1, -1, 3)), valid.gather(1, o1)
+    o2 = torch.argsort(s, dim=1, descending=True, stable=True)
+    s, cell, p, valid = s.gather(1, o2), cell.gather(1, o2), p.gather(1, o2[..., None].expand(-1, -1, 3)), valid.gather(1, o2)
+    # a cell's first occurrence in this order carries its maximum: drop the later ones
+    n = R * K
+    dup = (cell[:, :, None] == cell[:, None, :]) & torch.ones(n, n, dtype=torch.bool, device=dev).tril(-1)[None]
+    keep = valid & ~dup.any(dim=2)
+    rank = torch.cumsum(keep, dim=1) - 1
+    out_s = torch.full((Q, k), float("-inf"), dtype=sims.dtype, device=dev)
+    out_p = torch.full((Q, k, 3), -1, dtype=pos.dtype, device=dev)
+    take = keep & (rank < k)
+    qi = torch.arange(Q, device=dev)[:, None].expand(-1, n)[take]
+    out_s[qi, rank[take]] = s[take]
+    out_p[qi, rank[take]] = p[take].to(pos.dtype)
+    return out_s, out_p, torch.clamp(keep.sum(dim=1), max=k).to(counts.dtype)
+
+
+def query_sharded(store, q: torch.Tensor, k: int = 100, group=None, batch: bool = False, **filters):
+    """Query a scene whose cells are spread over the ranks of `group`: every rank scores its own store (exact path, or the
+    batch path with batch=True), the K best of each rank are all-gathered and merged.  Every rank returns the same
+    (sims (Q, k), positions (Q, k, 3), counts (Q,)) as a single store holding all the cells would."""
+    sims, pos, cnt = (store.query_batch if batch else store.query)(q, k=k, **filters)
+    world = dist.get_world_size(group)
+    outs = []
+    for t in (sims, pos, cnt):                       # concatenated along dim 0 (the layout every backend accepts), then (R, ...)
+        buf = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(buf, t.contiguous(), group=group)
+        outs.append(buf.reshape((world,) + tuple(t.shape)))
+    g_s, g_p, g_c = outs
+    return merge_topk(g_s, g_p, g_c, k)

@@ -36,6 +36,40 @@ def main():
     counts = dmod.merge_scene_across_ranks(st, int(ob[mine[0]]), int(ob[mine[-1]]) + H * W, st.g.max_slots * 3)   # capacity of the export buffers, rows
     canon = lambda s: {k: [(float(t[0]), int(t[1]), int(t[2]), t[3].tobytes()) for t in v] for k, v in s.snapshot().items()}
     assert canon(st) == canon(joint), f"rank {rank}: merged store differs from the joint build"
+    # queries over a scene whose grid rows are spread over the ranks: local top-K + one all-gather + K-way merge
+    # equals the query over one store holding every cell
+    qcfg = pkg.StoreConfig(height=H, width=W, grid_size=GS, floor_height=-2.0, map_height=2.0, token_dim=D, cache_size=2, bev=False,
+                           max_slots=4096)
+    gen = torch.Generator("cuda").manual_seed(3)                      # same stream of numbers on every rank
+    whole, part = pkg.SpatialStore(qcfg), pkg.SpatialStore(qcfg)
+    levels, n_cells, C = whole.g.levels, 2500, 2
+    cells = torch.randperm(GS * GS * levels, device="cuda", generator=gen)[:n_cells].to(torch.int32)
+    base = torch.randn(150, D, device="cuda", generator=gen)
+    feat = base[torch.randint(0, 150, (n_cells * C,), device="cuda", generator=gen)]           # repeated rows: ties
+    tok_h = torch.randint(0, 30, (n_cells * C,), device="cuda", generator=gen).to(torch.int32)
+
+    def install(s, sel):
+        rows = (sel[:, None] * C + torch.arange(C, device="cuda")[None]).flatten()
+        m = len(sel)
+        s.reset()
+        s.feat[:m * C] = feat[rows]
+        s.slot_cell[:m] = cells[sel]
+        s.occupied_ids[cells[sel].long()] = torch.arange(m, dtype=torch.int32, device="cuda")
+        s.row_key[:m * C] = 0
+        s.slot_keys[:m * C] = 0
+        s.tok_h[:m * C] = tok_h[rows]
+        s.row_norms(m * C)
+        s.counters[0] = m
+
+    install(whole, torch.arange(n_cells, device="cuda"))
+    grid_row = (cells.long() // levels) // GS
+    install(part, (grid_row % world == rank).nonzero().flatten())
+    q = torch.cat([base[:3] + 0.05 * torch.randn(3, D, device="cuda", generator=gen), torch.randn(2, D, device="cuda", generator=gen)])
+    for use_batch in (False, True):
+        got = dmod.query_sharded(part, q, k=50, batch=use_batch)
+        want = whole.query(q, k=50)
+        for a, b, name in zip(got, want, ("sims", "positions", "counts")):
+            assert torch.equal(a, b), f"rank {rank}: sharded query {name} differ from the whole store (batch={use_batch})"
     dist.barrier()
     if rank == 0:
         print("MERGE_OK", counts)

@@ -74,3 +74,50 @@ def test_shard_plans():
         assert max(len(s) for s in shards) - min(len(s) for s in shards) <= 1
     assert d.shard_scenes(90, 3, 8) == list(range(3, 90, 8))
     assert sorted(i for r in range(4) for i in d.shard_scenes(10, r, 4)) == list(range(10))
+
+
+class _FakeStore:
+    """Stands in for SpatialStore.query in the CPU test: returns this rank's pre-computed local top-K."""
+
+    def __init__(self, sims, pos, cnt):
+        self.res = (sims, pos, cnt)
+
+    def query(self, q, k=100, **_):
+        return self.res
+
+
+def _local_topk(rank, Q, K):
+    g = torch.Generator().manual_seed(50 + rank)
+    n = K if rank == 0 else K - 3                                # the second rank has fewer than K candidates
+    sims = torch.full((Q, K), float("-inf"))
+    pos = torch.full((Q, K, 3), -1, dtype=torch.int32)
+    for qi in range(Q):
+        s = torch.sort(torch.randn(n, generator=g), descending=True)[0]
+        sims[qi, :n] = s
+        pos[qi, :n] = torch.stack([torch.randperm(40, generator=g)[:n] * 2 + rank, torch.randint(0, 40, (n,), generator=g),
+                                   torch.randint(0, 20, (n,), generator=g)], dim=1).to(torch.int32)   # rows of rank r: parity r
+    return sims, pos, torch.full((Q,), n, dtype=torch.int32)
+
+
+def _query_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = importlib.import_module("bsc-nav_b200.dist")
+    s, p, c = d.query_sharded(_FakeStore(*_local_topk(rank, 3, 10)), torch.zeros(3, 8), k=10)
+    np.savez(os.path.join(out_dir, f"q{rank}.npz"), s=s.numpy(), p=p.numpy(), c=c.numpy())
+    dist.destroy_process_group()
+
+
+def test_query_sharded_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_query_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "q0.npz"), np.load(tmp_path / "q1.npz")
+    for k in ("s", "p", "c"):
+        assert np.array_equal(r0[k], r1[k])                       # every rank ends with the same merged top-K
+    (s0, p0, _), (s1, p1, _) = _local_topk(0, 3, 10), _local_topk(1, 3, 10)
+    for qi in range(3):
+        allv = [(float(s0[qi, j]), tuple(p0[qi, j].tolist())) for j in range(10)] + [(float(s1[qi, j]), tuple(p1[qi, j].tolist())) for j in range(7)]
+        exp = sorted(allv, key=lambda t: (-t[0], t[1]))[:10]
+        assert r0["c"][qi] == 10
+        assert [tuple(v) for v in r0["p"][qi].tolist()] == [e[1] for e in exp]
+        assert np.array_equal(r0["s"][qi], np.array([e[0] for e in exp], dtype=np.float32))

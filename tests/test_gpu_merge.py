@@ -90,6 +90,57 @@ def test_query_after_merge_matches_joint(pkg):
     assert torch.equal(c1, c2) and torch.equal(p1, p2) and torch.equal(s1, s2)
 
 
+def _install_cells(st, cells, feat, tok_h):
+    """Fill a store by hand: slot i holds cell cells[i] with the C token rows feat[i*C:(i+1)*C]."""
+    n, C = len(cells), st.g.cache
+    st.reset()
+    st.feat[:n * C] = feat
+    st.slot_cell[:n] = cells
+    st.occupied_ids[cells.long()] = torch.arange(n, dtype=torch.int32, device="cuda")
+    st.row_key[:n * C] = 0
+    st.slot_keys[:n * C] = 0
+    st.tok_h[:n * C] = tok_h
+    st.row_norms(n * C)
+    st.counters[0] = n
+    st.invalidate_shadow()
+
+
+@pytest.mark.parametrize("C,bev", [(1, True), (2, False)])
+@pytest.mark.parametrize("shards", [2, 3])
+def test_tile_sharded_query_merge_equals_joint(pkg, C, bev, shards):
+    """SURVEY 8(e), queries: row tiles of the grid on different ranks, local top-K, K-way merge (dist.merge_topk) == the query over
+    one store holding every cell, bit for bit -- with duplicated rows (ties) and fewer than K candidates on some shards."""
+    dmod = importlib.import_module("bsc-nav_b200.dist")
+    gs, Dq, n = 96, 128, 3000
+    cfg = pkg.StoreConfig(height=H, width=W, grid_size=gs, floor_height=-1.0, map_height=1.0, token_dim=Dq, cache_size=C, bev=bev,
+                          max_slots=4096)
+    gen = torch.Generator("cuda").manual_seed(10 * C + shards)
+    joint = pkg.SpatialStore(cfg)
+    levels = joint.g.levels
+    cells = torch.randperm(gs * gs * levels, device="cuda", generator=gen)[:n].to(torch.int32)
+    base = torch.randn(200, Dq, device="cuda", generator=gen)
+    feat = base[torch.randint(0, 200, (n * C,), device="cuda", generator=gen)]                  # many identical rows: ties
+    tok_h = torch.randint(0, max(joint.g.maxh - joint.g.minh, 1), (n * C,), device="cuda", generator=gen).to(torch.int32)
+    _install_cells(joint, cells, feat, tok_h)
+    q = torch.cat([base[:3] + 0.05 * torch.randn(3, Dq, device="cuda", generator=gen), torch.randn(2, Dq, device="cuda", generator=gen)])
+    row = (cells.long() // levels) // gs
+    # uneven tiles: the last shard holds only the top 4 rows of the grid (fewer than K cells)
+    owner = torch.where(row >= gs - 4, shards - 1, row % max(shards - 1, 1))
+    for k in (100, 7):
+        parts = []
+        for r in range(shards):
+            sel = (owner == r).nonzero().flatten()
+            rows = (sel[:, None] * C + torch.arange(C, device="cuda")[None]).flatten()
+            st = pkg.SpatialStore(cfg)
+            _install_cells(st, cells[sel].contiguous(), feat[rows], tok_h[rows])
+            parts.append(st.query(q, k=k) if r % 2 == 0 else st.query_batch(q, k=k))
+        got = dmod.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]),
+                              torch.stack([p[2] for p in parts]), k)
+        want = joint.query(q, k=k)
+        for a, b, name in zip(got, want, ("sims", "positions", "counts")):
+            assert torch.equal(a, b), f"k={k} {name} differ"
+
+
 def test_two_rank_nccl_merge():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")

@@ -6,8 +6,7 @@ The path shards two ways:
     own store, then ONE all-gather of the compacted per-rank deltas {cell, key, h, token row} and every rank applies
     the same winner rule (bscnav_merge_delta).  The rule is a min over (float32 r^2, ordinal) -- commutative and
     associative -- so the merged store does not depend on the number of ranks or on arrival order.
-  * queries over a grid whose cells are spread over ranks (tile-sharded scene, or un-merged frame shards with C large
-    enough): local top-K per rank, ONE all-gather of K x (similarity, position) per query, K-way merge on every rank
+  * queries over a grid whose cells are spread over ranks (tile-sharded scene): local top-K per rank, ONE all-gather of K x (similarity, position) per query, K-way merge on every rank
     (`query_sharded`, `merge_topk`) -- 1.6 KB per query and rank at K = 100.
 The reference has none of this (CUDA_VISIBLE_DEVICES='0', create_memory_for_dataset.py:38).
 """

@@ -86,3 +86,41 @@ def test_product_path_has_no_cpu_fallback(env, monkeypatch):
     monkeypatch.setattr(L, "LIB_PATH", "/nonexistent/libbscnav_b200.so")
     with pytest.raises(L.BscnavError):
         L.lib()
+
+
+def test_clip_tower_entry_points_validate(env):
+    """The agent-side CLIP entries (view check / label matching): nulls, sizes, and the ViT config rules (head dim 64 | 80,
+    text tower: head dim 64, no registers / pre-LN)."""
+    pkg, L, lib, _store = env
+    vit = importlib.import_module("bsc-nav_b200.vit")
+    buf = (C.c_char * 64)()
+    p = C.cast(buf, C.c_void_p)
+    assert lib.bscnav_vit_encode_images(None, p, 1, p, 1024, p, None) == EINVAL
+    assert lib.bscnav_text_encode(None, p, 1, p, 49408, p, 1024, p, None) == EINVAL
+    assert lib.bscnav_score_views(None, p, 12, 1024, p, p, None) == EINVAL
+    assert lib.bscnav_score_views(p, p, 0, 1024, p, p, None) == EINVAL
+    assert lib.bscnav_score_views(p, p, 1025, 1024, p, p, None) == EINVAL           # more views than one block scores
+    assert lib.bscnav_attention_f16_hd(None, None, 1, 77, 16, 64, 1, None) == EINVAL
+    # layouts: image tower with heads of 80, text tower; sizes follow the documented blob layout
+    for cfg in (pkg.OPENCLIP_H14, pkg.OPENCLIP_H14_TEXT, pkg.CLIP_L14):
+        c = vit._cfg_struct(cfg)
+        D, M, L_ = cfg.dim, cfg.mlp, cfg.depth
+        per_layer_half = 3 * D * D + D * D + 2 * M * D
+        per_layer_float = 2 * D + 3 * D + D + 2 * D + M + D
+        if cfg.text_context:
+            half, flt = L_ * per_layer_half, cfg.text_context * D + L_ * per_layer_float + 2 * D
+        else:
+            half = D * c.patch_k_pad + L_ * per_layer_half
+            flt = D + D + cfg.n_patch * D + (2 * D if cfg.ln_pre else 0) + L_ * per_layer_float + 2 * D
+        assert lib.bscnav_vit_half_elems(C.byref(c)) == half
+        assert lib.bscnav_vit_float_elems(C.byref(c)) == flt
+        assert lib.bscnav_vit_workspace_bytes(C.byref(c), 4) > 0
+    bad = vit._cfg_struct(pkg.OPENCLIP_H14)
+    bad.head_dim = 96                                                               # dim != heads * head_dim, and unsupported
+    assert lib.bscnav_vit_half_elems(C.byref(bad)) == EINVAL
+    bad = vit._cfg_struct(pkg.OPENCLIP_H14_TEXT)
+    bad.ln_pre = 1                                                                  # the text tower has no pre-LN
+    assert lib.bscnav_vit_float_elems(C.byref(bad)) == EINVAL
+    bad = vit._cfg_struct(pkg.OPENCLIP_H14_TEXT)
+    bad.text_context = -3
+    assert lib.bscnav_vit_workspace_bytes(C.byref(bad), 4) == EINVAL

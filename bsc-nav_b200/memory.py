@@ -379,6 +379,50 @@ class VoxelTokenMemory:
             return [o for o in self.long_memory_dict if self.floor_min_height <= o["loc"][2] <= self.floor_max_height]
         return self.long_memory_dict
 
+    # ------------------------------------------------------------------ small helpers of the reference class
+    def get_total_token_count(self) -> int:
+        """memory_2.py:312-323 (sum of the HDF5 groups' feature rows): stored token rows, counted on the device."""
+        self._join()
+        st = self._store
+        n = st.count() * st.g.cache
+        total = int((st.row_key[:n] != -1).sum().item()) if n else 0
+        print("total_tokens:", total)
+        return total
+
+    def read_memory(self):
+        """memory_2.py:539-540: a stub in the reference as well."""
+
+    def _reinit_cache(self):
+        """memory_2.py:724-729 re-zeroes the 50 000-token host staging buffers after a flush; tokens go straight into the
+        device store here, so there is nothing to re-initialise."""
+
+    def _out_of_range(self, row, col, height):
+        """memory_2.py:755-756."""
+        return col >= self.gs or row >= self.gs or height >= self.maxh or col < 0 or row < 0 or height < self.minh
+
+    def grid2loc_2d(self, x, y):
+        """memory_2.py:1148-1158: BEV cell (row, col) -> world (x, z, y) at the initial height."""
+        initial_x, initial_z, initial_y = self.Env.original_state.position
+        return np.array([initial_x + (y - self.gs // 2) * self.cs, initial_z, initial_y + (x - self.gs // 2) * self.cs])
+
+    def loc2grid_2d(self, x_base, y_base):
+        """memory_2.py:1160-1163."""
+        return int(self.gs / 2 - int(x_base / self.cs)), int(self.gs / 2 - int(y_base / self.cs))
+
+    def is_unknown(self, x: int, y: int) -> bool:
+        """memory_2.py:1165-1166 (needs colour=True: the BEV colour map is the occupancy evidence)."""
+        return bool(self.cv_map[x, y].sum() == 0)
+
+    def is_known(self, x: int, y: int) -> bool:
+        return not self.is_unknown(x, y)
+
+    def in_bounds(self, x: int, y: int) -> bool:
+        return 0 <= x < self.gs and 0 <= y < self.gs
+
+    def is_navigabale(self, x: int, y: int) -> bool:
+        """memory_2.py:1171-1172 (spelling kept): delegated to the injected simulator's path finder."""
+        return self.Env.plnner.pathfinder.is_navigable(self.grid2loc_2d(x, y))
+
     # ------------------------------------------------------------------ exploration drivers (simulator injected)
     def excute(self, obs, actions):
         """memory_2.py:1086-1101 without the cv2 preview."""

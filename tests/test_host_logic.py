@@ -69,3 +69,20 @@ def test_detect_floor_ranges():
     assert mem.num_floors == 2 and abs(mem.floor_heights[0] - 0.012) < 1e-9 and abs(mem.floor_heights[1] - 3.012) < 1e-9
     lo = 95 + (mem.floor_heights[1] - mem.floor_heights[0]) / 0.1
     assert (mem.floor_min_height, mem.floor_max_height) == (int(lo) + 1, 159 - 1)
+
+
+def test_facade_grid_helpers():
+    """grid2loc_2d / loc2grid_2d / _out_of_range / in_bounds of the memory class (memory_2.py:755-756, 1148-1170): plain
+    arithmetic on the ctor state, exercised without a device through a stand-in `self`."""
+    import types
+    M = importlib.import_module("bsc-nav_b200.memory").VoxelTokenMemory
+    env = types.SimpleNamespace(original_state=types.SimpleNamespace(position=np.array([1.5, 0.25, -2.0])))
+    me = types.SimpleNamespace(gs=1000, cs=0.05, minh=-40, maxh=60, Env=env)
+    loc = M.grid2loc_2d(me, 520, 480)                                     # (row, col)
+    assert np.allclose(loc, [1.5 + (480 - 500) * 0.05, 0.25, -2.0 + (520 - 500) * 0.05])
+    assert M.loc2grid_2d(me, 1.0, -2.0) == (480, 540)                     # gs/2 - int(x/cs), gs/2 - int(y/cs)
+    assert M.loc2grid_2d(me, 0.049, -0.049) == (500, 500)                 # int() truncates towards zero on both sides
+    assert not M._out_of_range(me, 0, 999, -40) and not M._out_of_range(me, 999, 0, 59)
+    for bad in ((1000, 0, 0), (0, 1000, 0), (-1, 0, 0), (0, -1, 0), (0, 0, 60), (0, 0, -41)):
+        assert M._out_of_range(me, *bad)
+    assert M.in_bounds(me, 0, 999) and not M.in_bounds(me, 1000, 0) and not M.in_bounds(me, 0, -1)

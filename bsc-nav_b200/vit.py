@@ -123,34 +123,68 @@ class ViTEngine:
                        "vit_forward_images")
         return {"x_norm_patchtokens": out}
 
+    # -- CUDA graphs for the launch-bound small calls (one goal image, one prompt: ~170-230 kernels of a few microseconds):
+    #    the forward for a given (entry, batch) is captured once on static buffers and replayed
+    def _graphed(self, key, run, x: torch.Tensor, out_shape) -> torch.Tensor:
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        if key not in self._graphs:
+            s_in = torch.empty_like(x)
+            s_out = torch.empty(out_shape, dtype=torch.float32, device=self.device)
+            s_in.copy_(x)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                 # warm-up off the capture: one-time attribute calls, a0 clearing
+                for _ in range(2):
+                    run(s_in, s_out)
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                run(s_in, s_out)
+            self._graphs[key] = (g, s_in, s_out)
+        g, s_in, s_out = self._graphs[key]
+        s_in.copy_(x)
+        g.replay()
+        return s_out.clone()
+
     # -- open_clip `encode_image` (BSCAgent.py:710, 721-724): normalised float images -> (B, embed) image embeddings
     @torch.no_grad()
-    def encode_image(self, x: torch.Tensor) -> torch.Tensor:
+    def encode_image(self, x: torch.Tensor, graph: bool = False) -> torch.Tensor:
         if self.proj is None:
             raise _lib.BscnavError("this ViT has no image-embedding head (weights['proj'])")
         x = x.to(self.device, torch.float32).contiguous()
         B, E = x.shape[0], self.proj.shape[1]
         assert x.shape[1:] == (3, self.cfg.image, self.cfg.image) and self.proj.shape[0] == self.cfg.dim, x.shape
+
+        def run(src, dst, nb=None):
+            nb = src.shape[0] if nb is None else nb
+            _lib.check(self.lib.bscnav_vit_encode_images(self._h, _lib.ptr(src), nb, _lib.ptr(self.proj), E, _lib.ptr(dst),
+                                                         _lib.stream_ptr()), "vit_encode_images")
+        if graph and B <= self.max_batch:
+            return self._graphed(("image", B), run, x, (B, E))
         out = torch.empty(B, E, dtype=torch.float32, device=self.device)
         for b0 in range(0, B, self.max_batch):
-            nb = min(self.max_batch, B - b0)
-            _lib.check(self.lib.bscnav_vit_encode_images(self._h, _lib.ptr(x[b0:]), nb, _lib.ptr(self.proj), E, _lib.ptr(out[b0:]),
-                                                         _lib.stream_ptr()), "vit_encode_images")
+            run(x[b0:], out[b0:], min(self.max_batch, B - b0))
         return out
 
     # -- open_clip `encode_text` (BSCAgent.py:545-546, 711): token ids (B, context) from the caller's tokenizer -> (B, embed)
     @torch.no_grad()
-    def encode_text(self, token_ids: torch.Tensor) -> torch.Tensor:
+    def encode_text(self, token_ids: torch.Tensor, graph: bool = False) -> torch.Tensor:
         if not self.cfg.text_context or self.proj is None:
             raise _lib.BscnavError("not a text tower (cfg.text_context, weights['tok_emb'], weights['proj'])")
         ids = token_ids.to(self.device, torch.int32).contiguous()
         assert ids.dim() == 2 and ids.shape[1] == self.cfg.text_context, ids.shape
         B, E = ids.shape[0], self.proj.shape[1]
+
+        def run(src, dst, nb=None):
+            nb = src.shape[0] if nb is None else nb
+            _lib.check(self.lib.bscnav_text_encode(self._h, _lib.ptr(src), nb, _lib.ptr(self.tok_emb), self.tok_emb.shape[0],
+                                                   _lib.ptr(self.proj), E, _lib.ptr(dst), _lib.stream_ptr()), "text_encode")
+        if graph and B <= self.max_batch:
+            return self._graphed(("text", B), run, ids, (B, E))
         out = torch.empty(B, E, dtype=torch.float32, device=self.device)
         for b0 in range(0, B, self.max_batch):
-            nb = min(self.max_batch, B - b0)
-            _lib.check(self.lib.bscnav_text_encode(self._h, _lib.ptr(ids[b0:]), nb, _lib.ptr(self.tok_emb), self.tok_emb.shape[0],
-                                                   _lib.ptr(self.proj), E, _lib.ptr(out[b0:]), _lib.stream_ptr()), "text_encode")
+            run(ids[b0:], out[b0:], min(self.max_batch, B - b0))
         return out
 
     def profile(self, enable: bool):

@@ -49,6 +49,8 @@ def test_config1_build_matches_reference(cfg1, golden):
             ref = tok[srow]
             worst = max(worst, float(np.linalg.norm(feat - ref) / np.linalg.norm(ref)))
     assert worst < 1e-3, worst
+    assert mem.get_total_token_count() == sum(len(v) for v in snap.values())      # memory_2.py:312-323
+    assert mem.in_bounds(0, 63) and not mem.in_bounds(64, 0) and mem._out_of_range(0, 0, 20)
 
 
 def test_config1_image_query_matches_reference(cfg1, golden):

@@ -226,3 +226,19 @@ def test_full_text_tower_and_label_matching(pkg):
     assert pkg.match_long_memory_label(got[5], got[:5]) == 0
     a, b = torch.nn.functional.normalize(ref[5:6], dim=-1), torch.nn.functional.normalize(ref[:5], dim=-1)
     assert int(torch.argmax((a @ b.T).squeeze(0))) == 0
+
+
+def test_graph_replay_equals_eager(pkg):
+    """The captured forward (CUDA graph on static buffers) of the small CLIP calls returns exactly what the eager launches do,
+    for new inputs on every replay."""
+    import dataclasses
+    tcfg = dataclasses.replace(pkg.tiny(pkg.OPENCLIP_H14_TEXT, dim=128, depth=2, heads=2, mlp=256), embed=64, vocab=1000)
+    txt = pkg.ViTEngine(tcfg, pkg.random_weights(tcfg, seed=9, perturb=True), max_batch=4)
+    icfg = dataclasses.replace(pkg.tiny(pkg.OPENCLIP_H14, dim=640, depth=2, heads=8, mlp=1280), embed=96)
+    img = pkg.ViTEngine(icfg, pkg.random_weights(icfg, seed=8, perturb=True), max_batch=2)
+    for rep in range(3):
+        ids = _token_rows(tcfg, [3 + rep, 40, 7], seed=rep).cuda()
+        assert torch.equal(txt.encode_text(ids, graph=True), txt.encode_text(ids))
+        x = torch.randn(1, 3, 224, 224, generator=torch.Generator().manual_seed(rep)).cuda()
+        assert torch.equal(img.encode_image(x, graph=True), img.encode_image(x))
+    assert set(txt._graphs) == {("text", 3)} and set(img._graphs) == {("image", 1)}

@@ -49,6 +49,10 @@ def main():
         out[f"check_text_goal_{n_views}_views_ms"] = round(timed(
             lambda: pkg.score_views(img.encode_image(views), txt.encode_text(ids)[0])), 3)
     out["encode_text_1_prompt_ms"] = round(timed(lambda: txt.encode_text(ids)), 3)
+    out["encode_text_1_prompt_graph_ms"] = round(timed(lambda: txt.encode_text(ids, graph=True)), 3)
+    one = torch.randn(1, 3, 224, 224, generator=g).cuda()
+    out["encode_image_1_goal_ms"] = round(timed(lambda: img.encode_image(one)), 3)
+    out["encode_image_1_goal_graph_ms"] = round(timed(lambda: img.encode_image(one, graph=True)), 3)
     labels = ids.repeat(8, 1)
     out["encode_text_8_labels_ms"] = round(timed(lambda: txt.encode_text(labels)), 3)
     print(json.dumps(out))

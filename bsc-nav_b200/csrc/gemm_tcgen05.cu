@@ -442,6 +442,10 @@ int gemm_f16_launch(const CUtensorMap* map_a, const CUtensorMap* map_w, const CU
   if (!map_out) map_out = map_a;       // unused by the direct-store epilogues
   static int use_cluster = -1;
   if (use_cluster < 0) { const char* e = getenv("BSCNAV_GEMM_CLUSTER"); use_cluster = e ? atoi(e) : 1; }   // CTA pairs by default
+  // few output tiles (small M: one goal image, one text prompt, a handful of queries): 128-wide tiles through the 128-row-box
+  // weight map double the number of CTAs that stream the layer's weights -- these calls are bound by that, not by the MMAs
+  if (gemm_block_n(N) == 256 && map_w_half && ((M + BM - 1) / BM) * (N / 256) * 2 <= sm_count())
+    return launch_bn<128>(map_a, map_w_half, nullptr, map_out, M, N, K, epi, stream);
   if (!use_cluster) map_w_half = nullptr;
   if (gemm_block_n(N) == 256) return launch_bn<256>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream);
   return launch_bn<128>(map_a, map_w, nullptr, map_out, M, N, K, epi, stream);

@@ -8,6 +8,8 @@
  * void*; calls enqueue work on that stream and return without synchronising (unless stated); the return
  * value is 0 on success or a negative BSCNAV_E* code; nothing throws; re-entrant per stream.
  * The library never allocates device memory: the caller owns every buffer (sizes given by *_bytes helpers).
+ * Process model: one process per GPU (the torch.distributed layout); per-kernel attributes (shared-memory opt-in,
+ * cluster occupancy) are cached per process for the device that is current at the first launch.
  */
 #ifndef BSCNAV_B200_H
 #define BSCNAV_B200_H

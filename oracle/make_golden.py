@@ -69,7 +69,8 @@ def build_vit(spec):
 
 
 def run_reference(name):
-    ci = case_inputs(name)
+    """name: a fixture name of case_inputs, or a case dict of the same shape (live cross-checks in the CPU tests)."""
+    ci = case_inputs(name) if isinstance(name, str) else name
     vit, dim = build_vit(ci["vit"])
     args = rh.default_args(**ci["args"])
     rh.reset_fake_h5()

@@ -11,12 +11,12 @@ CASES = ("cfg1", "two_pose", "sampled")
 
 
 def port_run(name, g):
-    ci = mg.case_inputs(name)
+    ci = mg.case_inputs(name) if isinstance(name, str) else name
     a = ci["args"]
     tok = g["patch_tokens"]
     p = mp.MemoryParams(height=a["height"], width=a["width"], grid_size=a["grid_size"],
                         floor_height=a.get("floor_height", -10.0), map_height=a.get("map_height", 10.0),
-                        depth_sample_rate=a["depth_sample_rate"], n_patch_h=tok.shape[2], n_patch_w=tok.shape[1],
+                        cell_size=a.get("cell_size", 0.1), depth_sample_rate=a["depth_sample_rate"], n_patch_h=tok.shape[2], n_patch_w=tok.shape[1],
                         token_dim=tok.shape[3], cache_size=10 ** 9)
     om = mp.OracleMemory(p)
     inv0 = None
@@ -113,3 +113,53 @@ def test_loop_restatement_equals_vectorised(golden):
     assert list(om.occupied.keys()) == list(om2.occupied.keys())
     assert np.array_equal(np.array(om.grid_rgb), np.array(om2.grid_rgb))
     assert sum(len(v) for v in om.tokens.values()) == sum(len(v) for v in om2.tokens.values())
+
+
+def _random_case(seed):
+    """Small random scene for the live cross-check: tilted / rolled poses (not only yaw), depth holes (0), points beyond
+    max_depth and below min_depth, points leaving the grid and the height range, a non-default cell size."""
+    rng = np.random.default_rng(seed)
+    h, w = (40, 56) if seed % 2 else (48, 48)
+    frames = []
+    for f in range(3):
+        rgb = rng.integers(0, 256, size=(h, w, 4), dtype=np.uint8)
+        depth = rng.uniform(0.3, 6.0, size=(h, w)).astype(np.float32)
+        depth[rng.random((h, w)) < 0.1] = 0.0                       # sensor holes
+        depth[rng.random((h, w)) < 0.05] = 25.0                     # beyond max_depth
+        depth[rng.random((h, w)) < 0.03] = 0.1                      # exactly min_depth: strict bound, dropped (utils.py:174-176)
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        if f == 0:
+            q = np.array([0.0, 0.0, 0.0, 1.0])
+        pose = np.concatenate([rng.uniform(-1.5, 1.5, 3) * (f > 0), q])
+        frames.append((rgb, depth, pose))
+    return dict(args=dict(height=h, width=w, grid_size=40, depth_sample_rate=1 if seed % 3 else 7, cell_size=[0.1, 0.07, 0.25][seed % 3],
+                          floor_height=-1.0, map_height=1.5), frames=frames, patch=14, vit=("table", 256, 16, 11 + seed),
+                **({} if seed % 3 else {"shuffle_seed": 3 + seed}))
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_port_matches_reference_live_random(seed):
+    """Beyond the three committed fixtures: the port against the unmodified reference executed here on random scenes."""
+    if not rh.available():
+        pytest.skip("/root/reference not mounted (GPU box)")
+    ci = _random_case(seed)
+    g = mg.run_reference(ci)
+    p, om = port_run(ci, g)
+    items = sorted(((t[1], k, t) for k, v in om.tokens.items() for t in v), key=lambda x: x[0])
+    assert len(items) == len(g["feat_dis"]) > 50
+    assert np.array_equal(np.array([[k[0], k[1], t[3]] for _, k, t in items]), g["feat_pos"])
+    assert np.array_equal(np.array([t[0] for _, k, t in items], dtype=np.float32), g["feat_dis"])
+    assert np.array_equal(np.array([[t[2][0], t[2][1] * p.n_patch_w + t[2][2]] for _, k, t in items]), g["feat_src"])
+    assert np.array_equal(np.array(list(om.occupied.keys())), g["grid_rgb_pos"])
+    assert np.array_equal(np.array(om.grid_rgb), g["grid_rgb"])
+    assert np.array_equal(np.array(om.weight, dtype=np.float32), g["weight"])
+    assert np.array_equal(om.cv_map, g["cv_map"]) and np.array_equal(om.max_height, g["max_height"])
+    # and the query over it
+    tok = g["patch_tokens"]
+    keys = sorted(om.tokens.keys())
+    feats = [np.stack([tok[t[2][0], t[2][1], t[2][2]] for t in sorted(om.tokens[k], key=lambda t: t[1])]) for k in keys]
+    _, pos, sim = mp.query_topk(np.array(keys), feats, g["query_vec"], K=100)
+    np.testing.assert_allclose(sim, g["topk_sim"], rtol=0, atol=2e-7)
+    cut = g["topk_sim"][-1] + 1e-6
+    assert {tuple(r) for r, s in zip(g["topk_pos"], g["topk_sim"]) if s > cut} <= {tuple(r) for r in pos}

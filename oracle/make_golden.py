@@ -56,6 +56,27 @@ def case_inputs(name):
         frames = [mp.synthetic_frame(f, 680, 680, n_frames=12) for f in (0, 1, 2)]
         return dict(args=dict(height=680, width=680, grid_size=1000, depth_sample_rate=1000), frames=frames,
                     patch=14, vit=("table", 256, 32, 9), shuffle_seed=7)
+    if name == "tilted":     # rolled / tilted poses (all nine rotation entries non-zero), sensor holes, points at / beyond both
+        rng = np.random.default_rng(21)                                    # depth bounds: the erasure cases of the path
+        frames = []
+        for f in range(3):
+            rgb, depth, pose = mp.synthetic_frame(f, 96, 128, n_frames=6)
+            depth = depth.copy()
+            depth[rng.random(depth.shape) < 0.08] = 0.0                    # holes
+            depth[rng.random(depth.shape) < 0.04] = 25.0                   # beyond max_depth
+            depth[rng.random(depth.shape) < 0.02] = np.float32(0.1)        # float32(0.1) > 0.1: just inside the strict bound
+            depth[rng.random(depth.shape) < 0.02] = np.float32(10.0)       # exactly max_depth: dropped
+            rv = rng.uniform(-0.35, 0.35, size=3)                          # rotation vector, up to ~35 degrees, any axis
+            ang = np.linalg.norm(rv)
+            dq = np.concatenate([np.sin(ang / 2) * rv / ang, [np.cos(ang / 2)]])
+            x1, y1, z1, w1 = pose[3:]
+            x2, y2, z2, w2 = dq
+            q = np.array([w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2,
+                          w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2, w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2])
+            pose = np.concatenate([pose[:3] + rng.uniform(-0.2, 0.2, size=3), q / np.linalg.norm(q)])
+            frames.append((rgb, depth, pose))
+        return dict(args=dict(height=96, width=128, grid_size=64, depth_sample_rate=1, floor_height=-2.0,
+                              map_height=2.0), frames=frames, patch=14, vit=("table", 256, 32, 13))
     raise KeyError(name)
 
 
@@ -135,7 +156,7 @@ def run_reference(name):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
-    for name in ("cfg1", "two_pose", "sampled"):
+    for name in sys.argv[1:] or ("cfg1", "two_pose", "sampled", "tilted"):
         out = run_reference(name)
         path = os.path.join(OUT, f"{name}.npz")
         np.savez_compressed(path, **out)

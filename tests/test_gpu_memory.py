@@ -58,7 +58,8 @@ def _oracle_kept(g, cache, bev, n_patch):
     return {k: sorted(v, key=lambda t: (t[0], t[1]))[:cache] for k, v in cells.items()}
 
 
-@pytest.mark.parametrize("name", ["cfg1", "two_pose", "sampled"])
+# "tilted": rolled / tilted poses, depth holes, points at and beyond both depth bounds, up to 136 points in one voxel
+@pytest.mark.parametrize("name", ["cfg1", "two_pose", "sampled", "tilted"])
 @pytest.mark.parametrize("cache,bev", [(1, False), (10, False), (1, True), (4, True)])
 def test_fuse_matches_reference_fixture(pkg, golden, name, cache, bev):
     g = golden(name)

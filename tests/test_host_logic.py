@@ -23,6 +23,24 @@ def test_pose_chain_matches_oracle_and_batch_is_bit_identical():
     assert np.array_equal(chain2.batch(poses[3:5]), np.stack(singles[3:5]))   # T0 stays the first pose ever seen
 
 
+def test_pose_chain_general_rotations():
+    """Rolled / tilted poses (all nine rotation entries non-zero), not only the yaw-only poses of the synthetic circle."""
+    geo = importlib.import_module("bsc-nav_b200.geometry")
+    p = mp.MemoryParams(height=48, width=64)
+    rng = np.random.default_rng(5)
+    q = rng.normal(size=(12, 4))
+    poses = np.concatenate([rng.uniform(-4, 4, size=(12, 3)), q / np.linalg.norm(q, axis=1, keepdims=True)], axis=1)
+    chain = geo.PoseChain(p.base_forward_axis, p.base_left_axis, p.base_up_axis, p.base2cam_rot, p.sensor_height)
+    inv0, singles = None, []
+    for po in poses:
+        T, inv0 = mp.pose_chain(p, po, inv0)
+        Tg = chain(po)
+        assert np.array_equal(T, Tg)
+        singles.append(Tg)
+    chain2 = geo.PoseChain(p.base_forward_axis, p.base_left_axis, p.base_up_axis, p.base2cam_rot, p.sensor_height)
+    assert np.array_equal(chain2.batch(poses), np.stack(singles))
+
+
 def test_geom_struct_matches_oracle_params():
     store = importlib.import_module("bsc-nav_b200.store")
     for kw in (dict(height=480, width=640, grid_size=512), dict(height=680, width=680, grid_size=1000),

@@ -7,7 +7,7 @@ from oracle import memory_port as mp
 from oracle import make_golden as mg
 from oracle import ref_harness as rh
 
-CASES = ("cfg1", "two_pose", "sampled")
+CASES = ("cfg1", "two_pose", "sampled", "tilted")
 
 
 def port_run(name, g):

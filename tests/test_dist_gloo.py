@@ -121,3 +121,31 @@ def test_query_sharded_world2(tmp_path):
         assert r0["c"][qi] == 10
         assert [tuple(v) for v in r0["p"][qi].tolist()] == [e[1] for e in exp]
         assert np.array_equal(r0["s"][qi], np.array([e[0] for e in exp], dtype=np.float32))
+
+
+def test_merge_topk_against_brute_force():
+    """K-way merge of per-rank results: per-cell max over ranks, similarity descending, ties by (row, col, h), padding past the
+    count -- against a dictionary-and-sort statement, with duplicated cells across ranks, empty ranks and k < candidates."""
+    d = importlib.import_module("bsc-nav_b200.dist")
+    for seed in range(6):
+        g = torch.Generator().manual_seed(seed)
+        R, Q, K = [(3, 4, 10), (2, 1, 16), (4, 3, 5)][seed % 3]
+        k = K if seed % 2 else max(1, K - 3)
+        sims = torch.randn(R, Q, K, generator=g)
+        if seed >= 3:
+            sims = torch.round(sims * 2) / 2                        # coarse values: many exact ties
+        pos = torch.randint(0, 5, (R, Q, K, 3), generator=g, dtype=torch.int32)   # small range: cells repeat across ranks
+        cnt = torch.randint(0, K + 1, (R, Q), generator=g, dtype=torch.int32)
+        cnt[:, 0] = 0 if seed == 0 else cnt[:, 0]                   # a query nobody has candidates for
+        s, p, c = d.merge_topk(sims, pos, cnt, k)
+        for qi in range(Q):
+            best = {}
+            for r in range(R):
+                for j in range(int(cnt[r, qi])):
+                    key, v = tuple(pos[r, qi, j].tolist()), float(sims[r, qi, j])
+                    best[key] = max(best.get(key, float("-inf")), v)
+            exp = sorted(best.items(), key=lambda kv: (-kv[1], kv[0]))[:k]
+            assert int(c[qi]) == len(exp)
+            assert [tuple(v) for v in p[qi, :len(exp)].tolist()] == [e[0] for e in exp]
+            assert s[qi, :len(exp)].tolist() == [float(np.float32(e[1])) for e in exp]
+            assert torch.all(s[qi, len(exp):] == float("-inf")) and torch.all(p[qi, len(exp):] == -1)

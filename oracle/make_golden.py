@@ -10,6 +10,7 @@ from __future__ import annotations
 import contextlib
 import importlib
 import io
+import math
 import os
 import sys
 
@@ -66,14 +67,11 @@ def case_inputs(name):
             depth[rng.random(depth.shape) < 0.04] = 25.0                   # beyond max_depth
             depth[rng.random(depth.shape) < 0.02] = np.float32(0.1)        # float32(0.1) > 0.1: just inside the strict bound
             depth[rng.random(depth.shape) < 0.02] = np.float32(10.0)       # exactly max_depth: dropped
-            rv = rng.uniform(-0.35, 0.35, size=3)                          # rotation vector, up to ~35 degrees, any axis
-            ang = np.linalg.norm(rv)
-            dq = np.concatenate([np.sin(ang / 2) * rv / ang, [np.cos(ang / 2)]])
-            x1, y1, z1, w1 = pose[3:]
-            x2, y2, z2, w2 = dq
-            q = np.array([w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2,
-                          w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2, w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2])
-            pose = np.concatenate([pose[:3] + rng.uniform(-0.2, 0.2, size=3), q / np.linalg.norm(q)])
+            # a general rotation near the circle pose, built with +, *, / and sqrt only (correctly rounded everywhere), so the
+            # GPU box regenerates bit-identical inputs whatever its libm / SIMD dispatch does with sin and cos
+            q = pose[3:] + rng.uniform(-0.3, 0.3, size=4)
+            q = q / math.sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3])
+            pose = np.concatenate([pose[:3] + rng.uniform(-0.2, 0.2, size=3), q])
             frames.append((rgb, depth, pose))
         return dict(args=dict(height=96, width=128, grid_size=64, depth_sample_rate=1, floor_height=-2.0,
                               map_height=2.0), frames=frames, patch=14, vit=("table", 256, 32, 13))

@@ -15,6 +15,7 @@ from __future__ import annotations
 import argparse
 import importlib
 import json
+import math
 import os
 import sys
 import threading
@@ -120,41 +121,67 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------- reference arm / cpu baseline
-_CPU_W = {}
+_CPU = {}
 
 
-def cpu_reference_rate(n_frames: int, sample_points: int, threads: int):
-    """The reference's CPU algorithm on `n_frames` frames: fp32 ViT forward on `threads` host threads (its per-frame,
-    batch-1 call pattern, memory_2.py:732-742) + the literal per-point loop of obs2voxeltoken (memory_2.py:863-903) over
-    the first `sample_points` valid points, scaled to the frame's valid points.  Returns (frames/s, detail)."""
+def _cpu_setup(threads: int):
     from oracle import memory_port as mp
-    from oracle import vit_ref
     vc = importlib.import_module("bsc-nav_b200.vit_config")
     torch.set_num_threads(threads)
-    cfg = vc.CLIP_L14
-    if "w" not in _CPU_W:
-        _CPU_W["w"] = vc.random_weights(cfg, seed=0)
-    w = _CPU_W["w"]
-    p = mp.MemoryParams(height=H, width=W, grid_size=GS, token_dim=D, cache_size=1, bev=True)
+    if "w" not in _CPU:
+        _CPU["w"] = vc.random_weights(vc.CLIP_L14, seed=0)
+    return mp, vc.CLIP_L14, _CPU["w"]
+
+
+def cpu_reference_step(frame: int, stride: int, threads: int, rate: int = 1):
+    """One step of the reference's CPU algorithm on frame `frame` of the workload (oracle port; memory_2.py:842-903):
+    the fp32 ViT-L/14 forward of the WHOLE frame on `threads` host threads (the reference's batch-1 call, :732-742) and the
+    literal per-point Python loop of obs2voxeltoken (:863-903) over every `stride`-th point of the visiting order.
+    rate > 1: the reference's own sub-sampling (depth_sample_rate, a seeded permutation; :746-749) -- then stride must be 1 and the
+    whole frame is processed.  Returns a dict of measured seconds and point counts; nothing is extrapolated here."""
+    from oracle import vit_ref
+    mp, cfg, w = _cpu_setup(threads)
+    p = mp.MemoryParams(height=H, width=W, grid_size=GS, token_dim=D, cache_size=1, bev=True, depth_sample_rate=rate)
     om = mp.OracleMemory(p)
-    inv0 = None
-    t_vit = t_loop = 0.0
-    for f in range(n_frames):
-        rgb, depth, pose = mp.synthetic_frame(f, H, W)
+    rgb, depth, pose = mp.synthetic_frame(frame, H, W)
+    t0 = time.perf_counter()
+    x = vit_ref.preprocess_frame(torch.from_numpy(rgb[None, :, :, :3]))
+    tok = vit_ref.vit_forward(x, w, cfg)[0].reshape(16, 16, D).numpy()
+    t1 = time.perf_counter()
+    T, _ = mp.pose_chain(p, pose, None)
+    perm = np.random.default_rng(frame).permutation(H * W) if rate > 1 else None
+    visited = mp.fuse_frame_loop(p, rgb, depth, T, tok, om, perm=perm, stride=stride)
+    t2 = time.perf_counter()
+    n_visit_full = int(((depth > p.min_depth) & (depth < p.max_depth)).sum()) if rate == 1 else visited
+    return {"t_vit": t1 - t0, "t_loop": t2 - t1, "visited": visited, "points_in_frame": n_visit_full}
+
+
+def cpu_dense_rate(steps: int, warmup: int, stride: int, threads: int, budget_s: float):
+    """frames/s of the dense (rate = 1) reference build from `steps` measured steps.  A step = whole-frame ViT + the point loop
+    over 1/stride of the frame's points; the per-frame time is t_vit + t_loop * (points in frame / points visited) -- the loop is
+    a flat per-point loop, its cost per point is what is measured.  Returns (value, measured wall seconds per step, steps run, text)."""
+    vals, walls = [], []
+    t_begin = time.perf_counter()
+    for i in range(warmup + steps):
         t0 = time.perf_counter()
-        x = vit_ref.preprocess_frame(torch.from_numpy(rgb[None, :, :, :3]))
-        tok = vit_ref.vit_forward(x, w, cfg)[0].reshape(16, 16, D).numpy()
-        t1 = time.perf_counter()
-        T, inv0 = mp.pose_chain(p, pose, inv0)
-        visited = mp.fuse_frame_loop(p, rgb, depth, T, tok, om, max_points=sample_points)
-        t2 = time.perf_counter()
-        n_valid = int(((depth > p.min_depth) & (depth < p.max_depth)).sum())
-        t_vit += t1 - t0
-        t_loop += (t2 - t1) * (n_valid / max(visited, 1))
-    per_frame = (t_vit + t_loop) / n_frames
-    detail = (f"{n_frames} frame(s) of the workload: fp32 ViT-L/14 forward on {threads} threads ({t_vit / n_frames:.2f} s/frame) + "
-              f"per-point loop over the first {sample_points} of ~{H * W} points, scaled ({t_loop / n_frames:.1f} s/frame)")
-    return 1.0 / per_frame, detail
+        m = cpu_reference_step(i, stride, threads)
+        wall = time.perf_counter() - t0
+        if i == 0:                                                  # the first step shows the box's speed: keep the run inside its budget
+            n_all = warmup + steps
+            factor = n_all * m["t_loop"] / max(budget_s - n_all * m["t_vit"], 0.25 * budget_s)
+            if factor > 1.0:
+                stride = int(math.ceil(stride * factor))
+        if i >= warmup:
+            per_frame = m["t_vit"] + m["t_loop"] * m["points_in_frame"] / max(m["visited"], 1)
+            vals.append(1.0 / per_frame)
+            walls.append(wall)
+            last = m
+        if i >= warmup and time.perf_counter() - t_begin > budget_s:
+            break
+    text = (f"each step: fp32 ViT-L/14 forward of one whole frame on {threads} threads ({last['t_vit']:.2f} s) + the per-point loop over "
+            f"{last['visited']} of {last['points_in_frame']} valid points (every {stride}-th, {last['t_loop']:.2f} s measured); frame time = "
+            f"t_vit + t_loop x points/visited; excluded: the reference's 4 KB D2H per point (memory_2.py:883) and its HDF5 flush (:326-358)")
+    return float(np.mean(vals)), float(np.mean(walls)), len(vals), text
 
 
 def run_reference(args):
@@ -162,21 +189,28 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    # warm-up + K steps; each step is one frame on a bounded point sample
-    vals = []
-    for i in range(args.warmup + args.steps):
-        v, detail = cpu_reference_rate(1, args.ref_points, threads)
-        if i >= args.warmup:
-            vals.append(v)
-        if i >= args.warmup and len(vals) >= 3 and time.time() - T_START > 240:
-            break
-    value = float(np.mean(vals))
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": len(vals),
-            "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (ViT) / f64 (geometry)", "data": "synthetic", "config": {"workload": WORKLOAD},
-            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port", "sample": detail},
+    stride = max(1, (H * W) // max(args.ref_points, 1))
+    value, wall, n, text = cpu_dense_rate(args.steps, args.warmup, stride, threads, budget_s=args.ref_budget)
+    legs = {}
+    if args.ref_legs:
+        # (alpha) the reference as shipped: depth_sample_rate = 1000 (args.py), whole frames, nothing scaled
+        t0 = time.perf_counter()
+        ms = [cpu_reference_step(100 + i, 1, threads, rate=1000) for i in range(args.ref_alpha_frames)]
+        legs["alpha_as_shipped_rate1000"] = {"frames_per_s": len(ms) / (time.perf_counter() - t0), "frames": len(ms),
+                                             "points_per_frame": ms[0]["visited"], "t_vit_s": float(np.mean([m["t_vit"] for m in ms])),
+                                             "t_loop_s": float(np.mean([m["t_loop"] for m in ms]))}
+        # (gamma) the reference's query arithmetic over stored tokens
+        sample = 20000
+        per = cpu_query_rate(sample)
+        legs["gamma_query"] = {"queries_per_s": 1.0 / (per * GS * GS), "cores": 1,
+                               "sample": f"oracle port of voxel_localized (memory_2.py:642-671) over {sample} of {GS * GS} stored tokens, per-token cost x {GS * GS}"}
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": n,
+            "warmup": args.warmup, "ms_per_step": wall * 1e3, "frames_per_step": value * wall, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (ViT) / f64 (geometry)", "data": "synthetic",
+            "config": {"workload": WORKLOAD},
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port", "sample": text},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "legs": legs, "gpu_launches": 0}
     print(json.dumps(line))
 
 
@@ -261,9 +295,11 @@ def query_leg(store, dev, peak_gbs, with_cpu):
 
 def gemm_traffic():
     """Mean DRAM traffic per k_gemm_f16 launch of a step, from the committed ncu --set full capture (profiles/)."""
-    p = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-    if not os.path.exists(p):
+    import glob
+    found = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_gemm_traffic.json")))
+    if not found:
         return None
+    p = found[-1]                                  # the latest round's capture
     with open(p) as f:
         d = json.load(f)
     per = {l["kernel"].split()[0]: l["traffic_bytes"] for l in d["launches"]}
@@ -295,153 +331,270 @@ def run_ours(args):
             dist.barrier()
     pkg = importlib.import_module("bsc-nav_b200")
     synth = importlib.import_module("bsc-nav_b200.synth")
+    dmod = importlib.import_module("bsc-nav_b200.dist")
     lib = blib.lib()
     B, K, Wm = args.batch, args.steps, args.warmup
     dev = torch.device("cuda", local)
+    frames_mode = args.sharding == "frames"
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # engine + memory (the reference-facing object)
-    cfg = pkg.CLIP_L14 if args.model == "clip" else pkg.DINOV2_L14_REG
-    eng = pkg.ViTEngine(cfg, pkg.random_weights(cfg, seed=0), max_batch=B, device=dev)
-    margs = synth.Args(height=H, width=W, grid_size=GS, depth_sample_rate=1)
-    mem = pkg.VoxelTokenMemory(margs, preload_dino=eng, need_diffusion=False, cache_size=1, bev=True, max_batch=B)
-    # synthetic pool: each rank owns a scene (weak scaling); P frames cycled, P*2.46 MB > L2
-    P = args.pool_batches * B
-    rgb_h = torch.empty(P, H, W, 4, dtype=torch.uint8, pin_memory=True)
-    dep_h = torch.empty(P, H, W, dtype=torch.float32, pin_memory=True)
-    poses = np.empty((P, 7))
-    for f in range(P):
-        r, d, po = synth.synthetic_frame(f, H, W, n_frames=1000, seed_base=100000 * rank)
-        rgb_h[f] = torch.from_numpy(r)
-        dep_h[f] = torch.from_numpy(d)
-        poses[f] = po
-    rgb_d, dep_d = rgb_h.to(dev), dep_h.to(dev)
-    chain = pkg.PoseChain(margs.base_forward_axis, margs.base_left_axis, margs.base_up_axis, margs.base2cam_rot, margs.sensor_height)
-    tfs = np.stack([chain(p) for p in poses]).reshape(P, 16)
-    tfs_d = torch.from_numpy(tfs).to(dev)
-    store = mem.store
-    npts = H * W
-
-    def step_device(s):
-        # ViT of this batch on the current stream; unprojection + scatter on the memory's side stream, overlapping the
-        # next batch's ViT (VoxelTokenMemory.fuse_device: the same schedule fuse_frames uses after its H2D copies)
-        b0 = (s % args.pool_batches) * B
-        ob = (np.arange(B, dtype=np.int64) + (s * B)) * npts % (2 ** 32 - npts * B)
-        mem.fuse_device(rgb_d[b0:b0 + B], dep_d[b0:b0 + B], tfs_d[b0:b0 + B], ord_base=ob)
-
-    def timed(fn, n):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        for s in range(n):
-            fn(s)
-        mem._join()                    # the last batch's scatter (side stream) belongs to the timed region
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
+    def max_over_ranks(ms):
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t[0])
         return ms
 
-    # ---- value: kernels only, inputs in HBM
-    for s in range(Wm):
-        step_device(s)
-    sampler = ClockSampler(local)
-    sampler.start()
-    l0 = lib.bscnav_launch_count()
-    ms = timed(step_device, K)
-    launches = lib.bscnav_launch_count() - l0
-    clocks = sampler.result()
-    value = world * B * K / (ms / 1e3)
-
-    # ---- roofline of the dominant kernel (tcgen05 GEMM), CUDA events around every launch of two more steps
-    eng.profile(True)
-    for s in range(2):
-        step_device(s)
-    mem._join()
-    torch.cuda.synchronize()
-    prof = eng.profile_read()
-    eng.profile(False)
-    peak_tf, peak_gbs, peak_src = peaks()
-    g_ms, g_flops, g_n = prof["gemm"]
-    achieved = g_flops / (g_ms / 1e3) / 1e12
-    step_ms_prof = sum(v[0] for v in prof.values()) / 2
-    roofline = {"bound": "tensor", "kernel": "k_gemm_f16 (tcgen05, fp16 x fp16 -> fp32)", "achieved": achieved, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": gemm_traffic(),
-                "traffic_source": "profiles/r01_gemm_traffic.json (ncu --set full, mean over the four GEMM shapes of a layer, B=55)",
-                "peak_source": peak_src,
-                "launches_per_step": g_n // 2, "share_of_step": (g_ms / 2) / (ms / K),
-                "breakdown_ms_per_step": {k: v[0] / 2 for k, v in prof.items()},
-                "attention_tflops": prof["attention"][1] / (prof["attention"][0] / 1e3) / 1e12 if prof["attention"][0] else None}
-
-    # ---- e2e: public API, pinned host buffers, H2D inside the timed region, D2H read of the slot count every step
-    mem._clear_memory()
-
-    reads = []
-
-    def step_e2e(s):
-        b0 = (s % args.pool_batches) * B
-        mem.fuse_frames(rgb_h[b0:b0 + B], dep_h[b0:b0 + B], poses[b0:b0 + B])   # H2D on a side stream, overlapped
-        reads.append(mem.max_id_async())                                         # D2H read of the step's result (pinned)
-
-    for s in range(Wm):
-        step_e2e(s)
-    ms_e2e = timed(step_e2e, K)
-    counts = [mem.max_id_wait(h) for h in reads[-K:]]
-    assert all(c > 0 for c in counts) and counts == sorted(counts), counts
-    e2e = {"value": world * B * K / (ms_e2e / 1e3), "unit": "frames/s",
-           "h2d_bytes_per_step": B * (H * W * 4 + H * W * 4 + 16 * 8 + 4), "d2h_bytes_per_step": 8,
-           "api": "VoxelTokenMemory.fuse_frames + max_id_async (copies overlap the previous batch)", "slots_after": counts[-1]}
-
-    # ---- N > 1: the collective path -- treat the ranks' stores as frame shards of ONE scene: export the rows each rank produced,
-    # one all-gather over NVLink, every rank merges the others' rows under the same winner rule (dist.merge_scene_across_ranks)
-    merge = None
+    # the collective path is parity-checked on these very ranks before anything is timed (raises on mismatch)
+    merge_check = None
     if world > 1:
-        dmod = importlib.import_module("bsc-nav_b200.dist")
-        mem._join()
-        slots_before = store.count()
+        merge_check = {"ok": True, "rows_exported_per_rank": dmod.merge_self_check(),
+                       "what": "frames of a small scene sharded over the ranks, packed all-gather merge == joint build, bit for bit"}
+
+    # engine + memory (the reference-facing object)
+    cfg = pkg.CLIP_L14 if args.model == "clip" else pkg.DINOV2_L14_REG
+    eng = pkg.ViTEngine(cfg, pkg.random_weights(cfg, seed=0), max_batch=B, device=dev)
+    margs = synth.Args(height=H, width=W, grid_size=GS, depth_sample_rate=1)
+    mem = pkg.VoxelTokenMemory(margs, preload_dino=eng, need_diffusion=False, cache_size=1, bev=True, max_batch=B)
+    # synthetic pool of colour / depth images (each rank its own seeds), cycled; P * 2.46 MB > L2.  The POSES never repeat
+    # (synth.tour_pose of the global frame index), so every step touches new cells and commits new winner rows.
+    P = args.pool_batches * B
+    rgb_h = torch.empty(P, H, W, 4, dtype=torch.uint8, pin_memory=True)
+    dep_h = torch.empty(P, H, W, dtype=torch.float32, pin_memory=True)
+    for f in range(P):
+        r, d, _ = synth.synthetic_frame(f, H, W, n_frames=1000, seed_base=100000 * (0 if frames_mode else rank))
+        rgb_h[f] = torch.from_numpy(r)
+        dep_h[f] = torch.from_numpy(d)
+    rgb_d, dep_d = rgb_h.to(dev), dep_h.to(dev)
+    store = mem.store
+    npts = H * W
+    n_prof = args.profile_steps
+
+    def poses_of(f0, n):
+        return np.stack([synth.tour_pose(f) for f in range(f0, f0 + n)])
+
+    def pool_slice(f0, n):
+        i = f0 % P
+        return slice(i, i + n) if i + n <= P else None
+
+    # ------------------------------------------------------------------------------------------------ scene-parallel (default)
+    def make_tfs(n_frames_total):
+        mem._clear_memory()
+        tfs = mem._chain.batch(poses_of(0, n_frames_total)).reshape(n_frames_total, 16)
+        return torch.from_numpy(tfs).to(dev)
+
+    def step_device(s, tfs_d):
+        # ViT of this batch on the current stream; unprojection + scatter on the memory's side stream, overlapping the
+        # next batch's ViT (VoxelTokenMemory.fuse_device: the same schedule fuse_frames uses after its H2D copies)
+        b0 = (s % args.pool_batches) * B
+        f0 = s * B
+        ob = (np.arange(B, dtype=np.int64) + f0) * npts % (2 ** 32 - npts * B)
+        mem.fuse_device(rgb_d[b0:b0 + B], dep_d[b0:b0 + B], tfs_d[f0:f0 + B], ord_base=ob)
+
+    def timed(fn, n, first=0):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
-        counts = dmod.merge_scene_across_ranks(store, 0, 2 ** 32 - 1, slots_before * store.g.cache + 16)
+        for s in range(first, first + n):
+            fn(s)
+        mem._join()                    # the last batch's scatter (side stream) belongs to the timed region
         e1.record()
         barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        merge = {"ms": float(t[0]), "rows_exported_per_rank": counts, "allgather_bytes": int(sum(counts)) * (D * 4 + 16),
-                 "slots_before": slots_before, "slots_after": store.count(),
-                 "what": "export delta + all-gather (NCCL) + merge of the other ranks' rows; host-timed protocol steps included"}
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    peak_tf, peak_gbs, peak_src = peaks()
+    line_extra = {}
+    if not frames_mode:
+        # ---- value: kernels only, inputs in HBM
+        tfs_d = make_tfs((Wm + K + n_prof) * B)
+        for s in range(Wm):
+            step_device(s, tfs_d)
+        mem._join()
+        torch.cuda.synchronize()
+        c0 = store.counters[:4].tolist()
+        sampler = ClockSampler(local)
+        sampler.start()
+        l0 = lib.bscnav_launch_count()
+        ms = timed(lambda s: step_device(s, tfs_d), K, first=Wm)
+        launches = lib.bscnav_launch_count() - l0
+        clocks = sampler.result()
+        c1 = store.counters[:4].tolist()
+        value = world * B * K / (ms / 1e3)
+        scatter_work = {"rows_committed_per_step": ((c1[3] - c0[3]) & 0xFFFFFFFF) / K, "slots_before": c0[0], "slots_after": c1[0],
+                        "note": "token rows (4 KB each) copied into the grid by k_commit inside the timed region, per step per rank"}
+
+        # ---- roofline of the dominant kernel (tcgen05 GEMM): CUDA events around every launch of n_prof more steps (outside the
+        # timed region), per-step figures, median over the steps
+        eng.profile(True)
+        per_step = []
+        for s in range(Wm + K, Wm + K + n_prof):
+            step_device(s, tfs_d)
+            mem._join()
+            torch.cuda.synchronize()
+            per_step.append(eng.profile_read())
+        eng.profile(False)
+        g_tf = [p["gemm"][1] / (p["gemm"][0] / 1e3) / 1e12 for p in per_step]
+        a_tf = [p["attention"][1] / (p["attention"][0] / 1e3) / 1e12 for p in per_step if p["attention"][0]]
+        achieved = float(np.median(g_tf))
+        brk = {k: float(np.median([p[k][0] for p in per_step])) for k in per_step[0]}
+        whole = cfg.flops_per_frame() * B / (ms / K / 1e3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "k_gemm_f16 (tcgen05, fp16 x fp16 -> fp32)", "achieved": achieved, "peak": peak_tf,
+                    "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": gemm_traffic(),
+                    "traffic_source": "profiles/ (ncu --set full, mean over the four GEMM shapes of a layer)",
+                    "peak_source": peak_src, "profiled_steps": n_prof, "achieved_min_max": [float(min(g_tf)), float(max(g_tf))],
+                    "launches_per_step": per_step[0]["gemm"][2], "share_of_step": brk["gemm"] / (ms / K),
+                    "breakdown_ms_per_step": brk,
+                    "attention_tflops": float(np.median(a_tf)) if a_tf else None,
+                    "whole_step": {"achieved": whole, "frac": whole / peak_tf,
+                                   "what": "ViT FLOPs of the step (SURVEY 8d formula) / ms_per_step of the TIMED region: every kernel of the step in the denominator"}}
+
+        # ---- e2e: public API, pinned host buffers, H2D inside the timed region, D2H read of the counters every step
+        mem._clear_memory()
+        reads = []
+
+        def step_e2e(s):
+            b0 = (s % args.pool_batches) * B
+            mem.fuse_frames(rgb_h[b0:b0 + B], dep_h[b0:b0 + B], poses_of(s * B, B))   # H2D on a side stream, overlapped
+            reads.append(mem.max_id_async())                                          # D2H read of the step's result (pinned)
+
+        for s in range(Wm):
+            step_e2e(s)
+        ms_e2e = timed(step_e2e, K, first=Wm)
+        counts = [mem.max_id_wait(h) for h in reads[-K:]]
+        rows = [store.rows_committed_wait(h) for h in reads[-K - 1:]]
+        assert all(c > 0 for c in counts) and counts == sorted(counts), counts
+        e2e = {"value": world * B * K / (ms_e2e / 1e3), "unit": "frames/s",
+               "h2d_bytes_per_step": B * (H * W * 4 + H * W * 4 + 16 * 8 + 4), "d2h_bytes_per_step": 16,
+               "api": "VoxelTokenMemory.fuse_frames + max_id_async (copies overlap the previous batch)",
+               "slots_first_last": [counts[0], counts[-1]],
+               "rows_committed_per_step": float(np.mean(np.diff(np.array(rows, dtype=np.int64)) % (2 ** 32)))}
+        step_ms = ms / K
+        cfg_extra = {"batch_frames_per_gpu": B, "frames_per_step": world * B,
+                     "l2": f"inputs larger than L2: {B * 2 * H * W * 4 / 1e6:.0f} MB of frames per step, pool of {P} images, poses never repeat",
+                     "sharding": "one scene per rank, no data-path collective" if world > 1 else "single GPU"}
+        scaling = "weak"
+        line_extra = {"scatter": scatter_work}
+    else:
+        # ------------------------------------------------------------------------------------------------ one scene, frames sharded
+        # BASELINE configs[4]: the frames of ONE scene are sharded over the ranks (dist.shard_frames); each rank fuses its shard into
+        # its own store, then export + ONE packed all-gather + merge (dist.merge_scene_across_ranks).  A step = the whole scene
+        # (build of every shard + the merge); total work is fixed as N grows -> strong scaling.
+        F = args.scene_frames
+        shard = dmod.shard_frames(F, rank, world)
+        all_tfs = None
+
+        def build_scene(_s):
+            nonlocal all_tfs
+            mem._clear_memory()
+            if all_tfs is None:
+                all_tfs = torch.from_numpy(mem._chain.batch(poses_of(0, F)).reshape(F, 16)).to(dev)
+            else:
+                mem._chain.batch(poses_of(0, 1))              # the scene's origin is the first pose on every rank
+            for f0 in range(shard.start, shard.stop, B):
+                n = min(B, shard.stop - f0)
+                i = f0 % (P - B + 1)
+                ob = (np.arange(n, dtype=np.int64) + f0) * npts
+                mem.fuse_device(rgb_d[i:i + n], dep_d[i:i + n], all_tfs[f0:f0 + n], ord_base=ob)
+            mem._join()
+            if world > 1:
+                build_scene.counts = dmod.merge_scene_across_ranks(mem._store, shard.start * npts, shard.stop * npts, GS * GS)
+
+        build_scene.counts = None
+        for s in range(Wm):
+            build_scene(s)
+        sampler = ClockSampler(local)
+        sampler.start()
+        l0 = lib.bscnav_launch_count()
+        ms = timed(build_scene, K)
+        launches = lib.bscnav_launch_count() - l0
+        clocks = sampler.result()
+        value = F * K / (ms / 1e3)
+        slots = store.count()
+        # the merge alone, device-timed, on the final stores (idempotent: a second merge changes nothing)
+        merge_ms = None
+        if world > 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            dmod.merge_scene_across_ranks(mem._store, shard.start * npts, shard.stop * npts, GS * GS)
+            e1.record()
+            barrier()
+            merge_ms = max_over_ranks(e0.elapsed_time(e1))
+        whole = cfg.flops_per_frame() * F * K / world / (ms / 1e3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "whole step (per rank)", "achieved": whole, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": whole / peak_tf, "traffic": None, "peak_source": peak_src}
+        e2e = None
+        step_ms = ms / K
+        cfg_extra = {"batch_frames_per_gpu": B, "frames_per_step": F, "scene_frames": F,
+                     "l2": f"inputs larger than L2: pool of {P} images per rank, poses never repeat",
+                     "sharding": f"ONE scene of {F} frames, contiguous frame shards over {world} ranks, packed NCCL all-gather merge in the timed region"}
+        scaling = "strong"
+        rb = 16 + 4 * D
+        line_extra = {"merge": None if world == 1 else {
+            "ms": merge_ms, "rows_exported_per_rank": build_scene.counts, "allgather_bytes_received_per_rank": int(max(build_scene.counts)) * world * rb,
+            "slots_after": slots, "what": "export_packed + counts all-gather + ONE packed all-gather (NCCL) + merge_packed, timed alone on the final stores"}}
 
     # every rank serves queries over its own scene (BASELINE configs[3]: scenes sharded across GPUs, no collective on the data path)
-    query = query_leg(store, dev, peak_gbs, with_cpu=(world == 1 and rank == 0))
-    if world > 1:
-        t = torch.tensor([query["batch256"]["queries_per_s"], query["single"]["queries_per_s"]], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        query["all_ranks"] = {"batch256_queries_per_s": float(t[0]), "single_queries_per_s": float(t[1]), "ranks": world,
-                              "sharding": "one scene per rank"}
+    query = None
+    latency = None
+    if not frames_mode:
+        if args.latency and rank == 0:
+            latency = latency_leg(mem, eng, synth)
+        query = query_leg(store, dev, peak_gbs, with_cpu=(world == 1 and rank == 0))
+        if world > 1:
+            t = torch.tensor([query["batch256"]["queries_per_s"], query["single"]["queries_per_s"]], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            query["all_ranks"] = {"batch256_queries_per_s": float(t[0]), "single_queries_per_s": float(t[1]), "ranks": world,
+                                  "sharding": "one scene per rank"}
 
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "f16 operands / f32 accumulate (ViT), f64 (cell index), f32 (tokens)", "data": "synthetic",
-            "config": {"workload": WORKLOAD if args.model == "clip" else WORKLOAD.replace("CLIP ViT-L/14", "DINOv2 ViT-L/14-reg"),
-                       "batch_frames_per_gpu": B, "frames_per_step": world * B,
-                       "l2": f"inputs larger than L2: {B * 2 * H * W * 4 / 1e6:.0f} MB of frames per step, pool of {P} frames",
-                       "sharding": "one scene per rank, no data-path collective" if world > 1 else "single GPU"},
+            "config": {"workload": WORKLOAD if args.model == "clip" else WORKLOAD.replace("CLIP ViT-L/14", "DINOv2 ViT-L/14-reg"), **cfg_extra},
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "vit_tflops": cfg.flops_per_frame() * B * K / (ms / 1e3) / 1e12, "query": query, "merge": merge}
-    if world == 1:
-        v, detail = cpu_reference_rate(1, args.ref_points, os.cpu_count() or 1)
-        line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": detail}
+            "vit_tflops": roofline["whole_step"]["achieved"] if "whole_step" in roofline else roofline["achieved"],
+            "query": query, "latency_b1": latency, "merge_check": merge_check, **line_extra}
+    if world == 1 and not frames_mode and args.cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, wall, n, text = cpu_dense_rate(1, 0, max(1, npts // max(args.ref_points, 1)), threads, budget_s=60.0)
+        line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": threads, "kind": "port", "sample": text}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def latency_leg(mem, eng, synth):
+    """The reference's own call pattern (memory_2.py:1086-1101): one obs2voxeltoken per simulator step, B = 1, numpy frames in.
+    `sync`: host wall time per call with the device idle before and drained after (what a simulator loop that looks at the map
+    every step sees); `pipelined`: back-to-back calls without a host wait (copies / ViT / scatter of consecutive frames overlap)."""
+    mem._clear_memory()
+    frames = [synth.synthetic_frame(f, H, W, n_frames=1000) for f in range(8)]
+    n = 40
+    for i in range(8):
+        mem.obs2voxeltoken({"rgb": frames[i % 8][0], "depth": frames[i % 8][1]}, synth.tour_pose(i))
+    mem._join()
+    torch.cuda.synchronize()
+    ts = []
+    for i in range(8, 8 + n):
+        t0 = time.perf_counter()
+        mem.obs2voxeltoken({"rgb": frames[i % 8][0], "depth": frames[i % 8][1]}, synth.tour_pose(i))
+        mem._join()
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    for i in range(8 + n, 8 + 2 * n):
+        mem.obs2voxeltoken({"rgb": frames[i % 8][0], "depth": frames[i % 8][1]}, synth.tour_pose(i))
+    mem._join()
+    torch.cuda.synchronize()
+    pipe = (time.perf_counter() - t0) / n
+    return {"api": "VoxelTokenMemory.obs2voxeltoken (B = 1, numpy obs in, H2D included)", "ms_per_frame_sync_median": float(np.median(ts) * 1e3),
+            "ms_per_frame_sync_p90": float(np.percentile(ts, 90) * 1e3), "ms_per_frame_pipelined": pipe * 1e3,
+            "frames_per_s_pipelined": 1.0 / pipe}
 
 
 T_START = time.time()
@@ -459,7 +612,17 @@ if __name__ == "__main__":
                     help="clip: CLIP ViT-L/14 (BASELINE.json's configuration, default); dinov2: DINOv2 ViT-L/14 with 4 registers, the "
                          "feature extractor the reference itself loads (args.py:50)")
     ap.add_argument("--pool-batches", type=int, default=3, help="distinct batches of synthetic frames cycled through")
-    ap.add_argument("--ref-points", type=int, default=20000, help="points of each frame the CPU reference loop visits")
+    ap.add_argument("--ref-points", type=int, default=10000, help="points of each frame the CPU reference loop visits per step")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds the dense leg of --impl reference may take")
+    ap.add_argument("--ref-alpha-frames", type=int, default=12, help="whole frames of the as-shipped (rate = 1000) reference leg")
+    ap.add_argument("--no-ref-legs", dest="ref_legs", action="store_false", help="--impl reference: skip the alpha / gamma legs")
+    ap.add_argument("--profile-steps", type=int, default=10, help="steps profiled per kernel (outside the timed region) for the roofline line")
+    ap.add_argument("--sharding", default="scenes", choices=["scenes", "frames"],
+                    help="scenes: one scene per rank, no collective (weak scaling, the driver's run); frames: ONE scene of --scene-frames "
+                         "frames sharded over the ranks, build + NCCL merge timed (strong scaling)")
+    ap.add_argument("--scene-frames", type=int, default=1000)
+    ap.add_argument("--no-latency", dest="latency", action="store_false", help="skip the B = 1 obs2voxeltoken latency leg")
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     a = ap.parse_args()
     if a.batch is None:
         a.batch = 54 if a.model == "clip" else 53

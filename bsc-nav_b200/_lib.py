@@ -76,6 +76,11 @@ _SIGS = {
     "bscnav_export_scratch_bytes": (C.c_int64, [C.POINTER(Geom)]),
     "bscnav_export_delta": (C.c_int, [C.POINTER(Geom), C.POINTER(Store), C.c_uint32, C.c_uint32, _P, _P, _P, _P, C.c_int32,
                                       _P, _P, C.c_int64, _P]),
+    "bscnav_packed_row_bytes": (C.c_int64, [C.POINTER(Geom)]),
+    "bscnav_export_packed": (C.c_int, [C.POINTER(Geom), C.POINTER(Store), C.c_uint32, C.c_uint32, _P, C.c_int32, _P, _P, C.c_int64, _P]),
+    "bscnav_merge_packed_scratch_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "bscnav_merge_packed": (C.c_int, [C.POINTER(Geom), C.POINTER(Store), _P, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32, _P,
+                                      C.c_int64, _P]),
     "bscnav_vit_half_elems": (C.c_int64, [C.POINTER(VitCfg)]),
     "bscnav_vit_float_elems": (C.c_int64, [C.POINTER(VitCfg)]),
     "bscnav_vit_workspace_bytes": (C.c_int64, [C.POINTER(VitCfg), C.c_int32]),

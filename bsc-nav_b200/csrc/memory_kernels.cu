@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(kThreads)
 k_commit(const uint4* __restrict__ rec, long long total, const int32_t* __restrict__ occupied,
          const unsigned long long* __restrict__ slot_keys, unsigned long long* __restrict__ row_key,
          int32_t* __restrict__ tok_h, float* __restrict__ norm2, float* __restrict__ feat,
-         const float* __restrict__ tokens, int C, int D) {
+         const float* __restrict__ tokens, long long tok_stride, int C, int D, int32_t* __restrict__ counters) {
   const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
   const int lane = threadIdx.x & 31;
   long long dst_row = -1;
@@ -301,12 +301,13 @@ k_commit(const uint4* __restrict__ rec, long long total, const int32_t* __restri
   }
   unsigned winners = __ballot_sync(0xffffffffu, dst_row >= 0);
   const int nvec = D >> 2;
+  if (lane == 0 && winners) atomicAdd(&counters[3], __popc(winners));     // rows committed since the last reset (wraps)
   while (winners) {
     const int src_lane = __ffs(winners) - 1;
     winners &= winners - 1;
     const long long row = __shfl_sync(0xffffffffu, dst_row, src_lane);
     const uint32_t a = __shfl_sync(0xffffffffu, aux, src_lane);
-    const float4* s = reinterpret_cast<const float4*>(tokens + (long long)(a & kSrcMask) * D);
+    const float4* s = reinterpret_cast<const float4*>(tokens + (long long)(a & kSrcMask) * tok_stride);
     float4* d = reinterpret_cast<float4*>(feat + row * D);
     float acc = 0.f;
     for (int c = lane; c < nvec; c += 32) {
@@ -391,7 +392,7 @@ k_export_scan(const int* __restrict__ tile_count, int* __restrict__ tile_off, in
     if (threadIdx.x == 0) carry += tot;
     __syncthreads();
   }
-  if (threadIdx.x == 0) *out_n = carry < max_out ? carry : max_out;
+  if (threadIdx.x == 0) { out_n[0] = carry < max_out ? carry : max_out; out_n[1] = carry; }   // [1] > max_out: truncated
 }
 __global__ void __launch_bounds__(kThreads)
 k_export_write(const unsigned long long* __restrict__ row_key, const int32_t* __restrict__ counters,
@@ -434,6 +435,72 @@ k_export_write(const unsigned long long* __restrict__ row_key, const int32_t* __
       for (int q = lane; q < (D >> 2); q += 32) d[q] = s[q];
     }
   }
+}
+
+// Packed delta rows (one buffer for the all-gather merge): { int32 cell; int32 h; uint64 key; float feat[D] }, 16 + 4 D bytes
+struct PackedHdr { int32_t cell; int32_t h; unsigned long long key; };
+
+__global__ void __launch_bounds__(kThreads)
+k_export_packed(const unsigned long long* __restrict__ row_key, const int32_t* __restrict__ counters,
+                const int32_t* __restrict__ slot_cell, const int32_t* __restrict__ tok_h, const float* __restrict__ feat,
+                int C, int D, uint32_t lo, uint32_t hi, const int* __restrict__ tile_off, char* __restrict__ packed, int max_out) {
+  const long long n_rows = (long long)counters[0] * C;
+  const long long base = (long long)blockIdx.x * kTile + threadIdx.x * kItems;
+  const long long row_bytes = 16 + 4ll * D;
+  bool f[kItems];
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    f[k] = base + k < n_rows && row_in_range(row_key, base + k, lo, hi);
+    c += f[k] ? 1 : 0;
+  }
+  int tot;
+  int rank = block_excl_scan(c, &tot) + tile_off[blockIdx.x];
+  long long my_dst = -1, my_src = -1;
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    my_dst = -1;
+    if (f[k]) {
+      if (rank < max_out) {
+        my_dst = rank;
+        my_src = base + k;
+        PackedHdr h;
+        h.cell = slot_cell[(base + k) / C]; h.h = tok_h[base + k]; h.key = row_key[base + k];
+        *reinterpret_cast<uint4*>(packed + rank * row_bytes) = *reinterpret_cast<const uint4*>(&h);
+      }
+      ++rank;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, my_dst >= 0);
+    while (m) {
+      const int sl = __ffs(m) - 1;
+      m &= m - 1;
+      const long long dr = __shfl_sync(0xffffffffu, my_dst, sl), sr = __shfl_sync(0xffffffffu, my_src, sl);
+      const float4* s = reinterpret_cast<const float4*>(feat + sr * D);
+      float4* d = reinterpret_cast<float4*>(packed + dr * row_bytes + 16);
+      for (int q = lane; q < (D >> 2); q += 32) d[q] = s[q];
+    }
+  }
+}
+
+// records of a chunk [first, first + n) of the gathered packed buffer: n_segments segments of seg_capacity rows, segment s holds
+// seg_counts[s * count_stride] valid rows; skip_segment (this rank's own rows, already in the store) is ignored
+__global__ void k_packed_records(const char* __restrict__ packed, long long row_bytes, long long first, int n, int seg_capacity,
+                                 const int32_t* __restrict__ seg_counts, int count_stride, int skip_segment, uint4* __restrict__ rec,
+                                 const int32_t* __restrict__ occupied, uint32_t* __restrict__ first_touch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long r = first + i;
+  const int seg = (int)(r / seg_capacity), j = (int)(r - (long long)seg * seg_capacity);
+  int cell = -1;
+  PackedHdr h;
+  h.cell = -1; h.h = 0; h.key = 0;
+  if (seg != skip_segment && j < seg_counts[seg * count_stride]) {
+    *reinterpret_cast<uint4*>(&h) = *reinterpret_cast<const uint4*>(packed + r * row_bytes);
+    cell = h.cell;
+  }
+  rec[i] = make_uint4((uint32_t)cell, (uint32_t)i | ((uint32_t)h.h << kSrcBits), (uint32_t)h.key, (uint32_t)(h.key >> 32));
+  if (cell >= 0 && occupied[cell] < 0) atomicMin(&first_touch[cell], (uint32_t)h.key);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -652,7 +719,7 @@ static int64_t scratch_layout(long long total, FuseScratch* s, char* base) {
 
 // shared tail of fuse / merge: slots, winners, rows
 static int run_store_update(const bscnav_geom_t* g, const bscnav_store_t* st, const FuseScratch& s, long long total,
-                            const float* tokens, cudaStream_t stream) {
+                            const float* tokens, long long tok_stride, cudaStream_t stream) {
   const int n_tiles = (int)((total + kTile - 1) / kTile);
   const int n_blocks = (int)((total + kThreads - 1) / kThreads);
   BSC_LAUNCH(k_count_new, n_tiles, kThreads, 0, stream, s.rec, total, st->occupied_ids, st->first_touch, s.tile_count);
@@ -663,7 +730,7 @@ static int run_store_update(const bscnav_geom_t* g, const bscnav_store_t* st, co
              reinterpret_cast<unsigned long long*>(st->slot_keys), g->cache);
   BSC_LAUNCH(k_commit, n_blocks, kThreads, 0, stream, s.rec, total, st->occupied_ids,
              reinterpret_cast<const unsigned long long*>(st->slot_keys), reinterpret_cast<unsigned long long*>(st->row_key),
-             st->tok_h, st->norm2, st->feat, tokens, g->cache, g->dim);
+             st->tok_h, st->norm2, st->feat, tokens, tok_stride, g->cache, g->dim, st->counters);
   return BSCNAV_OK;
 }
 
@@ -689,7 +756,7 @@ using namespace bscnav;
 
 extern "C" {
 
-int bscnav_abi_version(void) { return 2; }
+int bscnav_abi_version(void) { return 3; }
 const char* bscnav_last_error(void) { return g_last_error; }
 int64_t bscnav_launch_count(void) { return g_launches.load(); }
 
@@ -740,7 +807,7 @@ int bscnav_fuse_frames(const bscnav_geom_t* g, const bscnav_store_t* st, const f
   BSC_LAUNCH(k_index_points, n_blocks, kThreads, 0, stream, *g, depth, poses, ord_base, sample_idx, n_points, total, s.rec,
              st->occupied_ids, st->first_touch);
   if (records_out) BSC_CUDA(cudaMemcpyAsync(records_out, s.rec, total * 16, cudaMemcpyDeviceToDevice, stream));
-  return run_store_update(g, st, s, total, tokens, stream);
+  return run_store_update(g, st, s, total, tokens, g->dim, stream);
 }
 
 int bscnav_merge_delta(const bscnav_geom_t* g, const bscnav_store_t* st, const int32_t* d_cell, const uint64_t* d_key,
@@ -755,7 +822,7 @@ int bscnav_merge_delta(const bscnav_geom_t* g, const bscnav_store_t* st, const i
   cudaStream_t stream = (cudaStream_t)stream_;
   BSC_LAUNCH(k_delta_records, (n + kThreads - 1) / kThreads, kThreads, 0, stream, d_cell,
              reinterpret_cast<const unsigned long long*>(d_key), d_h, n, s.rec, st->occupied_ids, st->first_touch);
-  return run_store_update(g, st, s, n, d_feat, stream);
+  return run_store_update(g, st, s, n, d_feat, g->dim, stream);
 }
 
 int64_t bscnav_export_scratch_bytes(const bscnav_geom_t* g) {
@@ -780,6 +847,57 @@ int bscnav_export_delta(const bscnav_geom_t* g, const bscnav_store_t* st, uint32
   BSC_LAUNCH(k_export_scan, 1, kThreads, 0, stream, tile_count, tile_off, n_tiles, out_n, max_out);
   BSC_LAUNCH(k_export_write, n_tiles, kThreads, 0, stream, rk, st->counters, st->slot_cell, st->tok_h, st->feat, g->cache,
              g->dim, ord_lo, ord_hi, tile_off, d_cell, reinterpret_cast<unsigned long long*>(d_key), d_h, d_feat, max_out);
+  return BSCNAV_OK;
+}
+
+int64_t bscnav_packed_row_bytes(const bscnav_geom_t* g) {
+  if (check_geom(g)) return BSCNAV_EINVAL;
+  return 16 + 4ll * g->dim;
+}
+
+int bscnav_export_packed(const bscnav_geom_t* g, const bscnav_store_t* st, uint32_t ord_lo, uint32_t ord_hi, void* packed,
+                         int32_t max_out, int32_t* out_n, void* scratch, int64_t scratch_bytes, void* stream_) {
+  if (int e = check_geom(g)) return e;
+  if (!st || !packed || !out_n || !scratch || max_out <= 0 || (reinterpret_cast<uintptr_t>(packed) & 15)) return BSCNAV_EINVAL;
+  if (bscnav_export_scratch_bytes(g) > scratch_bytes) return BSCNAV_EINVAL;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const long long max_rows = (long long)g->max_slots * g->cache;
+  const int n_tiles = (int)((max_rows + kTile - 1) / kTile);
+  int* tile_count = static_cast<int*>(scratch);
+  int* tile_off = reinterpret_cast<int*>(static_cast<char*>(scratch) + align_up((long long)n_tiles * 4, 256));
+  const unsigned long long* rk = reinterpret_cast<const unsigned long long*>(st->row_key);
+  BSC_LAUNCH(k_export_count, n_tiles, kThreads, 0, stream, rk, st->counters, g->cache, ord_lo, ord_hi, tile_count);
+  BSC_LAUNCH(k_export_scan, 1, kThreads, 0, stream, tile_count, tile_off, n_tiles, out_n, max_out);
+  BSC_LAUNCH(k_export_packed, n_tiles, kThreads, 0, stream, rk, st->counters, st->slot_cell, st->tok_h, st->feat, g->cache,
+             g->dim, ord_lo, ord_hi, tile_off, static_cast<char*>(packed), max_out);
+  return BSCNAV_OK;
+}
+
+int64_t bscnav_merge_packed_scratch_bytes(int32_t n_segments, int32_t seg_capacity) {
+  if (n_segments <= 0 || seg_capacity <= 0) return BSCNAV_EINVAL;
+  const long long total = (long long)n_segments * seg_capacity;
+  return scratch_layout(total < (1ll << kSrcBits) ? total : (1ll << kSrcBits), nullptr, nullptr);
+}
+
+int bscnav_merge_packed(const bscnav_geom_t* g, const bscnav_store_t* st, const void* packed, int32_t n_segments,
+                        int32_t seg_capacity, const int32_t* seg_counts, int32_t count_stride, int32_t skip_segment,
+                        void* scratch, int64_t scratch_bytes, void* stream_) {
+  if (int e = check_geom(g)) return e;
+  if (!st || !packed || !seg_counts || !scratch || n_segments <= 0 || seg_capacity <= 0 || count_stride <= 0) return BSCNAV_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(packed) & 15)) return BSCNAV_EINVAL;
+  if (bscnav_merge_packed_scratch_bytes(n_segments, seg_capacity) > scratch_bytes) return BSCNAV_EINVAL;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const long long total = (long long)n_segments * seg_capacity, row_bytes = 16 + 4ll * g->dim;
+  const long long chunk = 1ll << kSrcBits;                    // the record's source-row field
+  for (long long first = 0; first < total; first += chunk) {
+    const int n = (int)(total - first < chunk ? total - first : chunk);
+    FuseScratch s;
+    scratch_layout(n, &s, static_cast<char*>(scratch));
+    BSC_LAUNCH(k_packed_records, (n + kThreads - 1) / kThreads, kThreads, 0, stream, static_cast<const char*>(packed), row_bytes,
+               first, n, seg_capacity, seg_counts, count_stride, skip_segment, s.rec, st->occupied_ids, st->first_touch);
+    const float* rows = reinterpret_cast<const float*>(static_cast<const char*>(packed) + first * row_bytes + 16);
+    if (int e = run_store_update(g, st, s, n, rows, row_bytes / 4, stream)) return e;
+  }
   return BSCNAV_OK;
 }
 

@@ -57,17 +57,59 @@ def gather_deltas(d_cell: torch.Tensor, d_key: torch.Tensor, d_h: torch.Tensor, 
 
 def merge_scene_across_ranks(store, ord_lo: int, ord_hi: int, max_rows: int, group=None):
     """Export the rows this rank produced (ordinals in [ord_lo, ord_hi)), all-gather them, and merge every other rank's
-    rows into the local store.  After the call all ranks hold the same kept-token set for the scene."""
-    rank = dist.get_rank(group)
-    d_cell, d_key, d_h, d_feat, n_dev = store.export_delta(ord_lo, ord_hi, max_rows)
-    n = int(n_dev.item())
-    g_cell, g_key, g_h, g_feat, counts = gather_deltas(d_cell, d_key, d_h, d_feat, n, group)
-    off = 0
-    for r, c in enumerate(counts):
-        if r != rank and c:
-            store.merge_delta(g_cell[off:off + c].contiguous(), g_key[off:off + c].contiguous(), g_h[off:off + c].contiguous(),
-                              g_feat[off:off + c].contiguous())
-        off += c
+    rows into the local store.  After the call all ranks hold the same kept-token set for the scene.
+
+    One packed buffer per rank ({cell, h, key, token row}, SpatialStore.export_packed), ONE all-gather of it over NVLink and
+    one merge launch over the gathered rows (the per-rank counts travel as a second, 8-byte all-gather and are read by the
+    merge kernels on the device).  The only host wait is the read of the maximum count, which sizes the gathered buffer
+    (all-gather needs equal shares; padding to the store's capacity would move a gigabyte per rank)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = store.device
+    packed, n_dev = store.export_packed(ord_lo, ord_hi, max_rows)
+    counts = torch.empty(world * 2, dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(counts, n_dev, group=group)
+    host = counts.view(world, 2).cpu()                       # the one host round trip: sizes the collective
+    if bool((host[:, 1] > max_rows).any()):
+        raise RuntimeError(f"export truncated: a rank produced {int(host[:, 1].max())} rows > max_rows = {max_rows}")
+    cap = max(int(host[:, 0].max()), 1)
+    gathered = torch.empty(world * cap, packed.shape[1], dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(gathered, packed[:cap], group=group)
+    store.merge_packed(gathered, world, cap, counts, count_stride=2, skip_segment=rank)
+    return host[:, 0].tolist()
+
+
+def merge_self_check(group=None, cache: int = 3, bev: bool = False) -> list:
+    """Parity check of the collective path on the ranks of `group` (run by tests/multi_rank_merge.py and once by every
+    `bench.py --gpus N` run, N > 1): a small scene whose frames are sharded over the ranks (shard_frames), fused per rank and
+    merged with merge_scene_across_ranks, must leave EVERY rank with exactly the store a single-process joint build produces
+    (cell set, kept keys, heights and token rows bit for bit).  Raises on any difference; returns the per-rank export counts."""
+    from . import synth
+    from .geometry import PoseChain
+    from .store import SpatialStore, StoreConfig
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    H, W, GS, D = 96, 128, 64, 128
+    n = 4 * world + 1
+    chain = PoseChain([0, 0, -1], [-1, 0, 0], [0, 1, 0], [1, 0, 0, 0, -1, 0, 0, 0, -1], 1.5)
+    frames = [synth.synthetic_frame(f, H, W, n_frames=n + 3) for f in range(n)]
+    depth = torch.from_numpy(np.stack([f[1] for f in frames])).cuda()
+    poses = np.stack([chain(f[2]) for f in frames])
+    tokens = torch.randn(n, 256, D, device="cuda", generator=torch.Generator("cuda").manual_seed(1))   # same on every rank
+    cfg = StoreConfig(height=H, width=W, grid_size=GS, floor_height=-2.0, map_height=2.0, token_dim=D, cache_size=cache, bev=bev,
+                      max_slots=16384)
+    ob = np.arange(n, dtype=np.int64) * H * W
+    joint = SpatialStore(cfg)
+    joint.fuse(depth, poses, tokens, ord_base=ob)
+    mine = list(shard_frames(n, rank, world))
+    st = SpatialStore(cfg)
+    st.fuse(depth[mine].contiguous(), poses[mine], tokens[mine].contiguous(), ord_base=ob[mine])
+    counts = merge_scene_across_ranks(st, int(ob[mine[0]]), int(ob[mine[-1]]) + H * W, st.g.max_slots * cache, group=group)
+
+    def canon(s):
+        return {k: [(float(t[0]), int(t[1]), int(t[2]), t[3].tobytes()) for t in v] for k, v in s.snapshot().items()}
+    got, want = canon(st), canon(joint)
+    if got != want:
+        bad = [k for k in set(got) | set(want) if got.get(k) != want.get(k)]
+        raise RuntimeError(f"rank {rank}: merged store differs from the joint build in {len(bad)} cells (first {sorted(bad)[:3]})")
     return counts
 
 
@@ -93,22 +135,25 @@ def merge_topk(sims: torch.Tensor, pos: torch.Tensor, counts: torch.Tensor, k: i
     cell = (p[..., 0] << 42) | (p[..., 1] << 21) | p[..., 2]               # grid coordinates are < 2^21
     cell = torch.where(valid, cell, torch.full_like(cell, torch.iinfo(torch.int64).max))
     s = torch.where(valid, s, torch.full_like(s, float("-inf")))
-    # order by (similarity desc, cell asc): stable sort by the minor key first
-    o1 = torch.argsort(cell, dim=1, stable=True)
-    s, cell, p, valid = s.gather(1, o1), cell.gather(1, o1), p.gather(1, o1[..., None].expand(-1, -1, 3)), valid.gather(1, o1)
-    o2 = torch.argsort(s, dim=1, descending=True, stable=True)
-    s, cell, p, valid = s.gather(1, o2), cell.gather(1, o2), p.gather(1, o2[..., None].expand(-1, -1, 3)), valid.gather(1, o2)
-    # a cell's first occurrence in this order carries its maximum: drop the later ones
+    # group by cell with the best similarity first: stable sort by similarity (desc), then by cell (asc)
+    def take(o, *ts):
+        return [t.gather(1, o[..., None].expand(-1, -1, 3)) if t.dim() == 3 else t.gather(1, o) for t in ts]
+    s, cell, p, valid = take(torch.argsort(s, dim=1, descending=True, stable=True), s, cell, p, valid)
+    s, cell, p, valid = take(torch.argsort(cell, dim=1, stable=True), s, cell, p, valid)
+    # a cell's first occurrence carries its maximum: later ones are dropped (neighbour comparison, O(R K) memory per query)
+    first = torch.ones_like(valid)
+    first[:, 1:] = cell[:, 1:] != cell[:, :-1]
+    keep = valid & first
+    # final order: similarity desc, ties by cell asc (the entries are in cell order, the sort is stable)
+    s = torch.where(keep, s, torch.full_like(s, float("-inf")))
+    s, p, keep = take(torch.argsort(s, dim=1, descending=True, stable=True), s, p, keep)
     n = R * K
-    dup = (cell[:, :, None] == cell[:, None, :]) & torch.ones(n, n, dtype=torch.bool, device=dev).tril(-1)[None]
-    keep = valid & ~dup.any(dim=2)
-    rank = torch.cumsum(keep, dim=1) - 1
-    out_s = torch.full((Q, k), float("-inf"), dtype=sims.dtype, device=dev)
-    out_p = torch.full((Q, k, 3), -1, dtype=pos.dtype, device=dev)
-    take = keep & (rank < k)
-    qi = torch.arange(Q, device=dev)[:, None].expand(-1, n)[take]
-    out_s[qi, rank[take]] = s[take]
-    out_p[qi, rank[take]] = p[take].to(pos.dtype)
+    if n < k:
+        s = torch.cat([s, torch.full((Q, k - n), float("-inf"), dtype=s.dtype, device=dev)], dim=1)
+        p = torch.cat([p, torch.full((Q, k - n, 3), -1, dtype=p.dtype, device=dev)], dim=1)
+        keep = torch.cat([keep, torch.zeros(Q, k - n, dtype=torch.bool, device=dev)], dim=1)
+    out_s = s[:, :k].contiguous()
+    out_p = torch.where(keep[:, :k, None], p[:, :k], torch.full_like(p[:, :k], -1)).to(pos.dtype)
     return out_s, out_p, torch.clamp(keep.sum(dim=1), max=k).to(counts.dtype)
 
 

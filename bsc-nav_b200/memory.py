@@ -192,50 +192,74 @@ class VoxelTokenMemory:
             idx.append(perm[:: self.depth_sample_rate])
         return torch.from_numpy(np.stack(idx).astype(np.int32)).to(self.device)
 
-    def _staging(self, name, shape, dtype):
-        buf = self._pinned.get(name)
-        if buf is None or buf.shape != tuple(shape) or buf.dtype != dtype:
-            buf = torch.empty(shape, dtype=dtype, pin_memory=True)
-            self._pinned[name] = buf
-        return buf
+    def _staging(self, name, slot, shape, dtype):
+        """Pinned staging buffer `name` of input slot `slot` (two slots, alternating per call).  Before the host writes into
+        it again, the host waits for the H2D copy that last read it (stream-side ordering alone would let a fast caller
+        overwrite pixels the copy engine has not fetched yet)."""
+        n = int(np.prod(shape))
+        ent = self._pinned.get((name, slot))
+        if ent is not None and ent[1] is not None:
+            ent[1].synchronize()
+        if ent is None or ent[0].numel() < n or ent[0].dtype != dtype:
+            ent = [torch.empty(n, dtype=dtype, pin_memory=True), None]
+            self._pinned[(name, slot)] = ent
+        return ent[0][:n].view(*shape), ent
 
     def _inputs_to_device(self, rgb, depth):
         """Host frames -> device through a side copy stream and two device buffers, so the copy of batch i+1 overlaps
-        the kernels of batch i.  Pinned torch tensors are copied directly; numpy arrays go through pinned staging."""
+        the kernels of batch i.  Pinned torch tensors are copied directly (the caller keeps them unchanged until the copy
+        has run, as with any non_blocking copy); numpy arrays go through per-slot pinned staging."""
         if torch.is_tensor(rgb) and rgb.is_cuda and torch.is_tensor(depth) and depth.is_cuda:
             return rgb.contiguous(), depth.contiguous(), None
-        if not torch.is_tensor(rgb):
-            rgb = np.asarray(rgb)
-            st = self._staging("rgb", rgb.shape, torch.uint8)
-            st.numpy()[...] = rgb
-            rgb = st
-        if not torch.is_tensor(depth):
-            depth = np.asarray(depth, dtype=np.float32)
-            st = self._staging("depth", depth.shape, torch.float32)
-            st.numpy()[...] = depth
-            depth = st
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
             self._in_bufs = [None, None]
             self._in_free = [None, None]
             self._in_slot = 0
         slot = self._in_slot = self._in_slot ^ 1
-        bufs = self._in_bufs[slot]
-        if bufs is None or bufs[0].shape != rgb.shape or bufs[1].shape != depth.shape:
-            bufs = self._in_bufs[slot] = (torch.empty(rgb.shape, dtype=torch.uint8, device=self.device),
-                                          torch.empty(depth.shape, dtype=torch.float32, device=self.device))
-            self._in_free[slot] = None
+        staged = []
+        if not torch.is_tensor(rgb):
+            rgb = np.asarray(rgb)
+            view, ent = self._staging("rgb", slot, rgb.shape, torch.uint8)
+            view.numpy()[...] = rgb
+            rgb = view
+            staged.append(ent)
+        if not torch.is_tensor(depth):
+            depth = np.asarray(depth, dtype=np.float32)
+            view, ent = self._staging("depth", slot, depth.shape, torch.float32)
+            view.numpy()[...] = depth
+            depth = view
+            staged.append(ent)
         cur = torch.cuda.current_stream()
+        bufs = self._in_bufs[slot]
+        if bufs is None or bufs[0].numel() < rgb.numel() or bufs[1].numel() < depth.numel():
+            # growing: the kernels that still read the old buffers finish first (they run on other streams than the one the
+            # caching allocator would hand the memory back to); the new memory may be recycled from work queued on `cur`
+            self._wait_events(self._in_free[slot])
+            self._in_free[slot] = None
+            bufs = self._in_bufs[slot] = (torch.empty(rgb.numel(), dtype=torch.uint8, device=self.device),
+                                          torch.empty(depth.numel(), dtype=torch.float32, device=self.device))
+            self._copy_stream.wait_stream(cur)
+        rgb_d = bufs[0][: rgb.numel()].view(rgb.shape)
+        dep_d = bufs[1][: depth.numel()].view(depth.shape)
         if self._in_free[slot] is not None:
             for ev in self._in_free[slot]:
                 self._copy_stream.wait_event(ev)                  # kernels that read this buffer two batches ago are done
         with torch.cuda.stream(self._copy_stream):
-            bufs[0].copy_(rgb, non_blocking=True)
-            bufs[1].copy_(depth, non_blocking=True)
+            rgb_d.copy_(rgb, non_blocking=True)
+            dep_d.copy_(depth, non_blocking=True)
             copied = torch.cuda.Event()
             copied.record(self._copy_stream)
+        for ent in staged:
+            ent[1] = copied
         cur.wait_event(copied)
-        return bufs[0], bufs[1], slot
+        return rgb_d, dep_d, slot
+
+    @staticmethod
+    def _wait_events(events):
+        for ev in events or ():
+            if ev is not None:
+                ev.synchronize()
 
     def fuse_frames(self, rgb, depth, poses, sample_idx=None):
         """Batched build step: rgb (B,H,W,3|4) uint8, depth (B,H,W) float32, poses (B,7) -- pinned host tensors, numpy
@@ -264,14 +288,22 @@ class VoxelTokenMemory:
         buf = self._tok_bufs[k]
         shape = (B, self.n_patch_h * self.n_patch_w, self.token_dim)
         if buf is None or buf.shape[0] < B:
+            self._wait_events([self._tok_free[k]])        # the side-stream scatter still reading the old buffer finishes first
             buf = self._tok_bufs[k] = torch.empty(shape, dtype=torch.float32, device=self.device)
             self._tok_free[k] = None
         if self._tok_free[k] is not None:
             main.wait_event(self._tok_free[k])            # the scatter that read this token buffer two calls ago is done
-        tokens = self._tokens_of(rgb_dev, out=buf[:B]) if isinstance(self.dinov2, ViTEngine) else self._tokens_of(rgb_dev)
+        engine = isinstance(self.dinov2, ViTEngine)
+        tokens = self._tokens_of(rgb_dev, out=buf[:B]) if engine else self._tokens_of(rgb_dev)
         ready = torch.cuda.Event()
         ready.record(main)
         side = self._fuse_stream if os.environ.get("BSCNAV_OVERLAP", "1") != "0" else main     # 0: everything on one stream (A/B)
+        if side is not main:
+            # tensors allocated on the main stream and read on the side stream: the allocator must not recycle them early
+            for t in (depth_dev, sample_idx, rgb_dev if self.colour else None, None if engine else tokens,
+                      tfs if torch.is_tensor(tfs) else None):
+                if torch.is_tensor(t) and t.is_cuda:
+                    t.record_stream(side)
         with torch.cuda.stream(side):
             side.wait_event(ready)
             self._store.fuse(depth_dev, tfs, tokens, sample_idx=sample_idx, ord_base=ord_base,

@@ -95,7 +95,7 @@ class SpatialStore:
         self._ring = [None] * 8
         self._ring_ev = [None] * 8
         self._ring_i = 0
-        self._cnt_ring = torch.zeros(4096, 2, dtype=torch.int32).pin_memory()
+        self._cnt_ring = torch.zeros(4096, 4, dtype=torch.int32).pin_memory()
         self._cnt_i = 0
         self.reset()
 
@@ -184,9 +184,10 @@ class SpatialStore:
         return pd, dev[B * 32:]
 
     def count_async(self):
-        """Enqueue a device->host read of (slots in use, overflow flag) into pinned memory; returns a handle for count_wait."""
+        """Enqueue a device->host read of (slots in use, overflow flag, colour mark, rows committed) into pinned memory;
+        returns a handle for count_wait / rows_committed_wait."""
         i = self._cnt_i = (self._cnt_i + 1) % self._cnt_ring.shape[0]
-        self._cnt_ring[i].copy_(self.counters[:2], non_blocking=True)
+        self._cnt_ring[i].copy_(self.counters[:4], non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
         return i, ev
@@ -198,6 +199,12 @@ class SpatialStore:
         if c[1]:
             raise _lib.BscnavError(f"slot capacity {self.g.max_slots} exceeded (reference: IndexError at memory_2.py:891)")
         return int(c[0])
+
+    def rows_committed_wait(self, handle) -> int:
+        """Token rows copied into the store since the last reset, as of the count_async() that produced `handle`."""
+        i, ev = handle
+        ev.synchronize()
+        return int(self._cnt_ring[i, 3]) & 0xFFFFFFFF
 
     def count(self) -> int:
         """Slots in use (max_id, memory_2.py:894); synchronises.  Raises if a batch overflowed the slot capacity."""
@@ -299,13 +306,40 @@ class SpatialStore:
         d_key = torch.empty(max_out, dtype=torch.int64, device=dev)
         d_h = torch.empty(max_out, dtype=torch.int32, device=dev)
         d_feat = torch.empty(max_out, g.dim, dtype=torch.float32, device=dev)
-        n = torch.zeros(1, dtype=torch.int32, device=dev)
+        n = torch.zeros(2, dtype=torch.int32, device=dev)     # [0] rows written, [1] rows in range (> max_out: truncated)
         nbytes = _lib.check(self.lib.bscnav_export_scratch_bytes(C.byref(g)), "export_scratch_bytes")
         scratch = self._scratch_for(nbytes)
         _lib.check(self.lib.bscnav_export_delta(C.byref(g), C.byref(self.st), ord_lo, ord_hi, _lib.ptr(d_cell), _lib.ptr(d_key),
                                                 _lib.ptr(d_h), _lib.ptr(d_feat), max_out, _lib.ptr(n), _lib.ptr(scratch), nbytes,
                                                 _lib.stream_ptr()), "export_delta")
         return d_cell, d_key, d_h, d_feat, n
+
+    def export_packed(self, ord_lo: int, ord_hi: int, max_out: int, out: torch.Tensor | None = None):
+        """The rows whose ordinal lies in [ord_lo, ord_hi) as ONE packed buffer (max_out, 16 + 4 D) uint8 -- the unit of the
+        all-gather merge -- plus the device counter pair [rows written, rows in range]."""
+        g = self.g
+        rb = _lib.check(self.lib.bscnav_packed_row_bytes(C.byref(g)), "packed_row_bytes")
+        if out is None:
+            out = torch.empty(max_out, rb, dtype=torch.uint8, device=self.device)
+        assert out.is_contiguous() and out.shape[0] >= max_out and out.shape[1] == rb
+        n = torch.zeros(2, dtype=torch.int32, device=self.device)
+        nbytes = _lib.check(self.lib.bscnav_export_scratch_bytes(C.byref(g)), "export_scratch_bytes")
+        scratch = self._scratch_for(nbytes)
+        _lib.check(self.lib.bscnav_export_packed(C.byref(g), C.byref(self.st), ord_lo, ord_hi, _lib.ptr(out), max_out, _lib.ptr(n),
+                                                 _lib.ptr(scratch), nbytes, _lib.stream_ptr()), "export_packed")
+        return out, n
+
+    def merge_packed(self, packed: torch.Tensor, n_segments: int, seg_capacity: int, seg_counts: torch.Tensor, count_stride: int = 2,
+                     skip_segment: int = -1):
+        """Merge a gathered packed buffer (n_segments x seg_capacity rows; segment s holds seg_counts[s * count_stride] valid
+        rows, read on the device) under the store's winner rule; nothing synchronises."""
+        self._shadow_valid = False
+        assert packed.is_contiguous() and seg_counts.dtype == torch.int32 and seg_counts.is_contiguous()
+        nbytes = _lib.check(self.lib.bscnav_merge_packed_scratch_bytes(n_segments, seg_capacity), "merge_packed_scratch_bytes")
+        scratch = self._scratch_for(nbytes)
+        _lib.check(self.lib.bscnav_merge_packed(C.byref(self.g), C.byref(self.st), _lib.ptr(packed), n_segments, seg_capacity,
+                                                _lib.ptr(seg_counts), count_stride, skip_segment, _lib.ptr(scratch), nbytes,
+                                                _lib.stream_ptr()), "merge_packed")
 
     def merge_delta(self, d_cell, d_key, d_h, d_feat):
         self._shadow_valid = False

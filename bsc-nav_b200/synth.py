@@ -27,6 +27,15 @@ def circle_pose(f, n_frames, radius=1.5):
     return np.array([radius * math.cos(psi), 0.0, radius * math.sin(psi), 0.0, math.sin(psi / 2), 0.0, math.cos(psi / 2)])
 
 
+def tour_pose(f, period=1000):
+    """Pose f of a tour that never repeats: yaw advances 2 pi / period per frame, the radius breathes with an incommensurate
+    period.  bench.py cycles a pool of depth/colour images (camera-frame box room) under these poses, so every step touches new
+    cells and new (r^2, ordinal) winners."""
+    psi = 2 * math.pi * f / period
+    radius = 1.5 + 0.9 * math.sin(2 * math.pi * f / (period * 0.6180339887))
+    return np.array([radius * math.cos(psi), 0.0, radius * math.sin(psi), 0.0, math.sin(psi / 2), 0.0, math.cos(psi / 2)])
+
+
 def synthetic_frame(f, h=480, w=640, n_frames=1000, seed_base=0):
     rgb = np.random.default_rng(seed_base + 1000 + f).integers(0, 256, size=(h, w, 4), dtype=np.uint8)
     depth = box_room_depth(h, w, w / 2.0, w / 2.0, w / 2.0, h / 2.0, seed_base + 2000 + f)

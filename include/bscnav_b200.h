@@ -61,7 +61,8 @@ typedef struct {
  *   norm2        float[S*C]     squared L2 norm of the row
  *   feat         float[S*C*D]   token rows                          (feat.h5df 'features', memory_2.py:335-354)
  *   counters     int32[8]       [0] = number of slots in use (max_id, memory_2.py:894), [1] = capacity-overflow flag,
- *                               [2] = slots whose colour is initialised (bscnav_colour_frames)
+ *                               [2] = slots whose colour is initialised (bscnav_colour_frames),
+ *                               [3] = token rows copied into the store since the last reset (bench.py's rows_committed_per_step)
  */
 typedef struct {
   int32_t*  occupied_ids;
@@ -181,11 +182,26 @@ int bscnav_merge_delta(const bscnav_geom_t* g, const bscnav_store_t* st, const i
                        void* stream);
 
 /* Export the rows whose key ordinal lies in [ord_lo, ord_hi) as a compact delta (for the all-gather merge).
- * out_n (device int32) receives the count; at most max_out rows are written. */
+ * out_n (device int32[2]): [0] = rows written (at most max_out), [1] = rows in range; [1] > max_out means the export was
+ * truncated and must not be merged (the caller raises). */
 int64_t bscnav_export_scratch_bytes(const bscnav_geom_t* g);
 int bscnav_export_delta(const bscnav_geom_t* g, const bscnav_store_t* st, uint32_t ord_lo, uint32_t ord_hi,
                         int32_t* d_cell, uint64_t* d_key, int32_t* d_h, float* d_feat, int32_t max_out,
                         int32_t* out_n, void* scratch, int64_t scratch_bytes, void* stream);
+
+/* The same delta as ONE packed buffer, the unit of the all-gather merge (one NCCL all-gather when a scene spans
+ * ranks).  Row layout, bscnav_packed_row_bytes(g) = 16 + 4 D bytes: { int32 cell; int32 h; uint64 key; float feat[D] }.
+ * out_n as in bscnav_export_delta.  bscnav_merge_packed merges a gathered buffer of n_segments x seg_capacity rows (segment s =
+ * rank s's export, of which the first seg_counts[s * count_stride] rows are valid -- the all-gathered out_n arrays, read on the
+ * device: no host round trip) under the store's winner rule in one pass; skip_segment (the caller's own rows; -1: none) is
+ * ignored.  The result does not depend on the number or order of segments. */
+int64_t bscnav_packed_row_bytes(const bscnav_geom_t* g);
+int bscnav_export_packed(const bscnav_geom_t* g, const bscnav_store_t* st, uint32_t ord_lo, uint32_t ord_hi, void* packed,
+                         int32_t max_out, int32_t* out_n, void* scratch, int64_t scratch_bytes, void* stream);
+int64_t bscnav_merge_packed_scratch_bytes(int32_t n_segments, int32_t seg_capacity);
+int bscnav_merge_packed(const bscnav_geom_t* g, const bscnav_store_t* st, const void* packed, int32_t n_segments,
+                        int32_t seg_capacity, const int32_t* seg_counts, int32_t count_stride, int32_t skip_segment,
+                        void* scratch, int64_t scratch_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * ViT feature extractor (replaces dinov2.forward_features, memory_2.py:591-592,732-742). */

@@ -214,15 +214,16 @@ def fuse_records(p: MemoryParams, depth: np.ndarray, pc_transform: np.ndarray, p
     return out
 
 
-def fuse_frame_loop(p: MemoryParams, rgb, depth, pc_transform, patch_tokens, state, perm=None, max_points=None):
+def fuse_frame_loop(p: MemoryParams, rgb, depth, pc_transform, patch_tokens, state, perm=None, max_points=None, stride=1):
     """Literal per-point restatement of the loop in obs2voxeltoken (memory_2.py:863-903) -- python loop, small cases
     and CPU-baseline timing only.  `state` is an OracleMemory; tokens are appended to state.pending (the 50 000-row
-    host buffer of the reference without its flush-drop quirk, harness rule SURVEY 8c).  Returns points visited."""
+    host buffer of the reference without its flush-drop quirk, harness rule SURVEY 8c).  Returns points visited.
+    `stride` > 1 visits every stride-th point of the visiting order (bounded, image-wide sample for CPU-baseline timing)."""
     rgb = np.array(rgb[:, :, :3])                                  # memory_2.py:853
     pc, pix = backproject_depth(depth, p.calib_mat, p.min_depth, p.max_depth, p.depth_sample_rate, perm)
     pc_global = transform_pc(pc, pc_transform)
     n = 0
-    for i, (pt, p_local) in enumerate(zip(pc_global.T, pc.T)):
+    for i, (pt, p_local) in enumerate(zip(pc_global.T[::stride], pc.T[::stride])):
         if max_points is not None and i >= max_points:
             break
         n += 1
@@ -308,6 +309,40 @@ class OracleMemory:
         """key -> list of the C best (r2f, ordinal, payload, h), best first."""
         C = self.p.cache_size
         return {k: sorted(v, key=lambda t: (t[0], t[1]))[:C] for k, v in self.tokens.items()}
+
+
+def kept_vectorised(p: MemoryParams, frames: list) -> dict:
+    """The same result as OracleMemory.fuse_frame(...) over `frames` followed by kept(), without the per-point Python loop
+    (full-size parity tests: 32 frames x 307 200 points).  `frames` = [(frame_id, fuse_records(...) dict)], dense raster order
+    (ordinal = frame_id * H*W + pix, memory_port.OracleMemory.fuse_frame).  Store rule as in the module docstring: per cell the C
+    smallest (float32 r^2, ordinal).  Returns {cell key: [(r2f, ordinal, (frame_id, ppy, ppx), h), ...] best first}
+    (tests/test_oracle_golden.py pins it against OracleMemory on small cases)."""
+    hw = p.height * p.width
+    cell, key, fid, ppy, ppx, hh = [], [], [], [], [], []
+    for frame_id, rec in frames:
+        c = rec["row"] * p.gs + rec["col"]
+        cell.append(c if p.bev else c * p.levels + rec["h"])
+        ordinal = np.uint64(frame_id * hw) + rec["pix"].astype(np.uint64)
+        key.append((rec["r2f"].view(np.uint32).astype(np.uint64) << np.uint64(32)) | ordinal)
+        fid.append(np.full(len(rec["pix"]), frame_id, dtype=np.int64))
+        ppy.append(rec["ppy"]); ppx.append(rec["ppx"]); hh.append(rec["h"])
+    cell, key, fid, ppy, ppx, hh = (np.concatenate(a) for a in (cell, key, fid, ppy, ppx, hh))
+    order = np.lexsort((key, cell))
+    cs = cell[order]
+    start = np.flatnonzero(np.concatenate(([True], cs[1:] != cs[:-1])))
+    rank = np.arange(len(cs)) - np.repeat(start, np.diff(np.concatenate((start, [len(cs)]))))
+    sel = order[rank < p.cache_size]
+    out = {}
+    for i in sel:
+        c = int(cell[i])
+        if p.bev:
+            k = (c // p.gs, c % p.gs)
+        else:
+            rc = c // p.levels
+            k = (rc // p.gs, rc % p.gs, c % p.levels)
+        r2f = np.array([int(key[i]) >> 32], dtype=np.uint32).view(np.float32)[0]
+        out.setdefault(k, []).append((r2f, int(key[i]) & 0xFFFFFFFF, (int(fid[i]), int(ppy[i]), int(ppx[i])), int(hh[i])))
+    return out
 
 
 def cosine_similarity(q: np.ndarray, feats: np.ndarray, eps=1e-8) -> np.ndarray:

@@ -10,7 +10,6 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import memory_port as mp  # noqa: E402
 
 
 def main():
@@ -19,23 +18,10 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = importlib.import_module("bsc-nav_b200")
     dmod = importlib.import_module("bsc-nav_b200.dist")
-    H, W, GS, D, n = 96, 128, 64, 128, 9
-    chain = pkg.PoseChain([0, 0, -1], [-1, 0, 0], [0, 1, 0], [1, 0, 0, 0, -1, 0, 0, 0, -1], 1.5)
-    frames = [mp.synthetic_frame(f, H, W, n_frames=12) for f in range(n)]
-    depth = torch.from_numpy(np.stack([f[1] for f in frames])).cuda()
-    poses = np.stack([chain(f[2]) for f in frames])
-    tokens = torch.randn(n, 256, D, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
-    cfg = pkg.StoreConfig(height=H, width=W, grid_size=GS, floor_height=-2.0, map_height=2.0, token_dim=D, cache_size=3, bev=False,
-                          max_slots=16384)
-    ob = np.arange(n, dtype=np.int64) * H * W
-    joint = pkg.SpatialStore(cfg)
-    joint.fuse(depth, poses, tokens, ord_base=ob)
-    mine = list(dmod.shard_frames(n, rank, world))
-    st = pkg.SpatialStore(cfg)
-    st.fuse(depth[mine].contiguous(), poses[mine], tokens[mine].contiguous(), ord_base=ob[mine])
-    counts = dmod.merge_scene_across_ranks(st, int(ob[mine[0]]), int(ob[mine[-1]]) + H * W, st.g.max_slots * 3)   # capacity of the export buffers, rows
-    canon = lambda s: {k: [(float(t[0]), int(t[1]), int(t[2]), t[3].tobytes()) for t in v] for k, v in s.snapshot().items()}
-    assert canon(st) == canon(joint), f"rank {rank}: merged store differs from the joint build"
+    H, W, GS, D = 96, 128, 64, 128
+    counts = dmod.merge_self_check()                                   # sharded build + packed all-gather merge == joint build
+    for cache, bev in ((1, True), (10, False)):
+        dmod.merge_self_check(cache=cache, bev=bev)
     # queries over a scene whose grid rows are spread over the ranks: local top-K + one all-gather + K-way merge
     # equals the query over one store holding every cell
     qcfg = pkg.StoreConfig(height=H, width=W, grid_size=GS, floor_height=-2.0, map_height=2.0, token_dim=D, cache_size=2, bev=False,

@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
-    assert lib.bscnav_abi_version() == 2
+    assert lib.bscnav_abi_version() == 3
 
 
 def test_struct_sizes_match_header():

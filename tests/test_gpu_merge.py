@@ -56,7 +56,7 @@ def test_merge_equals_joint_build(pkg, cache, bev):
     deltas = []
     for s, sh in zip(stores, shards):
         d_cell, d_key, d_h, d_feat, n_dev = s.export_delta(int(ob[sh[0]]), int(ob[sh[-1]]) + H * W, max_out=s.g.max_slots * cache)
-        k = int(n_dev.item())
+        k = int(n_dev[0].item())
         assert k == sum(len(v) for v in s.snapshot().values())
         deltas.append((d_cell[:k].contiguous(), d_key[:k].contiguous(), d_h[:k].contiguous(), d_feat[:k].contiguous()))
     stores[0].merge_delta(*deltas[1])
@@ -71,6 +71,49 @@ def test_merge_equals_joint_build(pkg, cache, bev):
     assert got0 == want, _diff(got0, want)
 
 
+@pytest.mark.parametrize("cache,bev,n_shards", [(1, True, 2), (3, False, 3), (1, False, 4)])
+def test_packed_merge_equals_joint_build(pkg, cache, bev, n_shards):
+    """The all-gather form: every shard exports ONE packed buffer, the buffers are laid side by side padded to the largest
+    count (what all_gather_into_tensor produces), one merge_packed launch per store with its own segment skipped."""
+    n = 9
+    depth, poses, tokens = _inputs(pkg, n)
+    cfg = pkg.StoreConfig(height=H, width=W, grid_size=GS, floor_height=-2.0, map_height=2.0, token_dim=D, cache_size=cache, bev=bev)
+    ob = np.arange(n, dtype=np.int64) * H * W
+    joint = pkg.SpatialStore(cfg)
+    joint.fuse(depth, poses, tokens, ord_base=ob)
+    dmod = importlib.import_module("bsc-nav_b200.dist")
+    shards = [list(dmod.shard_frames(n, r, n_shards)) for r in range(n_shards)]
+    stores, packed, counts = [], [], []
+    for idx in shards:
+        s = pkg.SpatialStore(cfg)
+        s.fuse(depth[idx].contiguous(), poses[idx], tokens[idx].contiguous(), ord_base=ob[idx])
+        buf, n_dev = s.export_packed(int(ob[idx[0]]), int(ob[idx[-1]]) + H * W, max_out=s.g.max_slots * cache)
+        assert int(n_dev[0]) == int(n_dev[1]) == sum(len(v) for v in s.snapshot().values())
+        stores.append(s); packed.append(buf); counts.append(n_dev)
+    cap = max(int(c[0]) for c in counts)
+    gathered = torch.cat([b[:cap] for b in packed]).contiguous()
+    seg_counts = torch.cat(counts).contiguous()
+    want = _canon(joint)
+    for r, s in enumerate(stores):
+        s.merge_packed(gathered, n_shards, cap, seg_counts, count_stride=2, skip_segment=r)
+        got = _canon(s)
+        assert got == want, _diff(got, want)
+    stores[0].merge_packed(gathered, n_shards, cap, seg_counts, count_stride=2, skip_segment=-1)     # idempotent, own rows included
+    assert _canon(stores[0]) == want
+
+
+def test_export_reports_truncation(pkg):
+    depth, poses, tokens = _inputs(pkg, 2)
+    cfg = pkg.StoreConfig(height=H, width=W, grid_size=GS, floor_height=-2.0, map_height=2.0, token_dim=D, cache_size=1, bev=True)
+    s = pkg.SpatialStore(cfg)
+    s.fuse(depth, poses, tokens)
+    total = s.count()
+    _, n_dev = s.export_packed(0, 2 ** 32 - 1, max_out=10)
+    assert n_dev.tolist() == [10, total]
+    *_, n_dev = s.export_delta(0, 2 ** 32 - 1, max_out=10)
+    assert n_dev.tolist() == [10, total]
+
+
 def test_query_after_merge_matches_joint(pkg):
     n = 6
     depth, poses, tokens = _inputs(pkg, n)
@@ -82,7 +125,7 @@ def test_query_after_merge_matches_joint(pkg):
     a.fuse(depth[:3].contiguous(), poses[:3], tokens[:3].contiguous(), ord_base=ob[:3])
     b.fuse(depth[3:].contiguous(), poses[3:], tokens[3:].contiguous(), ord_base=ob[3:])
     d_cell, d_key, d_h, d_feat, n_dev = b.export_delta(int(ob[3]), int(ob[-1]) + H * W, max_out=b.g.max_slots * 2)
-    k = int(n_dev.item())
+    k = int(n_dev[0].item())
     a.merge_delta(d_cell[:k].contiguous(), d_key[:k].contiguous(), d_h[:k].contiguous(), d_feat[:k].contiguous())
     q = tokens[2, 77:79].contiguous()
     s1, p1, c1 = joint.query(q, k=50)

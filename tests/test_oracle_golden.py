@@ -163,3 +163,21 @@ def test_port_matches_reference_live_random(seed):
     np.testing.assert_allclose(sim, g["topk_sim"], rtol=0, atol=2e-7)
     cut = g["topk_sim"][-1] + 1e-6
     assert {tuple(r) for r, s in zip(g["topk_pos"], g["topk_sim"]) if s > cut} <= {tuple(r) for r in pos}
+
+
+@pytest.mark.parametrize("bev,C", [(True, 1), (False, 1), (False, 3), (True, 2)])
+def test_kept_vectorised_equals_oracle_memory(golden, bev, C):
+    """kept_vectorised (full-size GPU parity tests) == OracleMemory.fuse_frame + kept() on the two-pose fixture's inputs."""
+    ci = mg.case_inputs("two_pose")
+    a = ci["args"]
+    p = mp.MemoryParams(height=a["height"], width=a["width"], grid_size=a["grid_size"], floor_height=a.get("floor_height", -10.0),
+                        map_height=a.get("map_height", 10.0), depth_sample_rate=1, token_dim=8, cache_size=C, bev=bev)
+    om = mp.OracleMemory(p)
+    inv0, frames = None, []
+    for f, (rgb, depth, pose) in enumerate(ci["frames"]):
+        T, inv0 = mp.pose_chain(p, pose, inv0)
+        frames.append((f, om.fuse_frame(rgb, depth, T, None, frame_id=f, colour=False)))
+    want, got = om.kept(), mp.kept_vectorised(p, frames)
+    assert set(want) == set(got)
+    for k, items in want.items():
+        assert [(t[0], t[1], t[2], t[3]) for t in items] == got[k]

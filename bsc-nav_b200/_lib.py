@@ -96,6 +96,7 @@ _SIGS = {
     "bscnav_text_encode": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P, _P]),
     "bscnav_gaussian_pool": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "bscnav_attention_f16": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "bscnav_debug_attention_ws2": (C.c_int, [C.c_int32, _P]),
     "bscnav_gemm_f16": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
 }
 EXPORTS = tuple(_SIGS)

@@ -259,6 +259,14 @@ extern "C" int bscnav_attention_f16(const void* qkv, void* out, int32_t batch, i
   if (!qkv || !out || batch <= 0 || T <= 0 || heads <= 0) return BSCNAV_EINVAL;
   if (impl == 0) return attention_f16(static_cast<const __half*>(qkv), static_cast<__half*>(out), batch, T, heads, 64, false, (cudaStream_t)stream);
   CUtensorMap m128, m16;
+  if (impl == 3) {
+    CUtensorMap mo;
+    if (int e = make_qkv_map3d(&m128, qkv, batch, T, 3LL * heads * 64, 128)) return e;
+    if (int e = make_qkv_map3d(&m16, qkv, batch, T, 3LL * heads * 64, 16)) return e;
+    if (int e = make_out_map3d(&mo, out, batch, T, 1LL * heads * 64)) return e;
+    return attention_ws2_launch(&m128, &m16, &mo, static_cast<const __half*>(qkv), static_cast<__half*>(out), batch, T, heads,
+                                (cudaStream_t)stream);
+  }
   if (impl == 2) {
     if (int e = make_qkv_map3d(&m128, qkv, batch, T, 3LL * heads * 64, 128)) return e;
     if (int e = make_qkv_map3d(&m16, qkv, batch, T, 3LL * heads * 64, 16)) return e;

@@ -341,6 +341,23 @@ int make_qkv_map3d(CUtensorMap* map, const void* ptr, long long batch, long long
   return BSCNAV_OK;
 }
 
+// attention output [batch, T, width] fp16 as a 3-D store map {column, token, frame} with box {64, 32, 1}: rows past a frame's last
+// token are clipped by the hardware (attention_ws2.cu stores whole 32-row boxes)
+int make_out_map3d(CUtensorMap* map, const void* ptr, long long batch, long long T, long long width) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { snprintf(g_last_error, sizeof(g_last_error), "cuTensorMapEncodeTiled entry point not found"); return BSCNAV_ECUDA; }
+  if (!ptr || batch <= 0 || T <= 0 || width <= 0 || width % BK != 0 || (reinterpret_cast<uintptr_t>(ptr) & 15)) return BSCNAV_EINVAL;
+  cuuint64_t dims[3] = {(cuuint64_t)width, (cuuint64_t)T, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)width * 2, (cuuint64_t)T * width * 2};
+  cuuint32_t box[3] = {(cuuint32_t)BK, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(g_last_error, sizeof(g_last_error), "cuTensorMapEncodeTiled(out 3d) failed: %d", (int)r); return BSCNAV_ECUDA; }
+  return BSCNAV_OK;
+}
+
 // output tensor [rows, N] -> map with a 32-row x 128-byte box (64 fp16 or 32 fp32 columns), 128-byte swizzle
 int make_store_map(CUtensorMap* map, const void* ptr, long long rows, long long N, bool is_float) {
   EncodeTiledFn fn = encode_fn();

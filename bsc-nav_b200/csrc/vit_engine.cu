@@ -101,7 +101,8 @@ struct VitEngine {
   CUtensorMap out_qkv, out_h, out_x;                 // store maps of the GEMM outputs
   CUtensorMap qkv128, qkv16;                         // qkv tensor as attention operand (128- and 16-row boxes)
   CUtensorMap qkv3d128, qkv3d16;                     // the same tensor as {column, token, frame} (attention_ws.cu)
-  int attn_impl = 0;                                 // 0 mma.sync, 1 tcgen05 v1, 2 tcgen05 warp-specialised
+  CUtensorMap ao3d;                                  // attention output as a 3-D store map (attention_ws2.cu)
+  int attn_impl = 0;                                 // 0 mma.sync, 1 tcgen05 v1, 2 tcgen05 warp-specialised, 3 second generation
   CUtensorMap map_qkv[64], map_proj[64], map_fc1[64], map_fc2[64];
   CUtensorMap half_qkv[64], half_proj[64], half_fc1[64], half_fc2[64];   // 128-row boxes of the same weights (cluster multicast)
   bool has_half[4] = {false, false, false, false};
@@ -168,7 +169,9 @@ static int run_layers(VitEngine* e, int batch, cudaStream_t stream) {
     { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * 3.0 * D * D);
       if (int r = gemm_f16_launch(&e->map_y, &e->map_qkv[i], &e->out_qkv, rows, 3 * D, D, e1, stream, e->has_half[0] ? &e->half_qkv[i] : nullptr)) return r; }
     { ProfScope ps(e, stream, kCatAttention, 4.0 * batch * (double)T * T * D);
-      if (e->attn_impl == 2) {
+      if (e->attn_impl == 3) {
+        if (int r = attention_ws2_launch(&e->qkv3d128, &e->qkv3d16, &e->ao3d, e->ws.qkv, e->ws.ao, batch, T, c.heads, stream)) return r;
+      } else if (e->attn_impl == 2) {
         // the 3-D map's frame extent is the engine's max_batch: frames >= batch are simply never addressed
         if (int r = attention_ws_launch(&e->qkv3d128, &e->qkv3d16, e->ws.ao, batch, T, c.heads, stream)) return r;
       } else if (e->attn_impl == 1) { if (int r = attention_tc_launch(&e->qkv128, &e->qkv16, e->ws.ao, batch, T, c.heads, stream)) return r; }
@@ -239,12 +242,14 @@ int bscnav_vit_create(const bscnav_vit_cfg_t* c, const void* w_half, const float
   // default: the warp-specialised tcgen05 kernel (70.6 us vs 82.0 us for mma.sync at 55 frames x 16 heads, T = 257);
   // BSCNAV_ATTENTION=0|1|2 selects mma.sync / tcgen05 v1 / tcgen05 warp-specialised (tests exercise all three)
   const char* impl_env = getenv("BSCNAV_ATTENTION");
-  e->attn_impl = impl_env ? atoi(impl_env) : 2;
+  e->attn_impl = impl_env ? atoi(impl_env) : 3;
   if ((c->head_dim && c->head_dim != 64) || text) e->attn_impl = 0;  // the tcgen05 kernels: head dim 64, no causal mask
+  if (e->attn_impl == 3 && !attention_ws2_supported(e->T)) e->attn_impl = 2;
   if (e->attn_impl == 2 && !attention_ws_supported(e->T)) e->attn_impl = 0;
   if (e->attn_impl == 1 && !attention_tc_supported(e->T)) e->attn_impl = 0;
   r = r ? r : make_qkv_map3d(&e->qkv3d128, e->ws.qkv, max_batch, e->T, 3 * D, 128);
   r = r ? r : make_qkv_map3d(&e->qkv3d16, e->ws.qkv, max_batch, e->T, 3 * D, 16);
+  r = r ? r : make_out_map3d(&e->ao3d, e->ws.ao, max_batch, e->T, D);
   r = r ? r : make_operand_map(&e->qkv128, e->ws.qkv, rows, 3 * D, 128);
   r = r ? r : make_operand_map(&e->qkv16, e->ws.qkv, rows, 3 * D, 16);
   r = r ? r : make_store_map(&e->out_qkv, e->ws.qkv, rows, 3 * D, false);

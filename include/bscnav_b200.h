@@ -273,12 +273,18 @@ int bscnav_gemm_f16(const void* a, const void* w, const float* bias, void* out, 
                     int32_t out_mode, int32_t act, void* stream);
 
 /* Stand-alone attention entry (tests/bench): qkv fp16 [batch*T, 3*heads*64] (q pre-scaled by 1/sqrt(64)) ->
- * out fp16 [batch*T, heads*64].  impl 0: mma.sync kernel (any T); impl 1: tcgen05 kernel (T <= 272). */
+ * out fp16 [batch*T, heads*64].  impl 0: mma.sync kernel (any T); impl 1 / 2: first tcgen05 kernels; impl 3: the engine's default
+ * (P in TMEM, SIMT tail rows, TMA-store epilogue; 17 <= T <= 272). */
 int bscnav_attention_f16(const void* qkv, void* out, int32_t batch, int32_t T, int32_t heads, int32_t impl, void* stream);
 /* The mma.sync kernel with an explicit head dim (64 | 80) and optional causal mask (keys <= query row; head dim 64):
  * qkv fp16 [batch*T, 3*heads*head_dim], q pre-scaled. */
 int bscnav_attention_f16_hd(const void* qkv, void* out, int32_t batch, int32_t T, int32_t heads, int32_t head_dim, int32_t causal,
                             void* stream);
+
+/* Profiling hook of the default attention kernel (csrc/attention_ws2.cu): `flags` switch single stages off for timing
+ * experiments (results are then wrong; 0 restores the product behaviour), `stamps` (device int64[512] or NULL) receives clock64
+ * stamps of the first CTA's first 32 tiles.  Process-wide; not used by the product path. */
+int bscnav_debug_attention_ws2(int32_t flags, void* stamps);
 
 /* Number of kernels launched by this library since load (bench.py's gpu_launches). */
 int64_t bscnav_launch_count(void);

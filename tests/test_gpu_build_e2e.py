@@ -141,7 +141,7 @@ def test_numpy_tight_loop_equals_device_path(pkg):
     rgb, depth, poses = (np.stack([f[i] for f in frames]) for i in range(3))
     out = []
     for mode in ("numpy", "device"):
-        mem = pkg.VoxelTokenMemory(args, preload_dino=eng, need_diffusion=False, cache_size=1, max_batch=bsz)
+        mem = pkg.VoxelTokenMemory(args, preload_dino=eng, need_diffusion=False, cache_size=1, max_batch=bsz, max_slots=65536)
         if mode == "numpy":
             a = torch.randn(8192, 8192, device="cuda")
             for _ in range(30):

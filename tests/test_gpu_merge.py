@@ -77,7 +77,8 @@ def test_packed_merge_equals_joint_build(pkg, cache, bev, n_shards):
     count (what all_gather_into_tensor produces), one merge_packed launch per store with its own segment skipped."""
     n = 9
     depth, poses, tokens = _inputs(pkg, n)
-    cfg = pkg.StoreConfig(height=H, width=W, grid_size=GS, floor_height=-2.0, map_height=2.0, token_dim=D, cache_size=cache, bev=bev)
+    cfg = pkg.StoreConfig(height=H, width=W, grid_size=GS, floor_height=-2.0, map_height=2.0, token_dim=D, cache_size=cache, bev=bev,
+                          max_slots=16384)
     ob = np.arange(n, dtype=np.int64) * H * W
     joint = pkg.SpatialStore(cfg)
     joint.fuse(depth, poses, tokens, ord_base=ob)

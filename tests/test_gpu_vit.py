@@ -91,8 +91,9 @@ def test_gaussian_pool(pkg):
     torch.testing.assert_close(got, vit_ref.gaussian_pool(t), rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("T,heads,batch", [(257, 16, 3), (261, 16, 2), (50, 12, 4), (128, 2, 2), (272, 4, 2), (200, 3, 1), (17, 1, 1)])
-@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("T,heads,batch", [(257, 16, 3), (261, 16, 2), (50, 12, 4), (128, 2, 2), (272, 4, 2), (200, 3, 1), (17, 1, 1),
+                                           (129, 2, 2), (144, 3, 2), (145, 2, 1), (256, 2, 1)])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3])
 def test_attention_kernels(pkg, T, heads, batch, impl):
     g = torch.Generator("cuda").manual_seed(T + heads)
     D = heads * 64
@@ -110,9 +111,15 @@ def test_attention_ws_many_items_matches_mma(pkg):
     g = torch.Generator("cuda").manual_seed(9)
     qkv = (torch.randn(B * T, 3 * heads * 64, device="cuda", generator=g) * 0.8).half()
     a = pkg.attention_f16(qkv, B, T, heads, impl=0).float()
-    for _ in range(3):
-        b = pkg.attention_f16(qkv, B, T, heads, impl=2).float()
+    for impl in (2, 3, 3, 3):
+        b = pkg.attention_f16(qkv, B, T, heads, impl=impl).float()
         torch.testing.assert_close(b, a, rtol=2e-3, atol=2e-3)
+    # DINOv2-reg length (5 tail rows shared by the two tail warps), several waves
+    T = 261
+    qkv = (torch.randn(B * T, 3 * heads * 64, device="cuda", generator=g) * 0.8).half()
+    a = pkg.attention_f16(qkv, B, T, heads, impl=0).float()
+    for _ in range(2):
+        torch.testing.assert_close(pkg.attention_f16(qkv, B, T, heads, impl=3).float(), a, rtol=2e-3, atol=2e-3)
 
 
 # ---- the agent's view-check encoder: open_clip ViT-H/14 image tower, heads of dimension 80 (BSCAgent.py:309, 700-731)

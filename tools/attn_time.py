@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 pkg = importlib.import_module("bsc-nav_b200")
 B = int(os.environ.get("B", 64)); T = int(os.environ.get("T", 257)); H = 16
 qkv = (torch.randn(B * T, 3 * H * 64, device="cuda") * 0.8).half()
-for impl in [int(x) for x in os.environ.get("IMPLS", "0,1").split(",")]:
+for impl in [int(x) for x in os.environ.get("IMPLS", "0,2,3").split(",")]:
     for _ in range(3): pkg.attention_f16(qkv, B, T, H, impl=impl)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -46,7 +46,8 @@ class Filter(C.Structure):
 class VitCfg(C.Structure):
     _fields_ = [("image", C.c_int32), ("patch", C.c_int32), ("dim", C.c_int32), ("depth", C.c_int32), ("heads", C.c_int32),
                 ("mlp", C.c_int32), ("n_reg", C.c_int32), ("act", C.c_int32), ("ln_pre", C.c_int32),
-                ("patch_k_pad", C.c_int32), ("ln_eps", C.c_float), ("head_dim", C.c_int32), ("text_context", C.c_int32)]
+                ("patch_k_pad", C.c_int32), ("ln_eps", C.c_float), ("head_dim", C.c_int32), ("text_context", C.c_int32),
+                ("precision", C.c_int32)]
 
 
 _P = C.c_void_p
@@ -86,6 +87,7 @@ _SIGS = {
     "bscnav_vit_workspace_bytes": (C.c_int64, [C.POINTER(VitCfg), C.c_int32]),
     "bscnav_vit_create": (C.c_int, [C.POINTER(VitCfg), _P, _P, _P, C.c_int64, C.c_int32, C.POINTER(_P)]),
     "bscnav_vit_destroy": (None, [_P]),
+    "bscnav_vit_range_status": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), _P]),
     "bscnav_vit_profile": (C.c_int, [_P, C.c_int32]),
     "bscnav_vit_profile_read": (C.c_int, [_P, _P, _P, _P]),
     "bscnav_vit_forward_frames": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
@@ -96,6 +98,7 @@ _SIGS = {
     "bscnav_text_encode": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P, _P]),
     "bscnav_gaussian_pool": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "bscnav_attention_f16": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "bscnav_gemm_bf16x3": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "bscnav_debug_attention_ws2": (C.c_int, [C.c_int32, _P]),
     "bscnav_gemm_f16": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
 }

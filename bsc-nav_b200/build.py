@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbscnav_b200.so")
-SOURCES = ("memory_kernels.cu", "query_batch.cu", "cluster.cu", "colour.cu", "gemm_tcgen05.cu", "attention_tc.cu", "attention_ws.cu", "attention_ws2.cu", "vit_kernels.cu", "vit_engine.cu")
+SOURCES = ("memory_kernels.cu", "query_batch.cu", "cluster.cu", "colour.cu", "gemm_tcgen05.cu", "attention_tc.cu", "attention_ws.cu", "attention_ws2.cu", "vit_kernels.cu", "wide_kernels.cu", "vit_engine.cu")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr"]
 

@@ -1,6 +1,7 @@
 // tcgen05 / TMEM / TMA GEMM for sm_100a -- see gemm_tcgen05.cuh for the design.
 #include <cstdlib>
 #include "gemm_tcgen05.cuh"
+#include <cuda_bf16.h>
 #include "tc_ptx.cuh"
 
 namespace bscnav {
@@ -58,7 +59,7 @@ template <int ACT> __device__ __forceinline__ float act_fn(float v) {
 template <int BN, int MODE, int ACT, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-           const __grid_constant__ CUtensorMap map_out, int M, int N, int K, const GemmEpilogue epi) {
+           const __grid_constant__ CUtensorMap map_out, int M, int N, int K, const GemmEpilogue epi, int split) {
   using C = Cfg<BN, CL>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -71,7 +72,8 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
   const uint32_t smem_base = smem_u32(smem);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tiles = (M + BM - 1) / BM, n_tiles = N / BN, k_blocks = K / BK;
+  const int kbk = K / BK;                                   // k-blocks of one pass; split: three passes (hi hi, lo hi, hi lo)
+  const int m_tiles = (M + BM - 1) / BM, n_tiles = N / BN, k_blocks = split ? 3 * kbk : kbk;
   const int m_groups = (m_tiles + CL - 1) / CL;             // CL == 2: pairs of row blocks (the last pair may be half empty)
   const int total_tiles = m_groups * n_tiles;
   const int rank = CL == 2 ? (int)cluster_ctarank() : 0;
@@ -118,16 +120,19 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);       // CL == 2: released by the leader's commit in both CTAs
           const uint32_t a_dst = smem_base + stage * C::kStageBytes;
           const uint32_t b_dst = a_dst + C::kABytes;
+          // split operands: pass 0 a_hi w_hi, pass 1 a_lo w_hi, pass 2 a_hi w_lo (lo halves start at column K)
+          const int pass = split ? kb / kbk : 0, kj = split ? kb - pass * kbk : kb;
+          const int a_col = kj * BK + (pass == 1 ? K : 0), w_col = kj * BK + (pass == 2 ? K : 0);
           if (CL == 2) {
             // bytes of both CTAs complete on the leader's barrier; the leader expects the pair's total
             const uint32_t full_leader = mapa_shared(full_bar + 8 * stage, 0);
             if (rank == 0) mbar_arrive_expect_tx(full_bar + 8 * stage, 2 * C::kStageBytes);
-            tma_load_2d_2sm(a_dst, &map_a, full_leader, kb * BK, m_blk * BM);              // rows past M arrive as zeros
-            tma_load_2d_2sm(b_dst, &map_w, full_leader, kb * BK, n_blk * BN + rank * (BN / 2));   // map_w: BN/2-row box
+            tma_load_2d_2sm(a_dst, &map_a, full_leader, a_col, m_blk * BM);                // rows past M arrive as zeros
+            tma_load_2d_2sm(b_dst, &map_w, full_leader, w_col, n_blk * BN + rank * (BN / 2));   // map_w: BN/2-row box
           } else {
             mbar_arrive_expect_tx(full_bar + 8 * stage, C::kStageBytes);
-            tma_load_2d(a_dst, &map_a, full_bar + 8 * stage, kb * BK, m_blk * BM);
-            tma_load_2d(b_dst, &map_w, full_bar + 8 * stage, kb * BK, n_blk * BN);
+            tma_load_2d(a_dst, &map_a, full_bar + 8 * stage, a_col, m_blk * BM);
+            tma_load_2d(b_dst, &map_w, full_bar + 8 * stage, w_col, n_blk * BN);
           }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
@@ -136,7 +141,7 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer (one thread; CL == 2: of the leader CTA)
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BN, CL == 2 ? 256 : 128);
+      const uint32_t idesc = umma_idesc_f16(BN, CL == 2 ? 256 : 128) | (split ? kUmmaBf16Operands : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -175,6 +180,7 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     // MODE is a template parameter and the column loop is not unrolled: the epilogue stays small enough for the
     // instruction cache (an unrolled multi-mode body spent a quarter of its samples in stall_no_inst).
     constexpr bool kHalfOut = MODE == kOutHalf || MODE == kOutHalfAct;
+    constexpr bool kActMode = MODE == kOutHalfAct || MODE == kOutSplitAct;
     constexpr bool kViaTma = kHalfOut || MODE == kOutResidual;
     constexpr int kCols = BN / 2;                        // columns handled by one warp
     constexpr int kIter = kHalfOut ? 64 : 32;            // columns per iteration == one 128-byte TMA box row
@@ -186,6 +192,7 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     const int sw = lane & 7;
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t range_chk = 0;        // fp16 outputs: bit 15 of a half-word is set when its exponent field is all ones (inf / nan)
     for (int tile = tile0; tile < total_tiles; tile += tile_step) {
       const int m_blk = (n_fastest ? tile / n_tiles : tile % m_groups) * CL + rank, n_blk = n_fastest ? tile % n_tiles : tile / m_groups;
       const int m0 = m_blk * BM + quarter * 32;
@@ -244,14 +251,38 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
             for (int j = 0; j < 4; ++j) {
               __half2 h0 = __floats2half2_rn(v[8 * j + 0], v[8 * j + 1]), h1 = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
               __half2 h2 = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]), h3 = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
-              sts128(row_base + (((u * 4 + j) ^ sw) << 4), *reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                     *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+              const uint32_t u0 = *reinterpret_cast<uint32_t*>(&h0), u1 = *reinterpret_cast<uint32_t*>(&h1);
+              const uint32_t u2 = *reinterpret_cast<uint32_t*>(&h2), u3 = *reinterpret_cast<uint32_t*>(&h3);
+              if (in_m)      // (h & 0x7fff) + 0x0400 carries into bit 15 exactly when the exponent field is 0x1f
+                range_chk |= (((u0 & 0x7FFF7FFFu) + 0x04000400u) | ((u1 & 0x7FFF7FFFu) + 0x04000400u)) |
+                             (((u2 & 0x7FFF7FFFu) + 0x04000400u) | ((u3 & 0x7FFF7FFFu) + 0x04000400u));
+              sts128(row_base + (((u * 4 + j) ^ sw) << 4), u0, u1, u2, u3);
             }
           } else if (MODE == kOutResidual) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               sts128(row_base + ((j ^ sw) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
                      __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+          } else if (MODE == kOutSplitAct) {
+            if (in_m) {
+              // wide-range path: v = hi + lo with hi = bf16(v), lo = bf16(v - hi); row layout [hi (N columns) | lo (N columns)]
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float a = act_fn<ACT>(v[2 * j]), b = act_fn<ACT>(v[2 * j + 1]);
+                const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+                const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah)), bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+                hi[j] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+                lo[j] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+              }
+              uint4* dh = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(epi.out) + out_row * epi.ld_out + n0 + 32 * u);
+              uint4* dl = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(epi.out) + out_row * epi.ld_out + N + n0 + 32 * u);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+              }
+            }
           } else if (in_m) {
             float* dstf = static_cast<float*>(epi.out) + out_row * epi.ld_out + n0 + 32 * u;
             if (MODE == kOutPatchEmbed) {
@@ -279,6 +310,7 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (kHalfOut && epi.range_flag && (range_chk & 0x80008000u)) atomicOr(epi.range_flag, 1);
     if (kViaTma && lane == 0) bulk_wait_all();           // outstanding bulk ops read shared memory: finish before exit
   }
 
@@ -403,7 +435,7 @@ static int max_cluster_pairs(const void* fn, int smem) {
 
 template <int BN, int MODE, int ACT = 0>
 static int launch_bn_mode(const CUtensorMap* map_a, const CUtensorMap* map_w, const CUtensorMap* map_w_half, const CUtensorMap* map_out,
-                          int M, int N, int K, const GemmEpilogue& epi, cudaStream_t stream) {
+                          int M, int N, int K, const GemmEpilogue& epi, cudaStream_t stream, int split) {
   static bool attr_set = false;
   static int pairs = 0;
   if (!attr_set) {
@@ -425,34 +457,37 @@ static int launch_bn_mode(const CUtensorMap* map_a, const CUtensorMap* map_w, co
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = at; cfg.numAttrs = 2;
-    BSC_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_f16<BN, MODE, ACT, 2>, *map_a, *map_w_half, *map_out, M, N, K, epi));
+    BSC_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_f16<BN, MODE, ACT, 2>, *map_a, *map_w_half, *map_out, M, N, K, epi, split));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return BSCNAV_OK;
   }
   const int tiles = m_tiles * n_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
   constexpr int smem1 = Cfg<BN, 1>::kSmem;
-  BSC_LAUNCH_PDL((k_gemm_f16<BN, MODE, ACT, 1>), grid, kGemmThreads, smem1, stream, *map_a, *map_w, *map_out, M, N, K, epi);
+  BSC_LAUNCH_PDL((k_gemm_f16<BN, MODE, ACT, 1>), grid, kGemmThreads, smem1, stream, *map_a, *map_w, *map_out, M, N, K, epi, split);
   return BSCNAV_OK;
 }
 
 template <int BN>
 static int launch_bn(const CUtensorMap* map_a, const CUtensorMap* map_w, const CUtensorMap* map_w_half, const CUtensorMap* map_out,
-                     int M, int N, int K, const GemmEpilogue& epi, cudaStream_t stream) {
+                     int M, int N, int K, const GemmEpilogue& epi, cudaStream_t stream, int split) {
   switch (epi.mode) {
-    case kOutHalf: return launch_bn_mode<BN, kOutHalf>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream);
+    case kOutHalf: return launch_bn_mode<BN, kOutHalf>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream, split);
     case kOutHalfAct:
-      if (epi.act == 0) return launch_bn_mode<BN, kOutHalfAct, 0>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream);
-      return launch_bn_mode<BN, kOutHalfAct, 1>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream);
-    case kOutResidual: return launch_bn_mode<BN, kOutResidual>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream);
-    case kOutPatchEmbed: return launch_bn_mode<BN, kOutPatchEmbed>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream);
-    case kOutFloat: return launch_bn_mode<BN, kOutFloat>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream);
+      if (epi.act == 0) return launch_bn_mode<BN, kOutHalfAct, 0>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream, split);
+      return launch_bn_mode<BN, kOutHalfAct, 1>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream, split);
+    case kOutSplitAct:
+      if (epi.act == 0) return launch_bn_mode<BN, kOutSplitAct, 0>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream, split);
+      return launch_bn_mode<BN, kOutSplitAct, 1>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream, split);
+    case kOutResidual: return launch_bn_mode<BN, kOutResidual>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream, split);
+    case kOutPatchEmbed: return launch_bn_mode<BN, kOutPatchEmbed>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream, split);
+    case kOutFloat: return launch_bn_mode<BN, kOutFloat>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream, split);
     default: return BSCNAV_EINVAL;
   }
 }
 
 int gemm_f16_launch(const CUtensorMap* map_a, const CUtensorMap* map_w, const CUtensorMap* map_out, int M, int N, int K,
-                    const GemmEpilogue& epi, cudaStream_t stream, const CUtensorMap* map_w_half) {
+                    const GemmEpilogue& epi, cudaStream_t stream, const CUtensorMap* map_w_half, int split) {
   if (M <= 0 || N <= 0 || K <= 0 || N % 128 != 0 || K % BK != 0 || !epi.out) return BSCNAV_EINVAL;
   const bool via_tma = epi.mode == kOutHalf || epi.mode == kOutHalfAct || epi.mode == kOutResidual;
   if (via_tma && !map_out) return BSCNAV_EINVAL;
@@ -462,10 +497,10 @@ int gemm_f16_launch(const CUtensorMap* map_a, const CUtensorMap* map_w, const CU
   // few output tiles (small M: one goal image, one text prompt, a handful of queries): 128-wide tiles through the 128-row-box
   // weight map double the number of CTAs that stream the layer's weights -- these calls are bound by that, not by the MMAs
   if (gemm_block_n(N) == 256 && map_w_half && ((M + BM - 1) / BM) * (N / 256) * 2 <= sm_count())
-    return launch_bn<128>(map_a, map_w_half, nullptr, map_out, M, N, K, epi, stream);
+    return launch_bn<128>(map_a, map_w_half, nullptr, map_out, M, N, K, epi, stream, split);
   if (!use_cluster) map_w_half = nullptr;
-  if (gemm_block_n(N) == 256) return launch_bn<256>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream);
-  return launch_bn<128>(map_a, map_w, nullptr, map_out, M, N, K, epi, stream);
+  if (gemm_block_n(N) == 256) return launch_bn<256>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream, split);
+  return launch_bn<128>(map_a, map_w, nullptr, map_out, M, N, K, epi, stream, split);
 }
 
 }  // namespace bscnav
@@ -486,6 +521,20 @@ extern "C" int bscnav_gemm_f16(const void* a, const void* w, const float* bias, 
   if (via_tma)
     if (int e = make_store_map(&mo, out, m, n, out_mode == kOutResidual)) return e;
   GemmEpilogue epi{};
-  epi.out = out; epi.bias = bias; epi.table = nullptr; epi.ld_out = n; epi.mode = out_mode; epi.act = act;
+  epi.out = out; epi.bias = bias; epi.table = nullptr; epi.ld_out = n; epi.mode = out_mode; epi.act = act; epi.range_flag = nullptr;
   return gemm_f16_launch(&ma, &mw, via_tma ? &mo : nullptr, m, n, k, epi, (cudaStream_t)stream, half_ok ? &mwh : nullptr);
+}
+
+// Stand-alone wide-range GEMM (tests): a [M, 2K] and w [N, 2K] bf16 (hi | lo) rows (vit.py:split_bf16), fp32 out = a w^T + bias.
+extern "C" int bscnav_gemm_bf16x3(const void* a, const void* w, const float* bias, float* out, int32_t m, int32_t n, int32_t k,
+                                  void* stream) {
+  if (!a || !w || !out || m <= 0 || n <= 0 || k <= 0 || n % 128 != 0 || k % 64 != 0) return BSCNAV_EINVAL;
+  CUtensorMap ma, mw, mwh;
+  if (int e = make_operand_map(&ma, a, m, 2LL * k, BM)) return e;
+  if (int e = make_operand_map(&mw, w, n, 2LL * k, gemm_block_n(n))) return e;
+  const bool half_ok = gemm_block_n(n) == 256;
+  if (half_ok) if (int e = make_operand_map(&mwh, w, n, 2LL * k, 128)) return e;
+  GemmEpilogue epi{};
+  epi.out = out; epi.bias = bias; epi.ld_out = n; epi.mode = kOutFloat;
+  return gemm_f16_launch(&ma, &mw, nullptr, m, n, k, epi, (cudaStream_t)stream, half_ok ? &mwh : nullptr, 1);
 }

@@ -20,7 +20,8 @@ enum GemmOut : int {
   kOutHalfAct = 1,     // fp16 out = act(acc + bias)
   kOutResidual = 2,    // fp32 out += acc + bias           (residual stream)
   kOutPatchEmbed = 3,  // fp32 out[remap(m)] = acc + bias + table[m % np]   (patch embedding + position embedding)
-  kOutFloat = 4,       // fp32 out = acc (+ bias)           (similarity matrices)
+  kOutFloat = 4,       // fp32 out = acc (+ bias)           (similarity matrices; qkv of the wide-range path)
+  kOutSplitAct = 5,    // bf16 (hi | lo) out = split(act(acc + bias)): out[m, n] = hi, out[m, N + n] = lo   (wide-range path, fc1)
 };
 
 struct GemmEpilogue {
@@ -31,13 +32,17 @@ struct GemmEpilogue {
   int mode;
   int act;              // 0 = GELU(erf), 1 = QuickGELU
   int np, tokens, row_off;  // kOutPatchEmbed: out row = (m / np) * tokens + row_off + m % np
+  int* range_flag;          // fp16 outputs: set to 1 when a value left the fp16 range (inf / nan after rounding); may be null
 };
 
 // map_out: store map of the output tensor (make_store_map) for the fp16 / residual epilogues; null for the others
 // map_w_half: the same weight matrix with a 128-row box (make_operand_map(..., 128)); when given (and N % 256 == 0, at least
 // two row blocks) the 2-CTA cluster variant runs: each CTA loads half of the weight tile and multicasts it to its peer
+// split != 0: wide-range operands ("bf16x3"): A is [M, 2K] and W is [N, 2K] bf16, each row holding the leading bf16 of every
+// fp32 value followed by the bf16 of the remainder (hi | lo); the K loop runs three passes a_hi w_hi + a_lo w_hi + a_hi w_lo into the
+// same fp32 accumulator (relative error ~2^-17 per product, fp32 range).  K is the logical depth, the maps cover 2K columns.
 int gemm_f16_launch(const CUtensorMap* map_a, const CUtensorMap* map_w, const CUtensorMap* map_out, int M, int N, int K,
-                    const GemmEpilogue& epi, cudaStream_t stream, const CUtensorMap* map_w_half = nullptr);
+                    const GemmEpilogue& epi, cudaStream_t stream, const CUtensorMap* map_w_half = nullptr, int split = 0);
 int make_store_map(CUtensorMap* map, const void* ptr, long long rows, long long N, bool is_float);
 
 // 2-D K-major fp16 operand [rows, K] -> tensor map with box {64, box_rows}, 128-byte swizzle

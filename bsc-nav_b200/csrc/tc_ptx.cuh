@@ -126,6 +126,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int n, int m = 128, int b_mn_major = 0) {
   return (1u << 4) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// a_format [7,10) and b_format [10,13) = 1: bf16 operands (fp32 exponent range)
+constexpr uint32_t kUmmaBf16Operands = (1u << 7) | (1u << 10);
 
 
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t* r) {

@@ -32,11 +32,14 @@ static int vit_layout(const bscnav_vit_cfg_t* c, VitLayout* L) {
   const bool text = c->text_context > 0;
   if (c->text_context < 0 || (text && (hd != 64 || c->n_reg || c->ln_pre))) return BSCNAV_EINVAL;
   if (!text && (c->patch <= 0 || c->image % c->patch || c->patch_k_pad % 64 || c->patch_k_pad < 3 * c->patch * c->patch)) return BSCNAV_EINVAL;
+  if (c->precision != 0 && c->precision != 1) return BSCNAV_EINVAL;
+  if (c->precision == 1 && hd != 64) return BSCNAV_EINVAL;              // the fp32 attention kernel: head dim 64
   const long long D = c->dim, M = c->mlp;
+  const long long ws = c->precision == 1 ? 2 : 1;                       // wide-range path: (hi | lo) pairs, rows of 2K
   const long long Np = text ? c->text_context : (long long)(c->image / c->patch) * (c->image / c->patch);
   long long h = 0, f = 0;
   if (!text) {
-    L->patch_w = h; h += D * c->patch_k_pad;
+    L->patch_w = h; h += ws * D * c->patch_k_pad;
     L->patch_b = f; f += D;
     L->cls_pos = f; f += D;
     L->reg = f; f += (long long)c->n_reg * D;
@@ -45,10 +48,10 @@ static int vit_layout(const bscnav_vit_cfg_t* c, VitLayout* L) {
   if (c->ln_pre) { L->ln_pre_w = f; f += D; L->ln_pre_b = f; f += D; }
   for (int i = 0; i < c->depth; ++i) {
     LayerOff& o = L->layer[i];
-    o.qkv_w = h; h += 3 * D * D;
-    o.proj_w = h; h += D * D;
-    o.fc1_w = h; h += M * D;
-    o.fc2_w = h; h += D * M;
+    o.qkv_w = h; h += ws * 3 * D * D;
+    o.proj_w = h; h += ws * D * D;
+    o.fc1_w = h; h += ws * M * D;
+    o.fc2_w = h; h += ws * D * M;
     o.ln1_w = f; f += D; o.ln1_b = f; f += D;
     o.qkv_b = f; f += 3 * D;
     o.proj_b = f; f += D;
@@ -70,7 +73,11 @@ struct Workspace {
   __half* qkv;   // [B*T, 3D]
   __half* ao;    // [B*T, D]
   __half* hmid;  // [B*T, M]
+  // wide-range path: a0 / y / ao / hmid hold (hi | lo) bf16 rows of twice the width, qkv is fp32
+  __half* a0h;   // fp16 patch rows written by the pre-processing kernel (scratch; the GEMM reads the split rows in a0)
+  float* pre_img; // [B, 3, S, S] pre-processed frames (input of the split im2col)
   float* pre_tab; // resize tap tables of the pre-processing kernel
+  int* range_flag; // set by the GEMM epilogues when an fp16 activation overflowed
   long long total;
 };
 static void workspace_layout(const bscnav_vit_cfg_t* c, int max_batch, Workspace* w, char* base) {
@@ -79,13 +86,17 @@ static void workspace_layout(const bscnav_vit_cfg_t* c, int max_batch, Workspace
   const long long T = text ? c->text_context : 1 + c->n_reg + Np;
   long long off = 0;
   auto take = [&](long long bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes, 1024); return p; };
-  w->a0 = reinterpret_cast<__half*>(take(text ? 0 : B * Np * c->patch_k_pad * 2));
+  const long long wide = c->precision == 1 ? 2 : 1;
+  w->a0 = reinterpret_cast<__half*>(take(text ? 0 : wide * B * Np * c->patch_k_pad * 2));
   w->x = reinterpret_cast<float*>(take(B * T * D * 4));
-  w->y = reinterpret_cast<__half*>(take(B * T * D * 2));
-  w->qkv = reinterpret_cast<__half*>(take(B * T * 3 * D * 2));
-  w->ao = reinterpret_cast<__half*>(take(B * T * D * 2));
-  w->hmid = reinterpret_cast<__half*>(take(B * T * M * 2));
+  w->y = reinterpret_cast<__half*>(take(wide * B * T * D * 2));
+  w->qkv = reinterpret_cast<__half*>(take(wide * B * T * 3 * D * 2));      // wide: fp32
+  w->ao = reinterpret_cast<__half*>(take(wide * B * T * D * 2));
+  w->hmid = reinterpret_cast<__half*>(take(wide * B * T * M * 2));
+  w->a0h = reinterpret_cast<__half*>(take(text || wide == 1 ? 0 : B * Np * c->patch_k_pad * 2));
+  w->pre_img = reinterpret_cast<float*>(take(text || wide == 1 ? 0 : B * 3 * (long long)c->image * c->image * 4));
   w->pre_tab = reinterpret_cast<float*>(take(text ? 0 : preprocess_table_bytes(c->image)));
+  w->range_flag = reinterpret_cast<int*>(take(256));
   w->total = off;
 }
 
@@ -143,7 +154,7 @@ static int vit_run(VitEngine* e, int batch, float* out_tokens, cudaStream_t stre
   ep.out = e->ws.x; ep.bias = wf + e->L.patch_b; ep.table = wf + e->L.pos; ep.ld_out = D; ep.mode = kOutPatchEmbed;
   ep.np = Np; ep.tokens = T; ep.row_off = 1 + c.n_reg;
   { ProfScope ps(e, stream, kCatGemm, 2.0 * batch * Np * (double)D * c.patch_k_pad);
-    if (int r = gemm_f16_launch(&e->map_a0, &e->map_patch_w, nullptr, batch * Np, D, c.patch_k_pad, ep, stream)) return r; }
+    if (int r = gemm_f16_launch(&e->map_a0, &e->map_patch_w, nullptr, batch * Np, D, c.patch_k_pad, ep, stream, nullptr, c.precision)) return r; }
   if (int r = fill_prefix_tokens(e->ws.x, wf + e->L.cls_pos, wf + e->L.reg, batch, T, c.n_reg, D, stream)) return r;
   if (c.ln_pre)
     if (int r = layernorm_inplace(e->ws.x, wf + e->L.ln_pre_w, wf + e->L.ln_pre_b, c.ln_eps, rows, D, stream)) return r;
@@ -154,8 +165,11 @@ static int vit_run(VitEngine* e, int batch, float* out_tokens, cudaStream_t stre
 }
 
 // the transformer blocks over the residual stream ws.x [batch*T, D] (image and text towers)
+static int run_layers_wide(VitEngine* e, int batch, cudaStream_t stream);
+
 static int run_layers(VitEngine* e, int batch, cudaStream_t stream) {
   const bscnav_vit_cfg_t& c = e->cfg;
+  if (c.precision == 1) return run_layers_wide(e, batch, stream);
   const int D = c.dim, M = c.mlp, T = e->T;
   const int rows = batch * T;
   const float* wf = e->wf;
@@ -165,7 +179,7 @@ static int run_layers(VitEngine* e, int batch, cudaStream_t stream) {
     { ProfScope ps(e, stream, kCatLayerNorm, (double)rows * D * 6);
       if (int r = layernorm_half(e->ws.x, wf + o.ln1_w, wf + o.ln1_b, c.ln_eps, rows, D, e->ws.y, stream)) return r; }
     GemmEpilogue e1{};
-    e1.out = e->ws.qkv; e1.bias = wf + o.qkv_b; e1.ld_out = 3 * D; e1.mode = kOutHalf;
+    e1.out = e->ws.qkv; e1.bias = wf + o.qkv_b; e1.ld_out = 3 * D; e1.mode = kOutHalf; e1.range_flag = e->ws.range_flag;
     { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * 3.0 * D * D);
       if (int r = gemm_f16_launch(&e->map_y, &e->map_qkv[i], &e->out_qkv, rows, 3 * D, D, e1, stream, e->has_half[0] ? &e->half_qkv[i] : nullptr)) return r; }
     { ProfScope ps(e, stream, kCatAttention, 4.0 * batch * (double)T * T * D);
@@ -183,13 +197,48 @@ static int run_layers(VitEngine* e, int batch, cudaStream_t stream) {
     { ProfScope ps(e, stream, kCatLayerNorm, (double)rows * D * 6);
       if (int r = layernorm_half(e->ws.x, wf + o.ln2_w, wf + o.ln2_b, c.ln_eps, rows, D, e->ws.y, stream)) return r; }
     GemmEpilogue e3{};
-    e3.out = e->ws.hmid; e3.bias = wf + o.fc1_b; e3.ld_out = M; e3.mode = kOutHalfAct; e3.act = c.act;
+    e3.out = e->ws.hmid; e3.bias = wf + o.fc1_b; e3.ld_out = M; e3.mode = kOutHalfAct; e3.act = c.act; e3.range_flag = e->ws.range_flag;
     { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * (double)M * D);
       if (int r = gemm_f16_launch(&e->map_y, &e->map_fc1[i], &e->out_h, rows, M, D, e3, stream, e->has_half[2] ? &e->half_fc1[i] : nullptr)) return r; }
     GemmEpilogue e4{};
     e4.out = e->ws.x; e4.bias = wf + o.fc2_b; e4.ld_out = D; e4.mode = kOutResidual;
     { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * (double)M * D);
       if (int r = gemm_f16_launch(&e->map_h, &e->map_fc2[i], &e->out_x, rows, D, M, e4, stream, e->has_half[3] ? &e->half_fc2[i] : nullptr)) return r; }
+  }
+  return BSCNAV_OK;
+}
+
+// the same blocks on the wide-range path: split bf16 operands, three GEMM passes, fp32 qkv and attention
+static int run_layers_wide(VitEngine* e, int batch, cudaStream_t stream) {
+  const bscnav_vit_cfg_t& c = e->cfg;
+  const int D = c.dim, M = c.mlp, T = e->T;
+  const int rows = batch * T;
+  const float* wf = e->wf;
+  const bool causal = c.text_context > 0;
+  for (int i = 0; i < c.depth; ++i) {
+    const LayerOff& o = e->L.layer[i];
+    { ProfScope ps(e, stream, kCatLayerNorm, (double)rows * D * 8);
+      if (int r = layernorm_split(e->ws.x, wf + o.ln1_w, wf + o.ln1_b, c.ln_eps, rows, D, e->ws.y, stream)) return r; }
+    GemmEpilogue e1{};
+    e1.out = e->ws.qkv; e1.bias = wf + o.qkv_b; e1.ld_out = 3 * D; e1.mode = kOutFloat;
+    { ProfScope ps(e, stream, kCatGemm, 3 * 2.0 * rows * 3.0 * D * D);
+      if (int r = gemm_f16_launch(&e->map_y, &e->map_qkv[i], nullptr, rows, 3 * D, D, e1, stream, e->has_half[0] ? &e->half_qkv[i] : nullptr, 1)) return r; }
+    { ProfScope ps(e, stream, kCatAttention, 4.0 * batch * (double)T * T * D);
+      if (int r = attention_f32_split(reinterpret_cast<const float*>(e->ws.qkv), e->ws.ao, batch, T, c.heads, causal, stream)) return r; }
+    GemmEpilogue e2{};
+    e2.out = e->ws.x; e2.bias = wf + o.proj_b; e2.ld_out = D; e2.mode = kOutResidual;
+    { ProfScope ps(e, stream, kCatGemm, 3 * 2.0 * rows * (double)D * D);
+      if (int r = gemm_f16_launch(&e->map_ao, &e->map_proj[i], &e->out_x, rows, D, D, e2, stream, e->has_half[1] ? &e->half_proj[i] : nullptr, 1)) return r; }
+    { ProfScope ps(e, stream, kCatLayerNorm, (double)rows * D * 8);
+      if (int r = layernorm_split(e->ws.x, wf + o.ln2_w, wf + o.ln2_b, c.ln_eps, rows, D, e->ws.y, stream)) return r; }
+    GemmEpilogue e3{};
+    e3.out = e->ws.hmid; e3.bias = wf + o.fc1_b; e3.ld_out = 2 * M; e3.mode = kOutSplitAct; e3.act = c.act;
+    { ProfScope ps(e, stream, kCatGemm, 3 * 2.0 * rows * (double)M * D);
+      if (int r = gemm_f16_launch(&e->map_y, &e->map_fc1[i], nullptr, rows, M, D, e3, stream, e->has_half[2] ? &e->half_fc1[i] : nullptr, 1)) return r; }
+    GemmEpilogue e4{};
+    e4.out = e->ws.x; e4.bias = wf + o.fc2_b; e4.ld_out = D; e4.mode = kOutResidual;
+    { ProfScope ps(e, stream, kCatGemm, 3 * 2.0 * rows * (double)M * D);
+      if (int r = gemm_f16_launch(&e->map_h, &e->map_fc2[i], &e->out_x, rows, D, M, e4, stream, e->has_half[3] ? &e->half_fc2[i] : nullptr, 1)) return r; }
   }
   return BSCNAV_OK;
 }
@@ -234,47 +283,62 @@ int bscnav_vit_create(const bscnav_vit_cfg_t* c, const void* w_half, const float
   e->Np = G * G;
   e->T = text ? c->text_context : 1 + c->n_reg + e->Np;
   const long long D = c->dim, M = c->mlp, rows = (long long)max_batch * e->T;
+  const long long kw = c->precision == 1 ? 2 : 1;        // operand rows are (hi | lo) pairs on the wide-range path
   int r = 0;
-  if (!text) r = r ? r : make_operand_map(&e->map_a0, e->ws.a0, (long long)max_batch * e->Np, c->patch_k_pad, 128);
-  r = r ? r : make_operand_map(&e->map_y, e->ws.y, rows, D, 128);
-  r = r ? r : make_operand_map(&e->map_ao, e->ws.ao, rows, D, 128);
-  r = r ? r : make_operand_map(&e->map_h, e->ws.hmid, rows, M, 128);
+  if (!text) r = r ? r : make_operand_map(&e->map_a0, e->ws.a0, (long long)max_batch * e->Np, kw * c->patch_k_pad, 128);
+  r = r ? r : make_operand_map(&e->map_y, e->ws.y, rows, kw * D, 128);
+  r = r ? r : make_operand_map(&e->map_ao, e->ws.ao, rows, kw * D, 128);
+  r = r ? r : make_operand_map(&e->map_h, e->ws.hmid, rows, kw * M, 128);
   // default: the warp-specialised tcgen05 kernel (70.6 us vs 82.0 us for mma.sync at 55 frames x 16 heads, T = 257);
   // BSCNAV_ATTENTION=0|1|2 selects mma.sync / tcgen05 v1 / tcgen05 warp-specialised (tests exercise all three)
   const char* impl_env = getenv("BSCNAV_ATTENTION");
   e->attn_impl = impl_env ? atoi(impl_env) : 3;
   if ((c->head_dim && c->head_dim != 64) || text) e->attn_impl = 0;  // the tcgen05 kernels: head dim 64, no causal mask
+  if (c->precision == 1) e->attn_impl = 0;                           // wide-range path: fp32 attention (run_layers_wide)
   if (e->attn_impl == 3 && !attention_ws2_supported(e->T)) e->attn_impl = 2;
   if (e->attn_impl == 2 && !attention_ws_supported(e->T)) e->attn_impl = 0;
   if (e->attn_impl == 1 && !attention_tc_supported(e->T)) e->attn_impl = 0;
-  r = r ? r : make_qkv_map3d(&e->qkv3d128, e->ws.qkv, max_batch, e->T, 3 * D, 128);
-  r = r ? r : make_qkv_map3d(&e->qkv3d16, e->ws.qkv, max_batch, e->T, 3 * D, 16);
-  r = r ? r : make_out_map3d(&e->ao3d, e->ws.ao, max_batch, e->T, D);
-  r = r ? r : make_operand_map(&e->qkv128, e->ws.qkv, rows, 3 * D, 128);
-  r = r ? r : make_operand_map(&e->qkv16, e->ws.qkv, rows, 3 * D, 16);
-  r = r ? r : make_store_map(&e->out_qkv, e->ws.qkv, rows, 3 * D, false);
-  r = r ? r : make_store_map(&e->out_h, e->ws.hmid, rows, M, false);
+  if (c->precision == 0) {
+    r = r ? r : make_qkv_map3d(&e->qkv3d128, e->ws.qkv, max_batch, e->T, 3 * D, 128);
+    r = r ? r : make_qkv_map3d(&e->qkv3d16, e->ws.qkv, max_batch, e->T, 3 * D, 16);
+    r = r ? r : make_out_map3d(&e->ao3d, e->ws.ao, max_batch, e->T, D);
+    r = r ? r : make_operand_map(&e->qkv128, e->ws.qkv, rows, 3 * D, 128);
+    r = r ? r : make_operand_map(&e->qkv16, e->ws.qkv, rows, 3 * D, 16);
+    r = r ? r : make_store_map(&e->out_qkv, e->ws.qkv, rows, 3 * D, false);
+    r = r ? r : make_store_map(&e->out_h, e->ws.hmid, rows, M, false);
+  }
   r = r ? r : make_store_map(&e->out_x, e->ws.x, rows, D, true);
-  if (!text) r = r ? r : make_operand_map(&e->map_patch_w, e->wh + e->L.patch_w, D, c->patch_k_pad, gemm_block_n((int)D));
+  if (!text) r = r ? r : make_operand_map(&e->map_patch_w, e->wh + e->L.patch_w, D, kw * c->patch_k_pad, gemm_block_n((int)D));
   for (int i = 0; i < c->depth && !r; ++i) {
     const LayerOff& o = e->L.layer[i];
-    r = r ? r : make_operand_map(&e->map_qkv[i], e->wh + o.qkv_w, 3 * D, D, gemm_block_n((int)(3 * D)));
-    r = r ? r : make_operand_map(&e->map_proj[i], e->wh + o.proj_w, D, D, gemm_block_n((int)D));
-    r = r ? r : make_operand_map(&e->map_fc1[i], e->wh + o.fc1_w, M, D, gemm_block_n((int)M));
-    r = r ? r : make_operand_map(&e->map_fc2[i], e->wh + o.fc2_w, D, M, gemm_block_n((int)D));
+    r = r ? r : make_operand_map(&e->map_qkv[i], e->wh + o.qkv_w, 3 * D, kw * D, gemm_block_n((int)(3 * D)));
+    r = r ? r : make_operand_map(&e->map_proj[i], e->wh + o.proj_w, D, kw * D, gemm_block_n((int)D));
+    r = r ? r : make_operand_map(&e->map_fc1[i], e->wh + o.fc1_w, M, kw * D, gemm_block_n((int)M));
+    r = r ? r : make_operand_map(&e->map_fc2[i], e->wh + o.fc2_w, D, kw * M, gemm_block_n((int)D));
     e->has_half[0] = gemm_block_n((int)(3 * D)) == 256; e->has_half[1] = e->has_half[3] = gemm_block_n((int)D) == 256;
     e->has_half[2] = gemm_block_n((int)M) == 256;
-    if (e->has_half[0]) r = r ? r : make_operand_map(&e->half_qkv[i], e->wh + o.qkv_w, 3 * D, D, 128);
-    if (e->has_half[1]) r = r ? r : make_operand_map(&e->half_proj[i], e->wh + o.proj_w, D, D, 128);
-    if (e->has_half[2]) r = r ? r : make_operand_map(&e->half_fc1[i], e->wh + o.fc1_w, M, D, 128);
-    if (e->has_half[3]) r = r ? r : make_operand_map(&e->half_fc2[i], e->wh + o.fc2_w, D, M, 128);
+    if (e->has_half[0]) r = r ? r : make_operand_map(&e->half_qkv[i], e->wh + o.qkv_w, 3 * D, kw * D, 128);
+    if (e->has_half[1]) r = r ? r : make_operand_map(&e->half_proj[i], e->wh + o.proj_w, D, kw * D, 128);
+    if (e->has_half[2]) r = r ? r : make_operand_map(&e->half_fc1[i], e->wh + o.fc1_w, M, kw * D, 128);
+    if (e->has_half[3]) r = r ? r : make_operand_map(&e->half_fc2[i], e->wh + o.fc2_w, D, kw * M, 128);
   }
+  if (!r && cudaMemset(e->ws.range_flag, 0, 256) != cudaSuccess) r = BSCNAV_ECUDA;
   if (r) { delete e; return r; }
   *out_engine = e;
   return BSCNAV_OK;
 }
 
 void bscnav_vit_destroy(void* engine) { delete static_cast<VitEngine*>(engine); }
+
+int bscnav_vit_range_status(void* engine, int32_t reset, int32_t* host_out, void* stream_) {
+  VitEngine* e = static_cast<VitEngine*>(engine);
+  if (!e || !host_out) return BSCNAV_EINVAL;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  BSC_CUDA(cudaMemcpyAsync(host_out, e->ws.range_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  if (reset) BSC_CUDA(cudaMemsetAsync(e->ws.range_flag, 0, sizeof(int32_t), stream));
+  BSC_CUDA(cudaStreamSynchronize(stream));
+  return BSCNAV_OK;
+}
 
 int bscnav_vit_profile(void* engine, int32_t enable) {
   VitEngine* e = static_cast<VitEngine*>(engine);
@@ -302,10 +366,15 @@ static int clear_a0_once(VitEngine* e, cudaStream_t stream) {
   if (e->cfg.text_context > 0) return BSCNAV_EINVAL;     // text engine: image entry points do not apply
   // the K padding columns of the patch rows are never written by im2col: zero them once
   if (!e->a0_cleared) {
-    BSC_CUDA(cudaMemsetAsync(e->ws.a0, 0, (size_t)e->max_batch * e->Np * e->cfg.patch_k_pad * 2, stream));
+    BSC_CUDA(cudaMemsetAsync(e->ws.a0, 0, (size_t)(e->cfg.precision == 1 ? 2 : 1) * e->max_batch * e->Np * e->cfg.patch_k_pad * 2, stream));
     e->a0_cleared = true;
   }
   return BSCNAV_OK;
+}
+
+static int im2col_any(VitEngine* e, const float* images, int batch, cudaStream_t stream) {
+  if (e->cfg.precision == 1) return im2col_images_split(images, batch, e->cfg.image, e->cfg.patch, e->cfg.patch_k_pad, e->ws.a0, stream);
+  return im2col_images(images, batch, e->cfg.image, e->cfg.patch, e->cfg.patch_k_pad, e->ws.a0, stream);
 }
 
 int bscnav_vit_forward_frames(void* engine, const uint8_t* rgb, int32_t batch, int32_t height, int32_t width,
@@ -314,6 +383,15 @@ int bscnav_vit_forward_frames(void* engine, const uint8_t* rgb, int32_t batch, i
   if (!e || !rgb || !out_tokens || batch <= 0 || batch > e->max_batch) return BSCNAV_EINVAL;
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int r = clear_a0_once(e, stream)) return r;
+  if (e->cfg.precision == 1) {
+    // wide-range path: the fp32 pre-processed frames are kept and split into (hi | lo) patch rows
+    { ProfScope ps(e, stream, kCatPre, (double)batch * height * width * channels);
+      if (int r = preprocess_frames(rgb, batch, height, width, channels, e->cfg.image, e->cfg.patch, e->cfg.patch_k_pad, e->ws.a0h,
+                                    e->ws.pre_img, e->ws.pre_tab, stream)) return r; }
+    if (out_pre) BSC_CUDA(cudaMemcpyAsync(out_pre, e->ws.pre_img, (size_t)batch * 3 * e->cfg.image * e->cfg.image * 4, cudaMemcpyDeviceToDevice, stream));
+    if (int r = im2col_images_split(e->ws.pre_img, batch, e->cfg.image, e->cfg.patch, e->cfg.patch_k_pad, e->ws.a0, stream)) return r;
+    return vit_run(e, batch, out_tokens, stream);
+  }
   { ProfScope ps(e, stream, kCatPre, (double)batch * height * width * channels);
     if (int r = preprocess_frames(rgb, batch, height, width, channels, e->cfg.image, e->cfg.patch, e->cfg.patch_k_pad, e->ws.a0,
                                   out_pre, e->ws.pre_tab, stream)) return r; }
@@ -325,7 +403,7 @@ int bscnav_vit_forward_images(void* engine, const float* images, int32_t batch, 
   if (!e || !images || !out_tokens || batch <= 0 || batch > e->max_batch) return BSCNAV_EINVAL;
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int r = clear_a0_once(e, stream)) return r;
-  if (int r = im2col_images(images, batch, e->cfg.image, e->cfg.patch, e->cfg.patch_k_pad, e->ws.a0, stream)) return r;
+  if (int r = im2col_any(e, images, batch, stream)) return r;
   return vit_run(e, batch, out_tokens, stream);
 }
 
@@ -335,7 +413,7 @@ int bscnav_vit_encode_images(void* engine, const float* images, int32_t batch, c
   if (!e || !images || !proj || !out_embed || embed_dim <= 0 || batch <= 0 || batch > e->max_batch) return BSCNAV_EINVAL;
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int r = clear_a0_once(e, stream)) return r;
-  if (int r = im2col_images(images, batch, e->cfg.image, e->cfg.patch, e->cfg.patch_k_pad, e->ws.a0, stream)) return r;
+  if (int r = im2col_any(e, images, batch, stream)) return r;
   return vit_run(e, batch, nullptr, stream, proj, embed_dim, out_embed);
 }
 

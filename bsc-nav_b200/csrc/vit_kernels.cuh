@@ -24,4 +24,10 @@ int cls_embed(const float* x, const float* g, const float* b, float eps, int bat
 int text_embed(const int32_t* ids, const float* tok_emb, int vocab, const float* pos, int batch, int ctx, int D, float* x,
                cudaStream_t stream);
 
+// wide-range ("bf16x3") path, wide_kernels.cu: operands as (hi | lo) bf16 row pairs, fp32 attention (head dim 64)
+int split_rows(const float* src, long long rows, int K, void* dst, cudaStream_t stream);
+int im2col_images_split(const float* img, int batch, int S, int P, int k_pad, void* a0, cudaStream_t stream);
+int layernorm_split(const float* x, const float* g, const float* b, float eps, long long rows, int D, void* out, cudaStream_t stream);
+int attention_f32_split(const float* qkv, void* out, int batch, int T, int heads, bool causal, cudaStream_t stream);
+
 }  // namespace bscnav

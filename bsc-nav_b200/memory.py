@@ -339,8 +339,10 @@ class VoxelTokenMemory:
 
     def update_memory_dist_base(self):
         """memory_2.py:326-358: the reference flushes its 50 000-row host buffer to HDF5 here.  Tokens are already in the
-        device store; this only surfaces a pending capacity error."""
+        device store; this only surfaces pending errors (slot capacity, fp16 range of the feature extractor)."""
         self._store.count()
+        if isinstance(self.dinov2, ViTEngine):
+            self.dinov2.check_range()
 
     def initial_memory(self):
         """memory_2.py:298-309: never overwrite an existing directory."""

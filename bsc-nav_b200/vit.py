@@ -16,15 +16,28 @@ from . import _lib
 from .vit_config import ViTConfig
 
 
-def _cfg_struct(cfg: ViTConfig) -> _lib.VitCfg:
+PRECISIONS = {"fp16": 0, "bf16x3": 1}
+
+
+def _cfg_struct(cfg: ViTConfig, precision: str = "fp16") -> _lib.VitCfg:
     k_pad = (cfg.patch_k + 63) // 64 * 64
     return _lib.VitCfg(image=cfg.image, patch=cfg.patch, dim=cfg.dim, depth=cfg.depth, heads=cfg.heads, mlp=cfg.mlp,
                        n_reg=cfg.n_reg, act=0 if cfg.act == "gelu" else 1, ln_pre=1 if cfg.ln_pre else 0,
-                       patch_k_pad=k_pad, ln_eps=cfg.ln_eps, head_dim=cfg.dim // cfg.heads, text_context=cfg.text_context)
+                       patch_k_pad=k_pad, ln_eps=cfg.ln_eps, head_dim=cfg.dim // cfg.heads, text_context=cfg.text_context,
+                       precision=PRECISIONS[precision])
 
 
-def pack_weights(cfg: ViTConfig, w: dict):
+def split_bf16(m: torch.Tensor) -> torch.Tensor:
+    """fp32 [N, K] -> bf16 [N, 2K] rows (hi | lo): hi = bf16(m), lo = bf16(m - hi); m = hi + lo up to ~2^-17 relative."""
+    m = m.float()
+    hi = m.to(torch.bfloat16)
+    lo = (m - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, lo], dim=1)
+
+
+def pack_weights(cfg: ViTConfig, w: dict, precision: str = "fp16"):
     """fp32 weight dict (vit_config.random_weights layout) -> (half blob, float blob), CPU tensors.
+    precision="bf16x3" (the wide-range path): the 16-bit blob holds every matrix as (hi | lo) bf16 row pairs (split_bf16).
 
     Folded on the host (exact in real arithmetic): 1/sqrt(head_dim) into the q rows of qkv (a power of two for
     head_dim 64, so also exact in fp16; for head_dim 80 the scaled fp32 weight is rounded to fp16 once), LayerScale gamma
@@ -62,7 +75,12 @@ def pack_weights(cfg: ViTConfig, w: dict):
         half += [qkv_w, proj_w, w[p + "fc1_w"], fc2_w]
         flt += [w[p + "ln1_w"], w[p + "ln1_b"], qkv_b, proj_b, w[p + "ln2_w"], w[p + "ln2_b"], w[p + "fc1_b"], fc2_b]
     flt += [w["ln_post_w"], w["ln_post_b"]]
-    hb = torch.cat([t.reshape(-1).float() for t in half]).to(torch.float16)
+    if precision == "bf16x3":
+        if dh != 64:
+            raise ValueError("the wide-range path supports head_dim 64")
+        hb = torch.cat([split_bf16(t).reshape(-1) for t in half])
+    else:
+        hb = torch.cat([t.reshape(-1).float() for t in half]).to(torch.float16)
     fb = torch.cat([t.reshape(-1).float() for t in flt]).contiguous()
     return hb, fb
 
@@ -70,13 +88,19 @@ def pack_weights(cfg: ViTConfig, w: dict):
 class ViTEngine:
     """Device-resident ViT: packed weights + workspace + TMA descriptors, one instance per GPU."""
 
-    def __init__(self, cfg: ViTConfig, weights: dict, max_batch: int = 64, device="cuda"):
+    def __init__(self, cfg: ViTConfig, weights: dict, max_batch: int = 64, device="cuda", precision: str = "fp16"):
+        """precision: "fp16" -- fp16 operands / fp32 accumulation, the throughput path (an activation beyond the fp16 range raises
+        through check_range()); "bf16x3" -- wide-range path: split bf16 operands, three tensor-core passes per product, fp32
+        attention: fp32 range and ~1e-5 relative error against the fp32 reference (memory_2.py:737-739) at ~1/3 of the rate."""
         self.lib = _lib.lib()
         self.cfg = cfg
         self.device = torch.device(device)
         self.max_batch = int(max_batch)
-        self._c = _cfg_struct(cfg)
-        hb, fb = pack_weights(cfg, weights)
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
+        self.precision = precision
+        self._c = _cfg_struct(cfg, precision)
+        hb, fb = pack_weights(cfg, weights, precision)
         if hb.numel() != self.lib.bscnav_vit_half_elems(C.byref(self._c)) or fb.numel() != self.lib.bscnav_vit_float_elems(C.byref(self._c)):
             raise _lib.BscnavError("weight blob layout mismatch between vit.py and vit_engine.cu")
         self.w_half = hb.to(self.device)
@@ -90,6 +114,27 @@ class ViTEngine:
             _lib.check(self.lib.bscnav_vit_create(C.byref(self._c), _lib.ptr(self.w_half), _lib.ptr(self.w_float),
                                                   _lib.ptr(self.workspace), nbytes, self.max_batch, C.byref(h)), "vit_create")
         self._h = h
+
+    @classmethod
+    def auto(cls, cfg: ViTConfig, weights: dict, max_batch: int = 64, device="cuda", probe: torch.Tensor | None = None,
+             tol: float = 5e-4):
+        """Pick the precision from the weights: run `probe` (uint8 frames (B, H, W, 3|4) on the device; default: 2 seeded
+        random 224 x 224 frames) through both paths and keep the fp16 throughput path only if its tokens agree with the
+        wide-range path to `tol` per token (half the 1e-3 parity bar) and no activation left the fp16 range.  Trained checkpoints
+        with outlier channels fail this and get the bf16x3 engine.  The measured error is kept in `.probe_error`."""
+        dev = torch.device(device)
+        if probe is None:
+            probe = torch.randint(0, 256, (2, cfg.image, cfg.image, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(0)).to(dev)
+        nb = min(int(probe.shape[0]), int(max_batch))
+        wide = cls(cfg, weights, max_batch=max_batch, device=device, precision="bf16x3")
+        ref = wide.forward_frames(probe[:nb].contiguous())
+        fast = cls(cfg, weights, max_batch=max_batch, device=device, precision="fp16")
+        got = fast.forward_frames(probe[:nb].contiguous())
+        overflow = fast.range_overflow()
+        err = float(((got - ref).norm(dim=-1) / ref.norm(dim=-1)).max()) if not overflow else float("inf")
+        keep = fast if (not overflow and err < tol) else wide
+        keep.probe_error = err
+        return keep
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -187,6 +232,18 @@ class ViTEngine:
             run(ids[b0:], out[b0:], min(self.max_batch, B - b0))
         return out
 
+    def range_overflow(self, reset: bool = True) -> bool:
+        """True when an fp16 activation (qkv or the MLP's hidden layer) overflowed since the last reset; synchronises."""
+        v = C.c_int32(0)
+        _lib.check(self.lib.bscnav_vit_range_status(self._h, 1 if reset else 0, C.byref(v), _lib.stream_ptr()), "vit_range_status")
+        return bool(v.value)
+
+    def check_range(self):
+        """Raise if the fp16 activation range was exceeded: the tokens produced since the last check are not trustworthy."""
+        if self.range_overflow():
+            raise _lib.BscnavError(f"{self.cfg.name}: an activation left the fp16 range (|x| > 65504) inside the ViT; "
+                                   "these weights need the wide-range path (ViTEngine(..., precision='bf16x3'))")
+
     def profile(self, enable: bool):
         _lib.check(self.lib.bscnav_vit_profile(self._h, 1 if enable else 0), "vit_profile")
 
@@ -224,6 +281,18 @@ def gemm_f16(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None,
             out.zero_()
     _lib.check(_lib.lib().bscnav_gemm_f16(_lib.ptr(a), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(out), M, N, K, out_mode, act,
                                           _lib.stream_ptr()), "gemm_f16")
+    return out
+
+
+def gemm_bf16x3(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None) -> torch.Tensor:
+    """out = a @ w.T (+bias) from fp32 inputs on the wide-range path: operands split into (hi | lo) bf16 pairs, three tcgen05
+    passes, fp32 out (tests)."""
+    M, K = a.shape
+    N = w.shape[0]
+    a2, w2 = split_bf16(a).contiguous(), split_bf16(w).contiguous()
+    out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    _lib.check(_lib.lib().bscnav_gemm_bf16x3(_lib.ptr(a2), _lib.ptr(w2), _lib.ptr(bias), _lib.ptr(out), M, N, K, _lib.stream_ptr()),
+               "gemm_bf16x3")
     return out
 
 

@@ -216,6 +216,11 @@ typedef struct {
   int32_t head_dim;               /* 0 or 64: dim == heads*64; 80: ViT-H/14 (mma.sync attention) */
   int32_t text_context;           /* 0: image tower; > 0: text tower over this many positions (causal attention,
                                      no patch embedding / cls / registers / pre-LN; image, patch, patch_k_pad unused) */
+  int32_t precision;              /* 0: fp16 operands, fp32 accumulation (throughput path; range guard bscnav_vit_range_status);
+                                     1: wide-range "bf16x3" path: every GEMM operand as a (hi, lo) pair of bf16, three tensor-core
+                                     passes per product, fp32 attention -- fp32 range, ~1e-5 relative error, ~1/3 of the GEMM rate
+                                     (head dim 64 only).  The half blob then holds, per weight matrix [N, K], rows of 2K bf16:
+                                     [hi (K) | lo (K)] (vit.py:pack_weights(..., precision="bf16x3")) */
 } bscnav_vit_cfg_t;
 
 /* Element counts of the two packed weight blobs (layout documented in DESIGN.md / vit.py:pack_weights). */
@@ -227,6 +232,12 @@ int64_t bscnav_vit_workspace_bytes(const bscnav_vit_cfg_t* c, int32_t max_batch)
 int bscnav_vit_create(const bscnav_vit_cfg_t* c, const void* w_half, const float* w_float, void* workspace,
                       int64_t workspace_bytes, int32_t max_batch, void** out_engine);
 void bscnav_vit_destroy(void* engine);
+
+/* Range guard of the fp16 activation path: the GEMM epilogues that write fp16 (qkv, fc1 + activation) set a device flag when a
+ * rounded value is inf / nan, i.e. an activation left the fp16 range (trained ViTs have outlier channels; random-init weights
+ * never do).  Reads the flag into *host_out (1 = overflow seen since the last reset) and synchronises `stream`; reset != 0
+ * clears it.  The Python host raises on 1 instead of storing non-finite tokens. */
+int bscnav_vit_range_status(void* engine, int32_t reset, int32_t* host_out, void* stream);
 
 /* Optional per-kernel timing for the roofline report: when enabled, every launch of the next forward calls is
  * bracketed by CUDA events on the caller's stream.  profile_read synchronises on them and returns, per category
@@ -271,6 +282,10 @@ int bscnav_gaussian_pool(const float* tokens, int32_t batch, int32_t grid, int32
  * tcgen05; out_mode 0: fp16 out, 1: fp16 out with activation `act`, 2: fp32 out += (residual accumulate). */
 int bscnav_gemm_f16(const void* a, const void* w, const float* bias, void* out, int32_t m, int32_t n, int32_t k,
                     int32_t out_mode, int32_t act, void* stream);
+
+/* Stand-alone wide-range GEMM (tests): a [M, 2K] and w [N, 2K] as (hi | lo) bf16 row pairs (hi = bf16(v), lo = bf16(v - hi)),
+ * three tcgen05 passes a_hi w_hi + a_lo w_hi + a_hi w_lo, fp32 out [M, N] = a w^T + bias. */
+int bscnav_gemm_bf16x3(const void* a, const void* w, const float* bias, float* out, int32_t m, int32_t n, int32_t k, void* stream);
 
 /* Stand-alone attention entry (tests/bench): qkv fp16 [batch*T, 3*heads*64] (q pre-scaled by 1/sqrt(64)) ->
  * out fp16 [batch*T, heads*64].  impl 0: mma.sync kernel (any T); impl 1 / 2: first tcgen05 kernels; impl 3: the engine's default

@@ -26,7 +26,7 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(_lib.Geom) == 12 * 4 + 3 * 8 + 27 * 8
     assert ctypes.sizeof(_lib.Store) == 9 * 8
     assert ctypes.sizeof(_lib.Filter) == 8 + 12 + 8 + 4
-    assert ctypes.sizeof(_lib.VitCfg) == 13 * 4
+    assert ctypes.sizeof(_lib.VitCfg) == 14 * 4
 
 
 def test_weight_blob_layout_matches_engine():

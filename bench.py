@@ -268,14 +268,20 @@ def query_leg(store, dev, peak_gbs, with_cpu):
     ms = timed(lambda r: store.query_batch(q[r % 64:r % 64 + 1], k=100, check=False), 40)
     out["single_via_batch_path"] = {"queries_per_s": 1e3 / ms, "ms_per_query": ms,
                                     "path": "one query through the candidate GEMM (reads the fp16 shadow: half the bytes) + exact re-score"}
+    peak_tf = peaks()[0]
     for name, Q, reps in (("batch256", 256, 20), ("batch2048", 2048, 5)):
         ms = timed(lambda r: store.query_batch(q[:Q], k=100, check=False), reps)
-        # shadow rows (fp16) read once per 256-query pass, similarity matrix written once and read twice
+        # algorithmic bytes: the fp16 shadow rows once per 256-query pass + the queries; algorithmic FLOPs: the candidate GEMM.
+        # The pass is bound by whichever is larger at the measured peaks (the GEMM: 137 GFLOP per pass)
         passes = (Q + 255) // 256
-        alg = passes * n * g.dim * 2 + 3 * Q * n * 4
+        alg = passes * n * g.dim * 2 + Q * g.dim * 4
+        flops = 2.0 * Q * n * g.dim
+        t_hbm, t_tc = alg / (peak_gbs * 1e9) * 1e3, flops / (peak_tf * 1e12) * 1e3
         out[name] = {"queries_per_s": Q / (ms / 1e3), "ms_per_call": ms, "algorithmic_GBps": alg / (ms / 1e3) / 1e9,
-                     "frac_of_hbm_peak": alg / (ms / 1e3) / 1e9 / peak_gbs,
-                     "path": "tcgen05 candidate GEMM (fp16 shadow) + histogram select + exact fp32 re-score; device-resident queries"}
+                     "frac_of_hbm_peak": alg / (ms / 1e3) / 1e9 / peak_gbs, "gemm_tflops": flops / (ms / 1e3) / 1e12,
+                     "roofline_floor_ms": max(t_hbm, t_tc), "frac_of_roofline": max(t_hbm, t_tc) / ms,
+                     "path": "tcgen05 candidate GEMM over the fp16 shadow with the selection fused into its epilogue (masked fp16 "
+                             "similarities + per-32-cell maxima), histogram over the maxima, exact fp32 re-score; device-resident queries"}
 
     def e2e_call(r):        # host queries in (pinned), host results out: the call a user of voxel_localized_batch makes
         qd = q_host[:256].to(dev, non_blocking=True)
@@ -538,6 +544,32 @@ def run_ours(args):
             "ms": merge_ms, "rows_exported_per_rank": build_scene.counts, "allgather_bytes_received_per_rank": int(max(build_scene.counts)) * world * rb,
             "slots_after": slots, "what": "export_packed + counts all-gather + ONE packed all-gather (NCCL) + merge_packed, timed alone on the final stores"}}
 
+    # both precisions of the feature extractor: the timed run above is the fp16 throughput path; the same batch
+    # through the wide-range path (split bf16 operands, three tensor-core passes, fp32 attention) for its rate and for the
+    # agreement of the two token sets
+    precision = None
+    if not frames_mode and rank == 0 and args.wide:
+        wide = pkg.ViTEngine(cfg, pkg.random_weights(cfg, seed=0), max_batch=B, device=dev, precision="bf16x3")
+        tok16 = eng.forward_frames(rgb_d[:B])
+        tokw = wide.forward_frames(rgb_d[:B])
+        for _ in range(2):
+            wide.forward_frames(rgb_d[:B], out=tokw)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            wide.forward_frames(rgb_d[:B], out=tokw)
+        e1.record()
+        torch.cuda.synchronize()
+        wms = e0.elapsed_time(e1) / 3
+        precision = {"timed_path": "fp16 operands / fp32 accumulate",
+                     "bf16x3": {"ms_per_batch_vit_only": wms, "vit_frames_per_s": B / (wms / 1e3),
+                                "what": "wide-range parity path: 3 tensor-core passes per product, fp32 attention; 2.4e-5 per-token error vs the fp32 oracle (tests/test_gpu_precision.py)"},
+                     "fp16_vs_bf16x3_max_rel_err_per_token": float(((tok16 - tokw).norm(dim=-1) / tokw.norm(dim=-1)).max()),
+                     "fp16_range_overflow": bool(eng.range_overflow())}
+        del wide, tokw, tok16
+        torch.cuda.empty_cache()
+
     # every rank serves queries over its own scene (BASELINE configs[3]: scenes sharded across GPUs, no collective on the data path)
     query = None
     latency = None
@@ -557,7 +589,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD if args.model == "clip" else WORKLOAD.replace("CLIP ViT-L/14", "DINOv2 ViT-L/14-reg"), **cfg_extra},
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "vit_tflops": roofline["whole_step"]["achieved"] if "whole_step" in roofline else roofline["achieved"],
-            "query": query, "latency_b1": latency, "merge_check": merge_check, **line_extra}
+            "query": query, "latency_b1": latency, "precision": precision, "merge_check": merge_check, **line_extra}
     if world == 1 and not frames_mode and args.cpu_baseline:
         threads = os.cpu_count() or 1
         v, wall, n, text = cpu_dense_rate(1, 0, max(1, npts // max(args.ref_points, 1)), threads, budget_s=60.0)
@@ -623,6 +655,7 @@ if __name__ == "__main__":
     ap.add_argument("--scene-frames", type=int, default=1000)
     ap.add_argument("--no-latency", dest="latency", action="store_false", help="skip the B = 1 obs2voxeltoken latency leg")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-wide", dest="wide", action="store_false", help="skip the wide-range (bf16x3) precision leg")
     a = ap.parse_args()
     if a.batch is None:
         a.batch = 54 if a.model == "clip" else 53

@@ -179,8 +179,7 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     // a bulk tensor reduce-add performed at L2 (one contributor per element per launch: deterministic).
     // MODE is a template parameter and the column loop is not unrolled: the epilogue stays small enough for the
     // instruction cache (an unrolled multi-mode body spent a quarter of its samples in stall_no_inst).
-    constexpr bool kHalfOut = MODE == kOutHalf || MODE == kOutHalfAct;
-    constexpr bool kActMode = MODE == kOutHalfAct || MODE == kOutSplitAct;
+    constexpr bool kHalfOut = MODE == kOutHalf || MODE == kOutHalfAct || MODE == kOutSims;
     constexpr bool kViaTma = kHalfOut || MODE == kOutResidual;
     constexpr int kCols = BN / 2;                        // columns handled by one warp
     constexpr int kIter = kHalfOut ? 64 : 32;            // columns per iteration == one 128-byte TMA box row
@@ -246,6 +245,20 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
             if (MODE == kOutHalfAct) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = act_fn<ACT>(v[j]);
+            }
+            if (MODE == kOutSims) {
+              // batched queries: columns are store cells; cells that take no part become -inf, and the maximum of every
+              // 32-cell block is kept in fp32 (the selection works on these 32x fewer numbers, csrc/query_batch.cu)
+              const uint4* mk = reinterpret_cast<const uint4*>(epi.mask + n0 + 32 * u);
+              const uint4 k0 = __ldg(mk), k1 = __ldg(mk + 1);
+              const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+              float bm = -INFINITY;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (!((kw[j >> 2] >> (8 * (j & 3))) & 0xFFu)) v[j] = -INFINITY;
+                bm = fmaxf(bm, v[j]);
+              }
+              if (in_m) epi.aux[(long long)m * epi.ld_aux + ((n0 + 32 * u) >> 5)] = bm;
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -482,6 +495,7 @@ static int launch_bn(const CUtensorMap* map_a, const CUtensorMap* map_w, const C
     case kOutResidual: return launch_bn_mode<BN, kOutResidual>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream, split);
     case kOutPatchEmbed: return launch_bn_mode<BN, kOutPatchEmbed>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream, split);
     case kOutFloat: return launch_bn_mode<BN, kOutFloat>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream, split);
+    case kOutSims: return launch_bn_mode<BN, kOutSims>(map_a, map_w, map_w_half, map_out, M, N, K, epi, stream, split);
     default: return BSCNAV_EINVAL;
   }
 }
@@ -489,7 +503,7 @@ static int launch_bn(const CUtensorMap* map_a, const CUtensorMap* map_w, const C
 int gemm_f16_launch(const CUtensorMap* map_a, const CUtensorMap* map_w, const CUtensorMap* map_out, int M, int N, int K,
                     const GemmEpilogue& epi, cudaStream_t stream, const CUtensorMap* map_w_half, int split) {
   if (M <= 0 || N <= 0 || K <= 0 || N % 128 != 0 || K % BK != 0 || !epi.out) return BSCNAV_EINVAL;
-  const bool via_tma = epi.mode == kOutHalf || epi.mode == kOutHalfAct || epi.mode == kOutResidual;
+  const bool via_tma = epi.mode == kOutHalf || epi.mode == kOutHalfAct || epi.mode == kOutResidual || epi.mode == kOutSims;
   if (via_tma && !map_out) return BSCNAV_EINVAL;
   if (!map_out) map_out = map_a;       // unused by the direct-store epilogues
   static int use_cluster = -1;

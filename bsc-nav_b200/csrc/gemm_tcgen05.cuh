@@ -22,6 +22,7 @@ enum GemmOut : int {
   kOutPatchEmbed = 3,  // fp32 out[remap(m)] = acc + bias + table[m % np]   (patch embedding + position embedding)
   kOutFloat = 4,       // fp32 out = acc (+ bias)           (similarity matrices; qkv of the wide-range path)
   kOutSplitAct = 5,    // bf16 (hi | lo) out = split(act(acc + bias)): out[m, n] = hi, out[m, N + n] = lo   (wide-range path, fc1)
+  kOutSims = 6,        // fp16 out = mask[n] ? acc : -inf, plus aux[m, n / 32] = max over each 32-column block (batched queries)
 };
 
 struct GemmEpilogue {
@@ -33,6 +34,9 @@ struct GemmEpilogue {
   int act;              // 0 = GELU(erf), 1 = QuickGELU
   int np, tokens, row_off;  // kOutPatchEmbed: out row = (m / np) * tokens + row_off + m % np
   int* range_flag;          // fp16 outputs: set to 1 when a value left the fp16 range (inf / nan after rounding); may be null
+  const uint8_t* mask;      // kOutSims: [N] column participates (0 / 1)
+  float* aux;               // kOutSims: [M, ld_aux] per-row maxima of 32-column blocks (fp32, before the fp16 rounding)
+  long long ld_aux;
 };
 
 // map_out: store map of the output tensor (make_store_map) for the fp16 / residual epilogues; null for the others

@@ -638,6 +638,9 @@ k_topk_decode(const bscnav_geom_t g, const unsigned long long* __restrict__ keys
     if (g.levels == 1) {
       row = cell / g.gs; col = cell - row * g.gs;
       const int slot = occupied[cell];
+      if (C == 1) {
+        h = tok_h[slot];                          // one token per cell: its height is the answer, nothing to re-score
+      } else {
       float best = -INFINITY;
       const float* qv = q + (long long)(q0 + qi) * D;
       float qn = 0.f;
@@ -651,6 +654,7 @@ k_topk_decode(const bscnav_geom_t g, const unsigned long long* __restrict__ keys
         acc = warp_sum(acc);
         const float s = acc / sqrtf(fmaxf(qn * norm2[r], 1e-16f));
         if (s > best) { best = s; h = tok_h[r]; }
+      }
       }
     } else {
       h = cell % g.levels; const int rc = cell / g.levels; row = rc / g.gs; col = rc - row * g.gs;

@@ -11,6 +11,8 @@
 //                  eps = 1.1e-3 of the exact cosine: both operands are rounded once to fp16 (relative 2^-11 each),
 //                  |sum(f^ q^) - cos| <= (2^-10 + 2^-22) sum|f^_i q^_i| <= 9.8e-4 by Cauchy-Schwarz, plus fp32
 //                  accumulation and subnormal terms < 1e-4
+//   (C == 1, the 512 x 512 BEV grid: steps 3-4 run on the GEMM epilogue's per-32-cell block maxima and fp16 similarities instead,
+//    see k_blk_hist / k_blk_select below: the similarity matrix is written once in fp16 and read only where a block opens)
 //   3. histogram   per query, 2048 bins of width 2^-10 over [-1, 1] of the per-cell max of approx (k_batch_hist)
 //   4. select      tb = bin holding the K-th largest approx value; every cell whose bin is >= tb - 3 becomes a
 //                  candidate (k_batch_select).  At least K cells have approx >= edge(tb), hence exact >= edge(tb) - eps;
@@ -93,7 +95,8 @@ k_row_ok(const bscnav_geom_t g, const unsigned long long* __restrict__ row_key, 
          uint8_t* __restrict__ row_ok) {
   const long long r = (long long)blockIdx.x * kMemThreads + threadIdx.x;
   const int C = g.cache;
-  if (r >= (long long)counters[0] * C) return;
+  if (r >= (long long)g.max_slots * C) return;
+  if (r >= (long long)counters[0] * C) { row_ok[r] = 0; return; }        // rows past the slots in use never take part
   const int slot = (int)(r / C);
   bool ok = row_key[r] != BSCNAV_KEY_EMPTY;
   if (ok) {
@@ -249,6 +252,77 @@ k_batch_select(const float* __restrict__ sims, long long ld, const uint8_t* __re
   });
 }
 
+// ---- C == 1 (the 512 x 512 BEV grid): selection over the GEMM epilogue's block maxima.
+// The epilogue (kOutSims) leaves sims16[q, cell] (fp16, -inf where the cell takes no part) and bmax[q, cell / 32] (fp32 maximum of
+// each 32-cell block).  tb = bin of the K-th largest BLOCK maximum: K distinct blocks each hold a cell >= their maximum, so at
+// least K cells have approx >= edge(tb) and the K-th exact similarity is >= edge(tb) - eps.  A cell is dropped when its block's
+// maximum or its own fp16 value lies below bin tb - 3; then approx < edge(tb) - 3 * 2^-10 + 2^-11 (fp16 rounding of the stored
+// value), exact < edge(tb) - 2.93e-3 + 4.9e-4 + eps < edge(tb) - eps for eps = 1.1e-3: it cannot belong to the exact top-K.
+// The full similarity matrix is written once (fp16) and read only where a block opens; the histogram reads 1/32 of it.
+static constexpr int kBlkChunk = 2048;       // block maxima per thread block in the two passes below
+
+__global__ void __launch_bounds__(kMemThreads)
+k_blk_hist(const float* __restrict__ bmax, long long ld, int n_blk, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t h[kBins];
+  const int qi = blockIdx.y;
+  const int b0 = blockIdx.x * kBlkChunk;
+  for (int b = threadIdx.x; b < kBins; b += kMemThreads) h[b] = 0;
+  __syncthreads();
+  const float* bq = bmax + (long long)qi * ld;
+  float v[kBlkChunk / kMemThreads];
+#pragma unroll
+  for (int i = 0; i < kBlkChunk / kMemThreads; ++i) {
+    const int b = b0 + i * kMemThreads + threadIdx.x;
+    v[i] = b < n_blk ? bq[b] : -INFINITY;
+  }
+#pragma unroll
+  for (int i = 0; i < kBlkChunk / kMemThreads; ++i)
+    if (v[i] > -INFINITY) atomicAdd(&h[sim_bin(v[i])], 1u);      // NaN fails the comparison: takes no part
+  __syncthreads();
+  for (int b = threadIdx.x; b < kBins; b += kMemThreads)
+    if (h[b]) atomicAdd(&hist[(long long)qi * kBins + b], h[b]);
+}
+
+// one block per query: the threshold bin, once (every select block used to re-derive it from the 8 KB histogram)
+__global__ void __launch_bounds__(kMemThreads)
+k_blk_threshold(const uint32_t* __restrict__ hist, int k, int32_t* __restrict__ thr) {
+  uint32_t n_sel;
+  const int t = threshold_bin(hist + (long long)blockIdx.x * kBins, k, kMarginBins, &n_sel);
+  if (threadIdx.x == 0) thr[blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(kMemThreads)
+k_blk_select(const __half* __restrict__ sims16, long long ld, const float* __restrict__ bmax, long long ld_b, int n_blk,
+             const int32_t* __restrict__ thr, int32_t* __restrict__ cand, int32_t* __restrict__ cand_count,
+             int32_t* __restrict__ overflow) {
+  const int qi = blockIdx.y;
+  const int b0 = blockIdx.x * kBlkChunk;
+  const int t = thr[qi];
+  const float* bq = bmax + (long long)qi * ld_b;
+  const __half* sq = sims16 + (long long)qi * ld;
+  for (int i = threadIdx.x; i < kBlkChunk; i += kMemThreads) {
+    const int b = b0 + i;
+    if (b >= n_blk) break;
+    const float bm = bq[b];
+    if (!(bm > -INFINITY) || sim_bin(bm) < t) continue;
+    const uint4* p = reinterpret_cast<const uint4*>(sq + (long long)b * 32);        // the block's 32 fp16 similarities
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 u = p[c];
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float sv = __half2float(__ushort_as_half((unsigned short)(w[e >> 1] >> (16 * (e & 1)))));
+        if (sv > -INFINITY && sim_bin(sv) >= t) {
+          const int pos = atomicAdd(&cand_count[qi], 1);
+          if (pos < kCandCap) cand[(long long)qi * kCandCap + pos] = b * 32 + c * 8 + e;
+          else overflow[qi] = pos + 1;
+        }
+      }
+    }
+  }
+}
+
 // ---- the same two stages over exact composite keys (single-query path, bscnav_query_topk): the bins are a monotone function of
 // the similarity, so every key in a bin at or above the k-th key's bin is kept and the sort of those few keys is exact
 __device__ __forceinline__ int key_bin(unsigned long long key) { return sim_bin(from_orderable(~(uint32_t)(key >> 32))); }
@@ -369,7 +443,7 @@ __global__ void k_mark_overflow(const int32_t* __restrict__ overflow, int n_quer
 }
 
 struct BatchScratch {
-  __half* qh; float* qn2; uint8_t* row_ok; float* sims; uint32_t* hist; int32_t* cand_count; int32_t* overflow;
+  __half* qh; float* qn2; uint8_t* row_ok; float* sims; float* bmax; uint32_t* hist; int32_t* cand_count; int32_t* overflow; int32_t* thr;
   int32_t* cand; unsigned long long* keys; unsigned long long* sorted;
 };
 static long long batch_rows(const bscnav_geom_t* g, long long n_rows_hint) {
@@ -385,10 +459,12 @@ static int64_t batch_layout(const bscnav_geom_t* g, int n_query, int k, long lon
   p = take(align_up(P, 128) * g->dim * 2); if (s) s->qh = reinterpret_cast<__half*>(p);
   p = take(P * 4); if (s) s->qn2 = reinterpret_cast<float*>(p);
   p = take((long long)g->max_slots * g->cache); if (s) s->row_ok = reinterpret_cast<uint8_t*>(p);
-  p = take(P * N * 4); if (s) s->sims = reinterpret_cast<float*>(p);
+  p = take(P * N * (g->cache == 1 ? 2 : 4)); if (s) s->sims = reinterpret_cast<float*>(p);      // C == 1: fp16 similarities
+  p = take(g->cache == 1 ? align_up(P, 128) * (N / 32) * 4 : 0); if (s) s->bmax = reinterpret_cast<float*>(p);
   p = take(P * kBins * 4); if (s) s->hist = reinterpret_cast<uint32_t*>(p);
   p = take(P * 4); if (s) s->cand_count = reinterpret_cast<int32_t*>(p);
   p = take(P * 4); if (s) s->overflow = reinterpret_cast<int32_t*>(p);
+  p = take(P * 4); if (s) s->thr = reinterpret_cast<int32_t*>(p);
   p = take(P * kCandCap * 4); if (s) s->cand = reinterpret_cast<int32_t*>(p);
   p = take(P * kCandCap * 8); if (s) s->keys = reinterpret_cast<unsigned long long*>(p);
   p = take(P * (long long)k * 8); if (s) s->sorted = reinterpret_cast<unsigned long long*>(p);
@@ -467,25 +543,42 @@ int bscnav_query_topk_batch(const bscnav_geom_t* g, const bscnav_store_t* st, co
   const int slot_blocks = (int)((N / C + kSelSlots - 1) / kSelSlots);
   BSC_LAUNCH(k_row_ok, (unsigned)((cap_rows + kMemThreads - 1) / kMemThreads), kMemThreads, 0, stream, *g,
              reinterpret_cast<const unsigned long long*>(st->row_key), st->slot_cell, st->tok_h, st->counters, flt, s.row_ok);
-  CUtensorMap map_w;
+  CUtensorMap map_w, map_wh;
   if (int e = make_operand_map(&map_w, shadow, N, D, gemm_block_n((int)N))) return e;
+  if (int e = make_operand_map(&map_wh, shadow, N, D, 128)) return e;          // 128-row boxes: the CTA-pair GEMM (N % 256 == 0)
   for (int q0 = 0; q0 < n_query; q0 += kPassQueries) {
     const int P = n_query - q0 < kPassQueries ? n_query - q0 : kPassQueries;
     const float* qp = q + (long long)q0 * D;
     BSC_LAUNCH(k_prep_queries, (P + kMemThreads / 32 - 1) / (kMemThreads / 32), kMemThreads, 0, stream, qp, P, D, s.qh, s.qn2);
     CUtensorMap map_a;
     if (int e = make_operand_map(&map_a, s.qh, align_up(P, 128), D, 128)) return e;   // rows past P: never stored (M = P)
-    GemmEpilogue epi{};
-    epi.out = s.sims; epi.bias = nullptr; epi.table = nullptr; epi.ld_out = N; epi.mode = kOutFloat; epi.act = 0;
-    if (int e = gemm_f16_launch(&map_a, &map_w, nullptr, P, (int)N, D, epi, stream)) return e;
     BSC_CUDA(cudaMemsetAsync(s.hist, 0, (size_t)P * kBins * 4, stream));
     BSC_CUDA(cudaMemsetAsync(s.cand_count, 0, (size_t)P * 4, stream));
     BSC_CUDA(cudaMemsetAsync(s.overflow, 0, (size_t)P * 4, stream));
     BSC_CUDA(cudaMemsetAsync(s.keys, 0xFF, (size_t)P * kCandCap * 8, stream));       // BSCNAV_KEY_EMPTY
-    BSC_LAUNCH(k_batch_hist, dim3((unsigned)slot_blocks, (unsigned)P), kMemThreads, 0, stream, s.sims, N, s.row_ok, st->counters, C,
-               s.hist);
-    BSC_LAUNCH(k_batch_select, dim3((unsigned)slot_blocks, (unsigned)P), kMemThreads, 0, stream, s.sims, N, s.row_ok, st->counters,
-               C, s.hist, k, s.cand, s.cand_count, s.overflow);
+    GemmEpilogue epi{};
+    epi.out = s.sims; epi.ld_out = N;
+    if (C == 1) {
+      // selection fused into the GEMM: masked fp16 similarities + fp32 block maxima from the epilogue, histogram over the maxima
+      // (1/32 of the matrix), blocks opened only where a candidate can be
+      const int n_blk = (int)(N / 32);
+      CUtensorMap map_o;
+      if (int e = make_store_map(&map_o, s.sims, P, N, false)) return e;                   // rows past P are clipped by the map
+      epi.mode = kOutSims; epi.mask = s.row_ok; epi.aux = s.bmax; epi.ld_aux = n_blk;
+      if (int e = gemm_f16_launch(&map_a, &map_w, &map_o, P, (int)N, D, epi, stream, &map_wh)) return e;
+      const unsigned blk_blocks = (unsigned)((n_blk + kBlkChunk - 1) / kBlkChunk);
+      BSC_LAUNCH(k_blk_hist, dim3(blk_blocks, (unsigned)P), kMemThreads, 0, stream, s.bmax, (long long)n_blk, n_blk, s.hist);
+      BSC_LAUNCH(k_blk_threshold, (unsigned)P, kMemThreads, 0, stream, s.hist, k, s.thr);
+      BSC_LAUNCH(k_blk_select, dim3(blk_blocks, (unsigned)P), kMemThreads, 0, stream, reinterpret_cast<const __half*>(s.sims), N,
+                 s.bmax, (long long)n_blk, n_blk, s.thr, s.cand, s.cand_count, s.overflow);
+    } else {
+      epi.mode = kOutFloat;
+      if (int e = gemm_f16_launch(&map_a, &map_w, nullptr, P, (int)N, D, epi, stream)) return e;
+      BSC_LAUNCH(k_batch_hist, dim3((unsigned)slot_blocks, (unsigned)P), kMemThreads, 0, stream, s.sims, N, s.row_ok, st->counters, C,
+                 s.hist);
+      BSC_LAUNCH(k_batch_select, dim3((unsigned)slot_blocks, (unsigned)P), kMemThreads, 0, stream, s.sims, N, s.row_ok, st->counters,
+                 C, s.hist, k, s.cand, s.cand_count, s.overflow);
+    }
     BSC_LAUNCH(k_batch_rescore, dim3(16, (unsigned)P), kMemThreads, 0, stream, *g, st->feat, st->norm2, s.row_ok, st->slot_cell, qp,
                s.qn2, s.cand, s.cand_count, s.overflow, s.keys);
     BSC_LAUNCH(k_sort_candidates, (unsigned)P, 1024, 0, stream, s.keys, s.cand_count, s.overflow, k, s.sorted);

@@ -2,10 +2,10 @@
 
 The reference keeps tokens in an HDF5 file (`feat.h5df`, one group `grid_{row}_{col}_{h}` per voxel with datasets
 `features (M, D) f32` and `distances (M,) f32`, memory_2.py:335-354).  The device store is persisted natively as flat arrays
-next to the reference's files; `export_h5` / `import_h5` write and read the reference's HDF5 layout through `h5py` when that
-module is importable (it is not part of this image: the functions take the module as an argument, the tests pass the oracle's
-in-memory stand-in), so memories built by either side can be loaded by the other.  `load_single_floor` floor detection
-(memory_2.py:202-256) is host logic over a handful of heights and lives here too.
+next to the reference's files; `export_h5` / `import_h5` write and read the reference's HDF5 layout -- through `h5py` when it is
+importable, else through the package's own reader / writer of that file family (`h5lite.py`; h5py is not part of this image) --
+so memories built by either side can be loaded by the other.  `load_single_floor` floor detection (memory_2.py:202-256) is host
+logic over a handful of heights and lives here too.
 """
 from __future__ import annotations
 
@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 
-def save_memory(mem, path: str):
+def save_memory(mem, path: str, write_h5: bool = True):
     os.makedirs(path, exist_ok=True)
     st = mem.store
     n = st.count()
@@ -37,9 +37,6 @@ def save_memory(mem, path: str):
         grid_rgb, weight = np.zeros((n, 3), np.uint8), np.zeros(n, np.float32)
     np.save(path + "/grid_rgb.npy", grid_rgb)
     np.save(path + "/weight.npy", weight)
-    h5 = _h5py()
-    if h5 is not None and g.levels > 1:
-        export_h5(mem, path, h5)
     with open(path + "/long_memory.json", "w") as f:
         json.dump(mem.long_memory_dict, f, indent=4)
     rows = n * g.cache
@@ -47,15 +44,22 @@ def save_memory(mem, path: str):
     np.save(path + "/bscnav_row_key.npy", st.row_key[:rows].cpu().numpy().view(np.uint64))
     np.save(path + "/bscnav_tok_h.npy", st.tok_h[:rows].cpu().numpy())
     np.save(path + "/bscnav_feat.npy", st.feat[:rows].cpu().numpy())
+    if getattr(mem, "colour", False):
+        np.save(path + "/bscnav_cv_key.npy", st.cv_key.cpu().numpy().view(np.uint64))     # max_height + its ordinal (memory_2.py:901-903)
     np.save(path + "/bscnav_meta.npy", np.array([g.gs, g.levels, g.cache, g.dim, st.next_ordinal], dtype=np.int64))
+    # the reference's token file last: a failure here leaves a complete native directory behind
+    if g.levels > 1 and write_h5:
+        export_h5(mem, path, _h5())
 
 
-def _h5py():
+def _h5():
+    """The HDF5 module: h5py when importable, else the package's own implementation of the same file family."""
     try:
         import h5py
         return h5py
     except ImportError:
-        return None
+        from . import h5lite
+        return h5lite
 
 
 def export_h5(mem, path: str, h5):
@@ -64,7 +68,8 @@ def export_h5(mem, path: str, h5):
     g = st.g
     if g.levels == 1:
         raise ValueError("the HDF5 layout is keyed by voxel (row, col, h): not defined for a BEV-keyed store")
-    with h5.File(os.path.join(path, "feat.h5df"), "a") as f:
+    # 'w': the file is rewritten as a whole (saving twice into the same directory must not fail on existing groups)
+    with h5.File(os.path.join(path, "feat.h5df"), "w") as f:
         for key, items in st.snapshot().items():
             name = f"grid_{key[0]}_{key[1]}_{key[2]}"
             feats = np.stack([t[3] for t in items]).astype(np.float32)
@@ -89,14 +94,25 @@ def import_h5(mem, path: str, h5):
     C_, D = g.cache, g.dim
     cells, rows_feat, rows_key, rows_h, slots = [], [], [], [], []
     ordinal = 0
+    pos = np.load(path + "/grid_rgb_pos.npy") if os.path.exists(path + "/grid_rgb_pos.npy") else None
     with h5.File(os.path.join(path, "feat.h5df"), "r") as f:
-        names = list(f.keys())
+        names = [nm for nm in f.keys() if nm.startswith("grid_")]
+        # the reference numbers a voxel even when its token was dropped at a buffer flush (memory_2.py:880-894): slots can outnumber
+        # the groups.  Size by the largest slot number in sight; slots without a group stay empty (keys KEY_EMPTY), their cell comes
+        # from grid_rgb_pos.npy
         n = len(names)
+        if occ is not None and occ.max() >= 0:
+            n = max(n, int(occ.max()) + 1)
+        if os.path.exists(path + "/max_id.npy"):
+            n = max(n, int(np.load(path + "/max_id.npy")))
         feat = np.zeros((n * C_, D), np.float32)
         row_key = np.full(n * C_, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)
         tok_h = np.zeros(n * C_, np.int32)
-        slot_cell = np.zeros(n, np.int32)
-        next_slot = 0
+        slot_cell = np.full(n, -1, np.int32)
+        next_slot = int(occ.max()) + 1 if occ is not None and occ.max() >= 0 else 0
+        if pos is not None:
+            m = min(len(pos), n)
+            slot_cell[:m] = (pos[:m, 0].astype(np.int64) * g.gs + pos[:m, 1]) * g.levels + pos[:m, 2]
         for name in names:
             row, col, h = (int(v) for v in name.split("_")[1:4])
             feats = np.asarray(f[name]["features"][:], dtype=np.float32)
@@ -118,6 +134,8 @@ def import_h5(mem, path: str, h5):
     n_slots = next_slot
     if n_slots > g.max_slots:
         raise ValueError(f"{n_slots} voxels exceed the store capacity {g.max_slots}")
+    if (slot_cell[:n_slots] < 0).any():
+        raise ValueError("a slot has neither a token group nor a position in grid_rgb_pos.npy")
     dev = st.device
     rows = n_slots * C_
     st.slot_cell[:n_slots] = torch.from_numpy(slot_cell[:n_slots]).to(dev)
@@ -201,11 +219,9 @@ def load_memory(mem, path: str):
     g = st.g
     if not os.path.exists(path + "/bscnav_meta.npy"):
         # a directory written by the reference: tokens live in feat.h5df
-        h5 = _h5py()
-        if h5 is None or not os.path.exists(path + "/feat.h5df"):
-            raise FileNotFoundError(f"{path}: neither the native token arrays (bscnav_*.npy) nor a readable feat.h5df "
-                                    "(h5py is needed to read a memory written by the reference)")
-        import_h5(mem, path, h5)
+        if not os.path.exists(path + "/feat.h5df"):
+            raise FileNotFoundError(f"{path}: neither the native token arrays (bscnav_*.npy) nor the reference's feat.h5df")
+        import_h5(mem, path, _h5())
         _load_side_files(mem, path)
         return
     meta = np.load(path + "/bscnav_meta.npy")
@@ -232,8 +248,37 @@ def load_memory(mem, path: str):
     _load_side_files(mem, path)
 
 
+def _load_colour(mem, path: str):
+    """grid_rgb / weight / cv_map of a saved memory back into the device arrays (the reference restores them, memory_2.py:191-193);
+    continued fusing then treats the loaded voxels as initialised (counters[2]) instead of re-initialising their colour."""
+    st = mem.store
+    if st.col is None or not os.path.exists(path + "/grid_rgb.npy"):
+        return
+    n = st.count()
+    rgb, wgt = np.load(path + "/grid_rgb.npy"), np.load(path + "/weight.npy")
+    m = min(n, len(rgb), len(wgt))
+    st.grid_rgb[:m] = torch.from_numpy(np.ascontiguousarray(rgb[:m]).astype(np.uint8)).to(st.device)
+    st.weight[:m] = torch.from_numpy(np.ascontiguousarray(wgt[:m]).astype(np.float32)).to(st.device)
+    if os.path.exists(path + "/cv_map.npy"):
+        st.cv_map.copy_(torch.from_numpy(np.load(path + "/cv_map.npy").astype(np.uint8)).to(st.device))
+    if os.path.exists(path + "/bscnav_cv_key.npy"):
+        st.cv_key.copy_(torch.from_numpy(np.load(path + "/bscnav_cv_key.npy").view(np.int64)).to(st.device))
+    else:
+        # a reference directory has no per-column key: rebuild max_height from the voxel positions (highest h per column); the
+        # ordinal part is 0, so the next point at the same height replaces the colour, as `>=` does in the reference (:901)
+        pos = st.positions().astype(np.int64)
+        key = np.zeros(st.g.gs * st.g.gs, dtype=np.uint64)
+        np.maximum.at(key, pos[:, 0] * st.g.gs + pos[:, 1], (pos[:, 2].astype(np.uint64) << np.uint64(32)) + np.uint64(1))
+        st.cv_key.copy_(torch.from_numpy(key.view(np.int64)).to(st.device))
+    st.counters[2] = m
+
+
 def _load_side_files(mem, path: str):
-    mem.minh, mem.maxh = [int(v) for v in np.load(path + "/map_height.npy")]
+    saved = [int(v) for v in np.load(path + "/map_height.npy")]
+    if (saved[0], saved[1]) != (mem.minh, mem.maxh):
+        raise ValueError(f"memory at {path} was built with height range {tuple(saved)} cells, this memory uses "
+                         f"{(mem.minh, mem.maxh)} (floor_height / map_height / cell_size differ)")
+    _load_colour(mem, path)
     if os.path.exists(path + "/long_memory.json"):
         with open(path + "/long_memory.json") as f:
             mem.long_memory_dict = json.load(f)

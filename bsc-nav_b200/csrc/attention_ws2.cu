@@ -138,11 +138,13 @@ __device__ __forceinline__ void w2_mma_16816(float* c, uint32_t a0, uint32_t a1,
 // byte offset of 16-byte chunk `chunk` of row `row` in a TMA 128-byte-swizzled [row][64 fp16] tile
 __device__ __forceinline__ uint32_t w2_sw_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
 
-// key split: first half a multiple of 32 (so 32-column softmax chunks tile it exactly), both halves >= 16
+// key split: both halves multiples of 16 (one P V step), both >= 16.  The second half carries the masked tail chunk (keys >= T), so
+// the first half takes the odd 16 keys: 272 keys -> 144 + 128 (measured against 128 + 144: the b pipeline was the longer loop)
 __host__ __device__ inline int w2_split(int Tk) {
   if (Tk <= 32) return 16;
-  int ka = ((Tk / 2) + 31) & ~31;
-  return ka > 128 ? 128 : ka;
+  int ka = ((Tk / 2) + 15) & ~15;
+  if ((Tk - ka) % 32 && ka + 16 < Tk) ka += 16;        // keep the second half in whole 32-key chunks when possible
+  return ka > 160 ? 160 : ka;
 }
 // query tiling: rows past the last full tile go to the tail warps when there are few of them
 __host__ __device__ inline int w2_tiles(int T, bool* tail) {

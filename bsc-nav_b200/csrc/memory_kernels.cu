@@ -45,13 +45,33 @@ __device__ __forceinline__ int trunc_i32(double v) {
   return (int)v;
 }
 
+// int(x / cs) of utils.py:201-205 without the IEEE division on the common path: t = x * (1 / cs) differs from the correctly
+// rounded quotient by at most 3 ulp, so unless t lies within 8 ulp (|t| 2^-49) of an integer both truncate to the same value;
+// next to an integer the exact division decides.  Verified against division + truncation on 10^8 inputs including planted
+// cell boundaries (tools/micro/div_trunc_check.py, tests/test_kernel_arith_emulation.py).
+__device__ __forceinline__ int trunc_div_cs(double x, double cs, double rcs) {
+  const double t = __dmul_rn(x, rcs);
+  if (fabs(t - rint(t)) > fabs(t) * 0x1p-49) return trunc_i32(t);
+  return trunc_i32(__ddiv_rn(x, cs));
+}
+// int(q0 / q2 - 0.5) of project_point (utils.py:208-213) with one reciprocal r = 1 / q2 shared by both coordinates; same guard
+__device__ __forceinline__ int trunc_quot_half(double q0, double q2, double r) {
+  const double t = __dmul_rn(q0, r);
+  const double u = __dsub_rn(t, 0.5);
+  if (fabs(u - rint(u)) > fmax(fabs(t), 1.0) * 0x1p-48) return trunc_i32(u);
+  return trunc_i32(__dsub_rn(__ddiv_rn(q0, q2), 0.5));
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // K1: unproject + pose + voxel index + patch projection + winner key.          (a3-a7 of SURVEY 8a)
+// fresh[i / 32] bit i % 32 = point i heads a run of points on a cell that has no slot yet: only these points can be the first
+// toucher of a new cell, so the slot-assignment passes read this 1-bit-per-point mask (2 MB per 54-frame batch) and open the
+// 16-byte record of a point only where its bit is set, instead of streaming all 270 MB of records twice.
 __global__ void __launch_bounds__(kThreads)
-k_index_points(const bscnav_geom_t g, const float* __restrict__ depth, const double* __restrict__ poses,
+k_index_points(const bscnav_geom_t g, const double rcs, const float* __restrict__ depth, const double* __restrict__ poses,
                const uint32_t* __restrict__ ord_base, const int32_t* __restrict__ sample_idx, int n_points,
                long long total, uint4* __restrict__ rec, const int32_t* __restrict__ occupied,
-               uint32_t* __restrict__ first_touch) {
+               uint32_t* __restrict__ first_touch, uint32_t* __restrict__ fresh) {
   const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
   const int lane = threadIdx.x & 31;
   int cell = -1;
@@ -76,16 +96,17 @@ k_index_points(const bscnav_geom_t g, const float* __restrict__ depth, const dou
       const double gz = dot4(M + 8, p0, p1, p2, 1.0);
       const double half = (double)g.gs / 2.0;
       // utils.py:201-205  row = int(gs/2 - int(x/cs)) ...
-      const int row = trunc_i32(__dsub_rn(half, (double)trunc_i32(__ddiv_rn(gx, g.cs))));
-      const int col = trunc_i32(__dsub_rn(half, (double)trunc_i32(__ddiv_rn(gy, g.cs))));
-      const int h = trunc_i32(__ddiv_rn(gz, g.cs));
+      const int row = trunc_i32(__dsub_rn(half, (double)trunc_div_cs(gx, g.cs, rcs)));
+      const int col = trunc_i32(__dsub_rn(half, (double)trunc_div_cs(gy, g.cs, rcs)));
+      const int h = trunc_div_cs(gz, g.cs, rcs);
       const bool out = col >= g.gs || row >= g.gs || h >= g.maxh || col < 0 || row < 0 || h < g.minh;  // memory_2.py:755-756
       if (!out) {
         // utils.py:208-214 with the patch intrinsics (memory_2.py:857,871)
         const double q0 = dot3(g.kpatch + 0, p0, p1, p2), q1 = dot3(g.kpatch + 3, p0, p1, p2),
                      q2 = dot3(g.kpatch + 6, p0, p1, p2);
-        const int ppx = trunc_i32(__dsub_rn(__ddiv_rn(q0, q2), 0.5));
-        const int ppy = trunc_i32(__dsub_rn(__ddiv_rn(q1, q2), 0.5));
+        const double rq = __drcp_rn(q2);
+        const int ppx = trunc_quot_half(q0, q2, rq);
+        const int ppy = trunc_quot_half(q1, q2, rq);
         if (!(ppx < 0 || ppy < 0 || ppx >= g.n_patch_h || ppy >= g.n_patch_w)) {   // memory_2.py:878 (token array is (W', H', D))
           const int hh = h - g.minh;                                               // memory_2.py:867
           cell = (g.levels == 1) ? row * g.gs + col : (row * g.gs + col) * g.levels + hh;
@@ -102,7 +123,10 @@ k_index_points(const bscnav_geom_t g, const float* __restrict__ depth, const dou
   // first-touch ordinal of still-unassigned cells; within a warp only the head of a run of equal cells issues
   // the atomic (ordinals ascend with the lane, so the head holds the run's minimum)
   const int prev = __shfl_up_sync(0xffffffffu, cell, 1);
-  if (cell >= 0 && (lane == 0 || prev != cell) && occupied[cell] < 0) atomicMin(&first_touch[cell], ord);
+  const bool fresh_head = cell >= 0 && (lane == 0 || prev != cell) && occupied[cell] < 0;
+  if (fresh_head) atomicMin(&first_touch[cell], ord);
+  const unsigned fm = __ballot_sync(0xffffffffu, fresh_head);
+  if (lane == 0 && i < total) fresh[i >> 5] = fm;
 }
 
 // block-wide exclusive scan of one int per thread (kThreads threads); returns exclusive prefix, total via *sum
@@ -142,52 +166,79 @@ __device__ __forceinline__ bool is_first_toucher(const uint4& r, const int32_t* 
 }
 
 // K2a: number of newly touched cells per 1024-point tile (a point is the "first toucher" of an unassigned cell)
+// the four mask bits of a thread's points (kItems consecutive points from `base`, a multiple of 4); null mask: every point
+__device__ __forceinline__ unsigned fresh_bits(const uint32_t* __restrict__ fresh, long long base) {
+  return fresh ? (fresh[base >> 5] >> (base & 31)) & 0xFu : 0xFu;
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_count_new(const uint4* __restrict__ rec, long long total, const int32_t* __restrict__ occupied,
-            const uint32_t* __restrict__ first_touch, int* __restrict__ tile_count) {
+            const uint32_t* __restrict__ first_touch, int* __restrict__ tile_count, const uint32_t* __restrict__ fresh) {
+  static_assert(kItems == 4, "fresh_bits extracts four bits per thread");
   const long long base = (long long)blockIdx.x * kTile + threadIdx.x * kItems;
+  const unsigned bits = fresh_bits(fresh, base);
   int c = 0;
 #pragma unroll
   for (int k = 0; k < kItems; ++k)
-    if (base + k < total) c += is_first_toucher(rec[base + k], occupied, first_touch) ? 1 : 0;
+    if (((bits >> k) & 1u) && base + k < total) c += is_first_toucher(rec[base + k], occupied, first_touch) ? 1 : 0;
   int tot;
   block_excl_scan(c, &tot);
   if (threadIdx.x == 0) tile_count[blockIdx.x] = tot;
 }
 
-// K2b: exclusive scan of the tile counts (single block), slot-range reservation, capacity check
-__global__ void __launch_bounds__(kThreads)
+// K2b: exclusive scan of the tile counts (single block), slot-range reservation, capacity check.
+// One block of 1024 threads, every thread owns a contiguous run of tiles: two serial passes over the run around one block-wide
+// scan of the 1024 partial sums (a loop of 256-wide block scans took 57 us for the 16 500 tiles of a 54-frame batch).
+static constexpr int kScanThreads = 1024;
+__global__ void __launch_bounds__(kScanThreads)
 k_scan_tiles(const int* __restrict__ tile_count, int* __restrict__ tile_off, int n_tiles, int* __restrict__ hdr,
              int32_t* __restrict__ counters, int max_slots) {
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
+  __shared__ int warp_tot[kScanThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int per = (n_tiles + kScanThreads - 1) / kScanThreads;
+  const int t0 = tid * per, t1 = min(t0 + per, n_tiles);
+  int sum = 0;
+  for (int t = t0; t < t1; ++t) sum += tile_count[t];
+  int inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) warp_tot[w] = inc;
   __syncthreads();
-  for (int base = 0; base < n_tiles; base += kThreads) {
-    const int idx = base + threadIdx.x;
-    const int v = idx < n_tiles ? tile_count[idx] : 0;
-    int tot;
-    const int ex = block_excl_scan(v, &tot);
-    if (idx < n_tiles) tile_off[idx] = carry + ex;
-    __syncthreads();
-    if (threadIdx.x == 0) carry += tot;
-    __syncthreads();
+  if (w == 0) {
+    const int v = warp_tot[lane];
+    int vi = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, vi, o);
+      if (lane >= o) vi += u;
+    }
+    warp_tot[lane] = vi - v;                      // exclusive prefix of the warp totals
+    if (lane == 31) {
+      const int total = vi;
+      const int base_slot = counters[0];
+      const bool ok = (long long)base_slot + total <= (long long)max_slots;
+      hdr[0] = base_slot;
+      hdr[1] = ok ? 1 : 0;
+      if (ok) counters[0] = base_slot + total; else counters[1] = 1;   // overflow: nothing from this batch is assigned
+    }
   }
-  if (threadIdx.x == 0) {
-    const int base_slot = counters[0];
-    const bool ok = (long long)base_slot + carry <= (long long)max_slots;
-    hdr[0] = base_slot;
-    hdr[1] = ok ? 1 : 0;
-    if (ok) counters[0] = base_slot + carry; else counters[1] = 1;   // overflow: nothing from this batch is assigned
-  }
+  __syncthreads();
+  int run = warp_tot[w] + inc - sum;
+  for (int t = t0; t < t1; ++t) { tile_off[t] = run; run += tile_count[t]; }
 }
 
 // K2c: slots in first-touch order == the reference's sequential numbering (memory_2.py:888-894)
 __global__ void __launch_bounds__(kThreads)
 k_assign_slots(const uint4* __restrict__ rec, long long total, int32_t* __restrict__ occupied,
                const uint32_t* __restrict__ first_touch, const int* __restrict__ tile_off,
-               const int* __restrict__ hdr, int32_t* __restrict__ slot_cell) {
-  if (!hdr[1]) return;
+               const int* __restrict__ hdr, int32_t* __restrict__ slot_cell, const uint32_t* __restrict__ fresh,
+               const int* __restrict__ tile_count) {
+  if (!hdr[1] || tile_count[blockIdx.x] == 0) return;
   const long long base = (long long)blockIdx.x * kTile + threadIdx.x * kItems;
+  const unsigned bits = fresh_bits(fresh, base);
   bool f[kItems];
   int cells[kItems];
   int c = 0;
@@ -195,7 +246,7 @@ k_assign_slots(const uint4* __restrict__ rec, long long total, int32_t* __restri
   for (int k = 0; k < kItems; ++k) {
     f[k] = false;
     cells[k] = -1;
-    if (base + k < total) {
+    if (((bits >> k) & 1u) && base + k < total) {
       const uint4 r = rec[base + k];
       f[k] = is_first_toucher(r, occupied, first_touch);
       cells[k] = (int)r.x;
@@ -220,12 +271,18 @@ k_assign_slots(const uint4* __restrict__ rec, long long total, int32_t* __restri
 // K3: top-C winner selection.  C == 1: warp-segmented min then one 64-bit atomicMin per run of equal cells.
 // C > 1: lock-free sorted insertion -- offer the key to slot position 0..C-1 with atomicMin and carry the
 // displaced key forward; position j ends up holding the (j+1)-th smallest key whatever the arrival order.
+// Every key that is offered to the store is also written, compacted per block, into the block's own segment of a candidate
+// array {slot, aux, key} (no global counter: one contended atomic per warp cost 100 us): the commit pass then looks at these few
+// entries instead of re-reading the whole record array (16 B x 16.6 M points per 54-frame batch).
 __global__ void __launch_bounds__(kThreads)
 k_select(const uint4* __restrict__ rec, long long total, const int32_t* __restrict__ occupied,
-         uint32_t* __restrict__ first_touch, unsigned long long* __restrict__ slot_keys, int C) {
+         uint32_t* __restrict__ first_touch, unsigned long long* __restrict__ slot_keys, int C,
+         uint4* __restrict__ cand, int* __restrict__ cand_n) {
+  __shared__ int warp_off[kThreads / 32 + 1];
   const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
   const int lane = threadIdx.x & 31;
   int cell = -1, slot = -1;
+  uint32_t aux = 0;
   unsigned long long key = BSCNAV_KEY_EMPTY;
   if (i < total) {
     const uint4 r = rec[i];
@@ -234,71 +291,85 @@ k_select(const uint4* __restrict__ rec, long long total, const int32_t* __restri
       first_touch[cell] = kNoTouch;      // restore the scratch invariant for the next batch
       slot = occupied[cell];             // < 0 only after a capacity overflow
       key = rec_key(r);
+      aux = r.y;
     }
   }
+  bool offered = false;
   if (C == 1) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const unsigned long long k2 = __shfl_down_sync(0xffffffffu, key, d);
       const int c2 = __shfl_down_sync(0xffffffffu, cell, d);
-      if (lane + d < 32 && c2 == cell && k2 < key) key = k2;
+      const uint32_t a2 = __shfl_down_sync(0xffffffffu, aux, d);
+      if (lane + d < 32 && c2 == cell && k2 < key) { key = k2; aux = a2; }
     }
     const int prev = __shfl_up_sync(0xffffffffu, cell, 1);
-    if (slot >= 0 && (lane == 0 || prev != cell) && key < slot_keys[slot]) atomicMin(&slot_keys[slot], key);
+    if (slot >= 0 && (lane == 0 || prev != cell) && key < slot_keys[slot]) {
+      atomicMin(&slot_keys[slot], key);
+      offered = true;
+    }
   } else if (slot >= 0) {
     unsigned long long* ks = slot_keys + (long long)slot * C;
     if (key < ks[C - 1]) {
+      offered = true;
+      unsigned long long k = key;
       for (int j = 0; j < C; ++j) {
-        const unsigned long long old = atomicMin(&ks[j], key);
-        if (old == key) break;                 // already stored (the same point offered again): idempotent
-        if (old > key) {
-          key = old;
-          if (key == BSCNAV_KEY_EMPTY) break;
+        const unsigned long long old = atomicMin(&ks[j], k);
+        if (old == k) break;                   // already stored (the same point offered again): idempotent
+        if (old > k) {
+          k = old;
+          if (k == BSCNAV_KEY_EMPTY) break;
         }
       }
     }
   }
+  const unsigned m = __ballot_sync(0xffffffffu, offered);
+  const int w = threadIdx.x >> 5;
+  if (lane == 0) warp_off[w + 1] = __popc(m);
+  if (threadIdx.x == 0) warp_off[0] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 1; k <= kThreads / 32; ++k) warp_off[k] += warp_off[k - 1];
+    cand_n[blockIdx.x] = warp_off[kThreads / 32];
+  }
+  __syncthreads();
+  if (offered)
+    cand[(long long)blockIdx.x * kThreads + warp_off[w] + __popc(m & ((1u << lane) - 1))] =
+        make_uint4((uint32_t)slot, aux, (uint32_t)key, (uint32_t)(key >> 32));
 }
 
 // K4: winners copy their 4 KB token row into the store with 128-bit loads/stores, one warp per row.
-__global__ void __launch_bounds__(kThreads)
-k_commit(const uint4* __restrict__ rec, long long total, const int32_t* __restrict__ occupied,
-         const unsigned long long* __restrict__ slot_keys, unsigned long long* __restrict__ row_key,
-         int32_t* __restrict__ tok_h, float* __restrict__ norm2, float* __restrict__ feat,
-         const float* __restrict__ tokens, long long tok_stride, int C, int D, int32_t* __restrict__ counters) {
-  const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  long long dst_row = -1;
-  uint32_t aux = 0;
-  if (i < total) {
-    const uint4 r = rec[i];
-    const int cell = (int)r.x;
-    const int slot = cell >= 0 ? occupied[cell] : -1;
-    if (slot >= 0) {
-      const unsigned long long key = rec_key(r);
-      aux = r.y;
-      const unsigned long long* ks = slot_keys + (long long)slot * C;
-      if (C == 1) {
-        if (ks[0] == key) { dst_row = slot; row_key[slot] = key; }
-      } else {
-        bool win = false;
-        for (int j = 0; j < C && ks[j] <= key; ++j) win |= (ks[j] == key);
-        if (win) {
-          // claim a physical row whose current token is no longer among the kept keys (or was never used)
-          unsigned long long* rk = row_key + (long long)slot * C;
-          for (int rr = 0; rr < C; ++rr)       // the token may already own a row (same point offered again)
-            if (rk[rr] == key) win = false;
-          for (int rr = 0; rr < C && win && dst_row < 0; ++rr) {
-            const unsigned long long cur = rk[rr];
-            bool kept = false;
-            for (int j = 0; j < C; ++j) kept |= (ks[j] == cur);
-            if (cur == BSCNAV_KEY_EMPTY) kept = false;
-            if (!kept && atomicCAS(&rk[rr], cur, key) == cur) dst_row = (long long)slot * C + rr;
-          }
-        }
-      }
-    }
+// Decide for one offered key whether it is kept and which physical row it takes (-1: not a winner).
+__device__ __forceinline__ long long claim_row(int slot, unsigned long long key, const unsigned long long* __restrict__ slot_keys,
+                                               unsigned long long* __restrict__ row_key, int C) {
+  const unsigned long long* ks = slot_keys + (long long)slot * C;
+  if (C == 1) {
+    if (ks[0] != key) return -1;
+    row_key[slot] = key;
+    return slot;
   }
+  bool win = false;
+  for (int j = 0; j < C && ks[j] <= key; ++j) win |= (ks[j] == key);
+  if (!win) return -1;
+  // claim a physical row whose current token is no longer among the kept keys (or was never used)
+  unsigned long long* rk = row_key + (long long)slot * C;
+  for (int rr = 0; rr < C; ++rr)         // the token may already own a row (same point offered again)
+    if (rk[rr] == key) return -1;
+  for (int rr = 0; rr < C; ++rr) {
+    const unsigned long long cur = rk[rr];
+    bool kept = false;
+    for (int j = 0; j < C; ++j) kept |= (ks[j] == cur);
+    if (cur == BSCNAV_KEY_EMPTY) kept = false;
+    if (!kept && atomicCAS(&rk[rr], cur, key) == cur) return (long long)slot * C + rr;
+  }
+  return -1;
+}
+// the warp copies the rows its lanes won, one after the other; norm2 / tok_h / the committed-row counter follow
+__device__ __forceinline__ void copy_won_rows(long long dst_row, uint32_t aux, int32_t* __restrict__ tok_h, float* __restrict__ norm2,
+                                              float* __restrict__ feat, const float* __restrict__ tokens, long long tok_stride, int D,
+                                              int32_t* __restrict__ counters) {
+  const int lane = threadIdx.x & 31;
   unsigned winners = __ballot_sync(0xffffffffu, dst_row >= 0);
   const int nvec = D >> 2;
   if (lane == 0 && winners) atomicAdd(&counters[3], __popc(winners));     // rows committed since the last reset (wraps)
@@ -317,6 +388,29 @@ k_commit(const uint4* __restrict__ rec, long long total, const int32_t* __restri
     }
     acc = warp_sum(acc);
     if (lane == 0) { norm2[row] = acc; tok_h[row] = (int)(a >> kSrcBits); }
+  }
+}
+
+// one warp per k_select block: its segment of offered keys (usually a handful, at most 256)
+__global__ void __launch_bounds__(kThreads)
+k_commit(const uint4* __restrict__ cand, const int* __restrict__ cand_n, int n_segments,
+         const unsigned long long* __restrict__ slot_keys, unsigned long long* __restrict__ row_key,
+         int32_t* __restrict__ tok_h, float* __restrict__ norm2, float* __restrict__ feat,
+         const float* __restrict__ tokens, long long tok_stride, int C, int D, int32_t* __restrict__ counters) {
+  const int lane = threadIdx.x & 31;
+  const int warps = gridDim.x * (kThreads / 32);
+  for (int seg = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); seg < n_segments; seg += warps) {
+    const int n = cand_n[seg];
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      long long dst_row = -1;
+      uint32_t aux = 0;
+      if (i0 + lane < n) {
+        const uint4 c = cand[(long long)seg * kThreads + i0 + lane];
+        aux = c.y;
+        dst_row = claim_row((int)c.x, ((unsigned long long)c.w << 32) | c.z, slot_keys, row_key, C);
+      }
+      copy_won_rows(dst_row, aux, tok_h, norm2, feat, tokens, tok_stride, D, counters);
+    }
   }
 }
 
@@ -705,7 +799,10 @@ struct FuseScratch {
   uint4* rec;
   int* tile_count;
   int* tile_off;
-  int* hdr;
+  int* hdr;            // [0] first new slot, [1] capacity ok
+  uint4* cand;         // offered keys {slot, aux, key}: one 256-entry segment per k_select block
+  int* cand_n;         // entries used in each segment
+  uint32_t* fresh;     // 1 bit per point: heads a run on a cell without a slot (k_index_points); padded to whole tiles
 };
 static int64_t scratch_layout(long long total, FuseScratch* s, char* base) {
   const long long n_tiles = (total + kTile - 1) / kTile;
@@ -718,21 +815,29 @@ static int64_t scratch_layout(long long total, FuseScratch* s, char* base) {
   off += align_up(n_tiles * 4, 256);
   if (s) s->hdr = reinterpret_cast<int*>(base + off);
   off += 256;
+  const long long n_blocks = (total + kThreads - 1) / kThreads;
+  if (s) s->cand = reinterpret_cast<uint4*>(base + off);
+  off += align_up(n_blocks * kThreads * 16, 256);
+  if (s) s->cand_n = reinterpret_cast<int*>(base + off);
+  off += align_up(n_blocks * 4, 256);
+  if (s) s->fresh = reinterpret_cast<uint32_t*>(base + off);
+  off += align_up(n_tiles * (kTile / 32) * 4, 256);
   return off;
 }
 
-// shared tail of fuse / merge: slots, winners, rows
+// shared tail of fuse / merge: slots, winners, rows.  fresh: k_index_points' mask, or null (every record is examined)
 static int run_store_update(const bscnav_geom_t* g, const bscnav_store_t* st, const FuseScratch& s, long long total,
-                            const float* tokens, long long tok_stride, cudaStream_t stream) {
+                            const float* tokens, long long tok_stride, const uint32_t* fresh, cudaStream_t stream) {
   const int n_tiles = (int)((total + kTile - 1) / kTile);
   const int n_blocks = (int)((total + kThreads - 1) / kThreads);
-  BSC_LAUNCH(k_count_new, n_tiles, kThreads, 0, stream, s.rec, total, st->occupied_ids, st->first_touch, s.tile_count);
-  BSC_LAUNCH(k_scan_tiles, 1, kThreads, 0, stream, s.tile_count, s.tile_off, n_tiles, s.hdr, st->counters, g->max_slots);
+  BSC_LAUNCH(k_count_new, n_tiles, kThreads, 0, stream, s.rec, total, st->occupied_ids, st->first_touch, s.tile_count, fresh);
+  BSC_LAUNCH(k_scan_tiles, 1, kScanThreads, 0, stream, s.tile_count, s.tile_off, n_tiles, s.hdr, st->counters, g->max_slots);
   BSC_LAUNCH(k_assign_slots, n_tiles, kThreads, 0, stream, s.rec, total, st->occupied_ids, st->first_touch, s.tile_off,
-             s.hdr, st->slot_cell);
+             s.hdr, st->slot_cell, fresh, s.tile_count);
   BSC_LAUNCH(k_select, n_blocks, kThreads, 0, stream, s.rec, total, st->occupied_ids, st->first_touch,
-             reinterpret_cast<unsigned long long*>(st->slot_keys), g->cache);
-  BSC_LAUNCH(k_commit, n_blocks, kThreads, 0, stream, s.rec, total, st->occupied_ids,
+             reinterpret_cast<unsigned long long*>(st->slot_keys), g->cache, s.cand, s.cand_n);
+  const int want = (n_blocks + kThreads / 32 - 1) / (kThreads / 32), cap = num_sms() * 16;
+  BSC_LAUNCH(k_commit, want < cap ? want : cap, kThreads, 0, stream, s.cand, s.cand_n, n_blocks,
              reinterpret_cast<const unsigned long long*>(st->slot_keys), reinterpret_cast<unsigned long long*>(st->row_key),
              st->tok_h, st->norm2, st->feat, tokens, tok_stride, g->cache, g->dim, st->counters);
   return BSCNAV_OK;
@@ -808,10 +913,13 @@ int bscnav_fuse_frames(const bscnav_geom_t* g, const bscnav_store_t* st, const f
   if (scratch_layout(total, &s, static_cast<char*>(scratch)) > scratch_bytes) return BSCNAV_EINVAL;
   cudaStream_t stream = (cudaStream_t)stream_;
   const int n_blocks = (int)((total + kThreads - 1) / kThreads);
-  BSC_LAUNCH(k_index_points, n_blocks, kThreads, 0, stream, *g, depth, poses, ord_base, sample_idx, n_points, total, s.rec,
-             st->occupied_ids, st->first_touch);
+  // mask words of the last, partial tile whose warps do not exist stay zero
+  const long long n_tiles = (total + kTile - 1) / kTile;
+  BSC_CUDA(cudaMemsetAsync(s.fresh + (n_tiles - 1) * (kTile / 32), 0, (kTile / 32) * 4, stream));
+  BSC_LAUNCH(k_index_points, n_blocks, kThreads, 0, stream, *g, 1.0 / g->cs, depth, poses, ord_base, sample_idx, n_points, total,
+             s.rec, st->occupied_ids, st->first_touch, s.fresh);
   if (records_out) BSC_CUDA(cudaMemcpyAsync(records_out, s.rec, total * 16, cudaMemcpyDeviceToDevice, stream));
-  return run_store_update(g, st, s, total, tokens, g->dim, stream);
+  return run_store_update(g, st, s, total, tokens, g->dim, s.fresh, stream);
 }
 
 int bscnav_merge_delta(const bscnav_geom_t* g, const bscnav_store_t* st, const int32_t* d_cell, const uint64_t* d_key,
@@ -826,7 +934,7 @@ int bscnav_merge_delta(const bscnav_geom_t* g, const bscnav_store_t* st, const i
   cudaStream_t stream = (cudaStream_t)stream_;
   BSC_LAUNCH(k_delta_records, (n + kThreads - 1) / kThreads, kThreads, 0, stream, d_cell,
              reinterpret_cast<const unsigned long long*>(d_key), d_h, n, s.rec, st->occupied_ids, st->first_touch);
-  return run_store_update(g, st, s, n, d_feat, g->dim, stream);
+  return run_store_update(g, st, s, n, d_feat, g->dim, nullptr, stream);
 }
 
 int64_t bscnav_export_scratch_bytes(const bscnav_geom_t* g) {
@@ -900,7 +1008,7 @@ int bscnav_merge_packed(const bscnav_geom_t* g, const bscnav_store_t* st, const 
     BSC_LAUNCH(k_packed_records, (n + kThreads - 1) / kThreads, kThreads, 0, stream, static_cast<const char*>(packed), row_bytes,
                first, n, seg_capacity, seg_counts, count_stride, skip_segment, s.rec, st->occupied_ids, st->first_touch);
     const float* rows = reinterpret_cast<const float*>(static_cast<const char*>(packed) + first * row_bytes + 16);
-    if (int e = run_store_update(g, st, s, n, rows, row_bytes / 4, stream)) return e;
+    if (int e = run_store_update(g, st, s, n, rows, row_bytes / 4, nullptr, stream)) return e;
   }
   return BSCNAV_OK;
 }

@@ -152,8 +152,39 @@ def run_reference(name):
     return out
 
 
+def run_text_goal(name="cfg1"):
+    """The text-goal branch of voxel_localized (memory_2.py:566-576): `imaginary(prompt)` returns generated images (SD3.5 in the
+    reference; here a stub handing back three seeded PIL images), the ViT runs on the batch of three, the pooled vectors are
+    averaged.  The unmodified reference runs on config 1's store; the stub's images are kept in the fixture."""
+    import types
+    from PIL import Image
+    ci = case_inputs(name)
+    vit, dim = build_vit(ci["vit"])
+    args = rh.default_args(**ci["args"])
+    args.imagenary_num = 3
+    rh.reset_fake_h5()
+    m = rh.make_reference_memory(args, vit, patch=ci["patch"], token_dim=dim, iter_size=400000, cache_size=10 ** 9, identity_shuffle=True)
+    for rgb, depth, pose in ci["frames"]:
+        m.obs2voxeltoken({"rgb": rgb, "depth": depth}, pose)
+    rh.flush_trimmed(m)
+    imgs = [Image.fromarray(np.random.default_rng(40 + i).integers(0, 256, size=(90 + 10 * i, 120, 3), dtype=np.uint8)) for i in range(3)]
+    m.imaginary = lambda prompt: types.SimpleNamespace(images=imgs)
+    with contextlib.redirect_stdout(io.StringIO()):
+        best, pos, sim = m.voxel_localized("a red chair next to the window", K=100)
+    x = torch.stack([m.transform(im) for im in imgs])
+    pooled = vit_ref.gaussian_pool(vit.forward_features(x)["x_norm_patchtokens"]).numpy()
+    return {"img0": np.asarray(imgs[0]), "img1": np.asarray(imgs[1]), "img2": np.asarray(imgs[2]), "query_vec": pooled,
+            "topk_pos": pos, "topk_sim": sim, "best_pos": best}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if sys.argv[1:] == ["text_goal"]:
+        out = run_text_goal()
+        path = os.path.join(OUT, "cfg1_text.npz")
+        np.savez_compressed(path, **out)
+        print("cfg1_text", {k: v.shape for k, v in out.items()}, os.path.getsize(path) // 1024, "KiB")
+        return
     for name in sys.argv[1:] or ("cfg1", "two_pose", "sampled", "tilted"):
         out = run_reference(name)
         path = os.path.join(OUT, f"{name}.npz")

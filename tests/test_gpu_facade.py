@@ -91,3 +91,28 @@ def test_localize_agent_and_roundtrip(cfg1, golden, tmp_path, pkg):
     _, p2, s2 = mem2.voxel_localized(q, K=50)
     assert np.array_equal(p1, p2) and np.array_equal(s1, s2)
     assert mem2.max_id == mem.max_id and np.array_equal(mem2.grid_rgb_pos, mem.grid_rgb_pos)
+
+
+def test_text_goal_branch_matches_reference(cfg1, golden):
+    """voxel_localized(str) (memory_2.py:566-576): the injected generator hands back three images, the engine runs the batch of
+    three, the pooled vectors are averaged -- against the unmodified reference run with the same stub (tests/golden/cfg1_text.npz,
+    oracle/make_golden.py text_goal)."""
+    import types
+    mem, eng = cfg1
+    g = golden("cfg1_text")
+    imgs = [Image.fromarray(g[f"img{i}"]) for i in range(3)]
+    calls = []
+    mem.imaginary = lambda prompt: (calls.append(prompt), types.SimpleNamespace(images=imgs))[1]
+    mem.args.imagenary_num = 3
+    q = mem._query_vector("a red chair next to the window").cpu().numpy()
+    assert calls == ["a red chair next to the window"] and q.shape == (1, 768)
+    assert np.linalg.norm(q - g["query_vec"]) / np.linalg.norm(g["query_vec"]) < 1e-3
+    best, pos, sim = mem.voxel_localized("a red chair next to the window", K=100)
+    assert pos.shape == (100, 3) and sim.dtype == np.float64
+    np.testing.assert_allclose(sim, g["topk_sim"], rtol=1e-3, atol=1e-4)
+    cut = g["topk_sim"][-1] + 2e-3
+    sure = {tuple(r) for r, s in zip(g["topk_pos"], g["topk_sim"]) if s > cut}
+    assert sure <= {tuple(r) for r in pos}
+    del mem.imaginary                       # back to the class's NotImplementedError for the next user of the fixture
+    with pytest.raises(NotImplementedError):
+        mem.voxel_localized("no generator injected")

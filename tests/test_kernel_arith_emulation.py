@@ -67,3 +67,15 @@ def test_index_math_statement_matches_reference_buffers(golden):
     assert np.array_equal(np.array(pos), g["feat_pos"])                 # voxel index of every accepted point, in visiting order
     assert np.array_equal(np.array(dis, dtype=np.float32), g["feat_dis"])
     assert np.array_equal(np.array(src), g["feat_src"])
+
+
+def test_guarded_multiply_equals_division_then_truncation():
+    """k_index_points replaces its five IEEE divisions per point by multiplications guarded next to integers
+    (trunc_div_cs / trunc_quot_half in csrc/memory_kernels.cu): the guarded forms return the integer the division returns, on
+    random inputs and on inputs planted on and next to cell boundaries (the long form: tools/micro/div_trunc_check.py)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "micro"))
+    import div_trunc_check
+    total, slow = div_trunc_check.check(n_rounds=2, size=300_000)
+    assert total > 4_000_000 and slow > 100_000          # the planted boundary cases do exercise the exact-division path

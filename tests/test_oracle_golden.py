@@ -181,3 +181,20 @@ def test_kept_vectorised_equals_oracle_memory(golden, bev, C):
     assert set(want) == set(got)
     for k, items in want.items():
         assert [(t[0], t[1], t[2], t[3]) for t in items] == got[k]
+
+
+def test_text_goal_fixture_query_vector(golden):
+    """The text-goal branch's query vector (memory_2.py:566-608, three generated images): the oracle's pooling over a batch of three
+    reproduces what the unmodified reference computed (tests/golden/cfg1_text.npz)."""
+    import torch
+    from PIL import Image
+    from torchvision import transforms
+    from oracle import vit_ref
+    g = golden("cfg1_text")
+    tf = transforms.Compose([transforms.Resize((224, 224)), transforms.ToTensor(),
+                             transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    x = torch.stack([tf(Image.fromarray(g[f"img{i}"])) for i in range(3)])
+    vit, _dim = mg.build_vit(mg.case_inputs("cfg1")["vit"])
+    q = vit_ref.gaussian_pool(vit.forward_features(x)["x_norm_patchtokens"]).numpy()
+    np.testing.assert_allclose(q, g["query_vec"], rtol=1e-5, atol=1e-6)
+    assert g["topk_pos"].shape == (100, 3) and np.all(np.diff(g["topk_sim"]) <= 0)

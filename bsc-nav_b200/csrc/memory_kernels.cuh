@@ -23,7 +23,8 @@ __device__ __forceinline__ bool filter_pass(const bscnav_filter_t& flt, int row,
     const long long dr = row - flt.cur[0], dc = col - flt.cur[1], dh = h - flt.cur[2];
     ok = dr * dr + dc * dc + dh * dh <= flt.radius2;
   }
-  if (flt.floor_min <= flt.floor_max) ok = ok && h >= flt.floor_min && h <= flt.floor_max;
+  // explicit enable bit: an empty range from load_single_floor (min > max) must select nothing, not switch the filter off
+  if ((flt.reserved & 1) || flt.floor_min <= flt.floor_max) ok = ok && h >= flt.floor_min && h <= flt.floor_max;
   return ok;
 }
 

@@ -239,6 +239,7 @@ class SpatialStore:
             flt.cur[:] = [int(v) for v in curr_grid]
         if floor_range is not None:
             flt.floor_min, flt.floor_max = int(floor_range[0]), int(floor_range[1])
+            flt.reserved = 1               # explicit enable: a degenerate (empty) floor range returns nothing
         return flt
 
     def invalidate_shadow(self):

@@ -102,13 +102,14 @@ int bscnav_fuse_frames(const bscnav_geom_t* g, const bscnav_store_t* st, const f
                        const uint32_t* ord_base, const int32_t* sample_idx, int32_t n_frames, int32_t n_points,
                        const float* tokens, void* scratch, int64_t scratch_bytes, void* records_out, void* stream);
 
-/* Candidate filter of voxel_localized (memory_2.py:624-640). radius2 < 0 disables the sphere test;
- * floor_min > floor_max disables the floor test. */
+/* Candidate filter of voxel_localized (memory_2.py:624-640). radius2 < 0 disables the sphere test.  The floor test is applied when
+ * bit 0 of `flags` is set (an empty range floor_min > floor_max then selects nothing) or, for callers that leave flags 0, when
+ * floor_min <= floor_max. */
 typedef struct {
   int64_t radius2;                 /* region_radius^2 in cells^2 (compared as integers) */
   int32_t cur[3];                  /* curr_grid (row, col, h-minh)                       */
   int32_t floor_min, floor_max;    /* load_single_floor range, inclusive                 */
-  int32_t reserved;
+  int32_t reserved;                /* flags: bit 0 = floor test enabled                  */
 } bscnav_filter_t;
 
 int64_t bscnav_query_scratch_bytes(const bscnav_geom_t* g, int32_t n_query, int32_t k);

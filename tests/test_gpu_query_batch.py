@@ -57,6 +57,10 @@ def test_batch_equals_exact(pkg, C, bev, n, D, dup, Q):
     # region + floor filters
     kw = dict(region_radius=37.5, curr_grid=(80, 70, 9), floor_range=(3, 15))
     _same(st.query_batch(q, k=50, **kw), st.query(q, k=50, **kw))
+    # a degenerate (empty) floor range from load_single_floor selects nothing -- it must not switch the filter off
+    for path in (st.query, st.query_batch):
+        _s, _p, cnt = path(q, k=50, floor_range=(9, 3))
+        assert cnt.tolist() == [0] * Q
 
 
 def test_batch_fewer_than_k_and_empty(pkg):

@@ -281,6 +281,15 @@ extern "C" int bscnav_attention_f16(const void* qkv, void* out, int32_t batch, i
 extern "C" int bscnav_attention_f16_hd(const void* qkv, void* out, int32_t batch, int32_t T, int32_t heads, int32_t head_dim,
                                        int32_t causal, void* stream) {
   if (!qkv || !out || batch <= 0 || T <= 0 || heads <= 0) return BSCNAV_EINVAL;
+  if (causal == 2) {      // causal mask on the second-generation tcgen05 kernel (head dim 64, 17 <= T <= 272): what the text tower runs
+    if (head_dim != 64 || !attention_ws2_supported(T)) return BSCNAV_EINVAL;
+    CUtensorMap m128, m16, mo;
+    if (int e = make_qkv_map3d(&m128, qkv, batch, T, 3LL * heads * 64, 128)) return e;
+    if (int e = make_qkv_map3d(&m16, qkv, batch, T, 3LL * heads * 64, 16)) return e;
+    if (int e = make_out_map3d(&mo, out, batch, T, 1LL * heads * 64)) return e;
+    return attention_ws2_launch(&m128, &m16, &mo, static_cast<const __half*>(qkv), static_cast<__half*>(out), batch, T, heads,
+                                (cudaStream_t)stream, true);
+  }
   return attention_f16(static_cast<const __half*>(qkv), static_cast<__half*>(out), batch, T, heads, head_dim, causal != 0,
                        (cudaStream_t)stream);
 }

@@ -158,7 +158,7 @@ template <int DBG, bool STAMP>
 __global__ void __launch_bounds__(kW2Threads, 1)
 k_attention_ws2(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap map16,
                 const __grid_constant__ CUtensorMap map_out, const __half* __restrict__ qkv, __half* __restrict__ out,
-                int T, int heads, int n_items, long long* __restrict__ dbg_out_) {
+                int T, int heads, int n_items, int causal, long long* __restrict__ dbg_out_) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(smem);
@@ -324,6 +324,9 @@ k_attention_ws2(const __grid_constant__ CUtensorMap map128, const __grid_constan
       tcgen05_fence_after();
       stamp(n, 3 * x);
       float mx = -INFINITY, sum = 0.f;
+      // keys this row may see: all T, or (causal mask of the text tower) the keys up to its own position.  A half with no visible
+      // key reports (max -inf, sum 0) and an all-zero P: the epilogue's weights then drop it
+      const int lim = causal ? min(T, m * kW2TileQ + r + 1) : T;
       if (live) {
         // Two passes over this half's S columns in chunks of 32 (the last may be 16 wide).  (Keeping the next chunk's TMEM load
         // in flight behind the current chunk's math was measured: no gain, the passes are bound by the FMA / XU pipes.)
@@ -337,14 +340,14 @@ k_attention_ws2(const __grid_constant__ CUtensorMap map128, const __grid_constan
         auto red = [&](int c, const uint32_t (&v)[32]) {
           const bool wide = c + 32 <= c_hi;
           const int w = wide ? 32 : 16;
-          if (c + w <= T) {
+          if (c + w <= lim) {
 #pragma unroll
             for (int j = 0; j < 32; j += 2)
               if (j < 16 || wide) m2[(j >> 1) & 1] = w2_max3(m2[(j >> 1) & 1], __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if ((j < 16 || wide) && c + j < T) m2[j & 1] = fmaxf(m2[j & 1], __uint_as_float(v[j]));
+              if ((j < 16 || wide) && c + j < lim) m2[j & 1] = fmaxf(m2[j & 1], __uint_as_float(v[j]));
           }
         };
         if (!(dbg & 1)) {
@@ -373,9 +376,9 @@ k_attention_ws2(const __grid_constant__ CUtensorMap map128, const __grid_constan
               v[j] = __float_as_uint(a); v[j + 1] = __float_as_uint(b);
             } else { v[j] = 0u; v[j + 1] = 0u; }
           }
-          if (c + w > T) {
+          if (c + w > lim) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (c + j >= T) v[j] = 0u;
+            for (int j = 0; j < 32; ++j) if (c + j >= lim) v[j] = 0u;
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -520,8 +523,9 @@ k_attention_ws2(const __grid_constant__ CUtensorMap map128, const __grid_constan
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int key = kb * 64 + i * 8 + fc;
-              if (i >= 2 * ng || key >= T) sc[i][0] = -INFINITY;
-              if (i >= 2 * ng || key + 1 >= T) sc[i][1] = -INFINITY;
+              const int vis = causal ? min(T, tail0 + fr + 1) : T;        // keys this row may see
+              if (i >= 2 * ng || key >= vis) sc[i][0] = -INFINITY;
+              if (i >= 2 * ng || key + 1 >= vis) sc[i][1] = -INFINITY;
               bm = fmaxf(bm, fmaxf(sc[i][0], sc[i][1]));
             }
             bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
@@ -585,7 +589,7 @@ static long long* g_w2_dbg_out = nullptr;
 bool attention_ws2_supported(int T) { const int Tk = (T + 15) & ~15; return T >= 17 && Tk <= kW2MaxKeys; }
 
 int attention_ws2_launch(const CUtensorMap* map128, const CUtensorMap* map16, const CUtensorMap* map_out, const __half* qkv,
-                         __half* out, int batch, int T, int heads, cudaStream_t stream) {
+                         __half* out, int batch, int T, int heads, cudaStream_t stream, bool causal) {
   if (!attention_ws2_supported(T) || batch <= 0 || heads <= 0 || !map_out || !qkv || !out) return BSCNAV_EINVAL;
   static int sms = 0;
   if (!sms) {
@@ -604,7 +608,7 @@ int attention_ws2_launch(const CUtensorMap* map128, const CUtensorMap* map16, co
       attr_set = true;                                                                                                      \
     }                                                                                                                       \
     BSC_LAUNCH_PDL((k_attention_ws2<DBG_, STAMP_>), grid, kW2Threads, kW2Smem, stream, *map128, *map16, *map_out, qkv, out, T, \
-                   heads, n_items, g_w2_dbg_out);                                                                           \
+                   heads, n_items, causal ? 1 : 0, g_w2_dbg_out);                                                                           \
   } while (0)
   if (g_w2_dbg == 0 && !g_w2_dbg_out) BSC_W2_LAUNCH(0, false);
   else if (g_w2_dbg == 0) BSC_W2_LAUNCH(0, true);

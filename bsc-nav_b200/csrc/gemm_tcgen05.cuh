@@ -68,7 +68,7 @@ int attention_ws_launch(const CUtensorMap* map128, const CUtensorMap* map16, __h
 int make_out_map3d(CUtensorMap* map, const void* ptr, long long batch, long long T, long long width);
 bool attention_ws2_supported(int T);
 int attention_ws2_launch(const CUtensorMap* map128, const CUtensorMap* map16, const CUtensorMap* map_out, const __half* qkv,
-                         __half* out, int batch, int T, int heads, cudaStream_t stream);
+                         __half* out, int batch, int T, int heads, cudaStream_t stream, bool causal = false);
 
 int gemm_block_n(int N);   // 256 when N % 256 == 0 (BN=128 is shared-memory-bandwidth bound at cta_group::1), else 128
 

@@ -184,7 +184,7 @@ static int run_layers(VitEngine* e, int batch, cudaStream_t stream) {
       if (int r = gemm_f16_launch(&e->map_y, &e->map_qkv[i], &e->out_qkv, rows, 3 * D, D, e1, stream, e->has_half[0] ? &e->half_qkv[i] : nullptr)) return r; }
     { ProfScope ps(e, stream, kCatAttention, 4.0 * batch * (double)T * T * D);
       if (e->attn_impl == 3) {
-        if (int r = attention_ws2_launch(&e->qkv3d128, &e->qkv3d16, &e->ao3d, e->ws.qkv, e->ws.ao, batch, T, c.heads, stream)) return r;
+        if (int r = attention_ws2_launch(&e->qkv3d128, &e->qkv3d16, &e->ao3d, e->ws.qkv, e->ws.ao, batch, T, c.heads, stream, causal)) return r;
       } else if (e->attn_impl == 2) {
         // the 3-D map's frame extent is the engine's max_batch: frames >= batch are simply never addressed
         if (int r = attention_ws_launch(&e->qkv3d128, &e->qkv3d16, e->ws.ao, batch, T, c.heads, stream)) return r;
@@ -293,7 +293,8 @@ int bscnav_vit_create(const bscnav_vit_cfg_t* c, const void* w_half, const float
   // BSCNAV_ATTENTION=0|1|2 selects mma.sync / tcgen05 v1 / tcgen05 warp-specialised (tests exercise all three)
   const char* impl_env = getenv("BSCNAV_ATTENTION");
   e->attn_impl = impl_env ? atoi(impl_env) : 3;
-  if ((c->head_dim && c->head_dim != 64) || text) e->attn_impl = 0;  // the tcgen05 kernels: head dim 64, no causal mask
+  if (c->head_dim && c->head_dim != 64) e->attn_impl = 0;            // the tcgen05 kernels: head dim 64
+  if (text && e->attn_impl != 3) e->attn_impl = 0;                   // causal mask: the second-generation kernel or mma.sync
   if (c->precision == 1) e->attn_impl = 0;                           // wide-range path: fp32 attention (run_layers_wide)
   if (e->attn_impl == 3 && !attention_ws2_supported(e->T)) e->attn_impl = 2;
   if (e->attn_impl == 2 && !attention_ws_supported(e->T)) e->attn_impl = 0;

@@ -316,10 +316,10 @@ def attention_f16(qkv: torch.Tensor, batch: int, T: int, heads: int, impl: int =
     or 80, optional causal mask at head_dim 64), 1 / 2 = tcgen05 kernels (head_dim 64, no mask)."""
     out = torch.empty(batch * T, heads * head_dim, dtype=torch.float16, device=qkv.device)
     if head_dim != 64 or causal:
-        if impl != 0:
-            raise ValueError("head_dim != 64 and causal masks run on the mma.sync kernel only (impl=0)")
-        _lib.check(_lib.lib().bscnav_attention_f16_hd(_lib.ptr(qkv), _lib.ptr(out), batch, T, heads, head_dim, 1 if causal else 0,
-                                                      _lib.stream_ptr()), "attention_f16_hd")
+        if impl not in (0, 3) or (impl == 3 and (head_dim != 64 or not causal)):
+            raise ValueError("head_dim != 64 runs on the mma.sync kernel only (impl=0); causal masks on impl 0 or 3")
+        _lib.check(_lib.lib().bscnav_attention_f16_hd(_lib.ptr(qkv), _lib.ptr(out), batch, T, heads, head_dim,
+                                                      (2 if impl == 3 else 1) if causal else 0, _lib.stream_ptr()), "attention_f16_hd")
         return out
     _lib.check(_lib.lib().bscnav_attention_f16(_lib.ptr(qkv), _lib.ptr(out), batch, T, heads, impl, _lib.stream_ptr()), "attention_f16")
     return out

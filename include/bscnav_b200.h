@@ -292,8 +292,9 @@ int bscnav_gemm_bf16x3(const void* a, const void* w, const float* bias, float* o
  * out fp16 [batch*T, heads*64].  impl 0: mma.sync kernel (any T); impl 1 / 2: first tcgen05 kernels; impl 3: the engine's default
  * (P in TMEM, SIMT tail rows, TMA-store epilogue; 17 <= T <= 272). */
 int bscnav_attention_f16(const void* qkv, void* out, int32_t batch, int32_t T, int32_t heads, int32_t impl, void* stream);
-/* The mma.sync kernel with an explicit head dim (64 | 80) and optional causal mask (keys <= query row; head dim 64):
- * qkv fp16 [batch*T, 3*heads*head_dim], q pre-scaled. */
+/* The mma.sync kernel with an explicit head dim (64 | 80) and optional causal mask (causal = 1: keys <= query row; head dim 64):
+ * qkv fp16 [batch*T, 3*heads*head_dim], q pre-scaled.  causal = 2: the same mask on the default tcgen05 kernel (head dim 64,
+ * 17 <= T <= 272), the path the text tower takes. */
 int bscnav_attention_f16_hd(const void* qkv, void* out, int32_t batch, int32_t T, int32_t heads, int32_t head_dim, int32_t causal,
                             void* stream);
 

@@ -181,12 +181,14 @@ def test_score_views_matches_torch(pkg, n, E):
 
 
 # ---- the same CLIP's text tower (encode_text: goal text, long-term labels; BSCAgent.py:541-557, 708-711)
-@pytest.mark.parametrize("T,heads,batch", [(77, 16, 3), (20, 2, 2), (130, 3, 2), (64, 1, 1), (257, 2, 1)])
-def test_attention_causal(pkg, T, heads, batch):
+@pytest.mark.parametrize("impl", [0, 3])
+@pytest.mark.parametrize("T,heads,batch", [(77, 16, 3), (20, 2, 2), (130, 3, 2), (64, 1, 1), (257, 2, 1), (261, 2, 2), (200, 1, 1)])
+def test_attention_causal(pkg, T, heads, batch, impl):
+    """Causal mask (text tower): the mma.sync kernel and the default tcgen05 kernel (tile rows, halves without a visible key, tail rows)."""
     g = torch.Generator("cuda").manual_seed(T * 3 + heads)
     D = heads * 64
     qkv = (torch.randn(batch * T, 3 * D, device="cuda", generator=g) * 0.8).half()
-    out = pkg.attention_f16(qkv, batch, T, heads, impl=0, causal=True).float().view(batch, T, heads, 64)
+    out = pkg.attention_f16(qkv, batch, T, heads, impl=impl, causal=True).float().view(batch, T, heads, 64)
     q, k, v = qkv.float().view(batch, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
     mask = torch.full((T, T), float("-inf"), device="cuda").triu(1)
     ref = (torch.softmax(q @ k.transpose(-1, -2) + mask, dim=-1) @ v).permute(0, 2, 1, 3)

@@ -607,9 +607,12 @@ __global__ void __launch_bounds__(kThreads)
 k_query_slots(const bscnav_geom_t g, const float* __restrict__ feat, const float* __restrict__ norm2,
               const unsigned long long* __restrict__ row_key, const int32_t* __restrict__ slot_cell,
               const int32_t* __restrict__ tok_h, const int32_t* __restrict__ counters, const float* __restrict__ q,
-              int q0, int nq, const bscnav_filter_t flt, unsigned long long* __restrict__ keys, long long key_stride) {
+              int q0, int nq, const bscnav_filter_t flt, unsigned long long* __restrict__ keys, long long key_stride,
+              uint32_t* __restrict__ zero_words, int n_zero) {
   extern __shared__ float4 sq[];            // nq * D floats
   __shared__ float q_n2[kQ];
+  // the histogram / counters of the select stages behind this kernel start from zero: cleared here instead of by three memsets
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n_zero; i += gridDim.x * kThreads) zero_words[i] = 0u;
   const int D = NV * 128;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < nq * (D >> 2); i += kThreads) sq[i] = reinterpret_cast<const float4*>(q + (long long)q0 * D)[i];
@@ -686,6 +689,8 @@ __global__ void __launch_bounds__(1024)
 k_topk_chunks(const unsigned long long* __restrict__ in, long long in_stride, const int32_t* __restrict__ n_dev, int n_host,
               unsigned long long* __restrict__ out, long long out_stride, int k, const int32_t* __restrict__ run_flag) {
   __shared__ unsigned long long s[kChunk];
+  pdl_wait();                           // chained behind the previous stage with programmatic dependent launch
+  pdl_launch_dependents();
   const int n = n_dev ? *n_dev : n_host;
   const int qi = blockIdx.y;
   if (run_flag && !run_flag[qi]) return;        // fall-back sorter: only for queries the histogram select handed over
@@ -718,6 +723,8 @@ k_topk_decode(const bscnav_geom_t g, const unsigned long long* __restrict__ keys
               const int32_t* __restrict__ tok_h, const float* __restrict__ feat, const float* __restrict__ norm2,
               const float* __restrict__ q, int q0, float* __restrict__ out_sim, int32_t* __restrict__ out_pos,
               int32_t* __restrict__ out_count) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int qi = blockIdx.x;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int D = g.dim, C = g.cache;
@@ -768,6 +775,8 @@ static int num_sms() { return mem_num_sms(); }
 // queries flagged by the histogram select take the chunked sorter's result
 __global__ void k_pick_fallback(const int32_t* __restrict__ overflow, const unsigned long long* __restrict__ fallback,
                                 long long fb_stride, unsigned long long* __restrict__ sorted, int k) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int qi = blockIdx.x;
   if (!overflow[qi]) return;
   for (int i = threadIdx.x; i < k; i += blockDim.x) sorted[(long long)qi * k + i] = fallback[(long long)qi * fb_stride + i];
@@ -1043,13 +1052,15 @@ int bscnav_query_topk(const bscnav_geom_t* g, const bscnav_store_t* st, const fl
   for (int q0 = 0; q0 < n_query; q0 += kQ) {
     const int nq = (n_query - q0) < kQ ? (n_query - q0) : kQ;
     const size_t smem = (size_t)nq * D * sizeof(float);
+    char* sel_base = base + align_up(lvl0 * 8, 256) + 2 * align_up(cand * 8, 256) + 256;
 #define BSC_QUERY_CASE(NV)                                                                                            \
   case NV: {                                                                                                          \
     if (smem > 48 * 1024)                                                                                             \
       BSC_CUDA(cudaFuncSetAttribute(k_query_slots<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
     BSC_LAUNCH(k_query_slots<NV>, grid, kThreads, smem, stream, *g, st->feat, st->norm2,                             \
                reinterpret_cast<const unsigned long long*>(st->row_key), st->slot_cell, st->tok_h, st->counters, q,  \
-               q0, nq, flt, keys0, (long long)g->max_slots);                                                         \
+               q0, nq, flt, keys0, (long long)g->max_slots, reinterpret_cast<uint32_t*>(sel_base),                   \
+               (int)(exact_select_zero_bytes(kQ) / 4));                                                              \
   } break;
     switch (D / 128) {
       BSC_QUERY_CASE(1) BSC_QUERY_CASE(2) BSC_QUERY_CASE(3) BSC_QUERY_CASE(4) BSC_QUERY_CASE(5) BSC_QUERY_CASE(6)
@@ -1062,29 +1073,31 @@ int bscnav_query_topk(const bscnav_geom_t* g, const bscnav_store_t* st, const fl
     char* sel = base + align_up(lvl0 * 8, 256) + 2 * align_up(cand * 8, 256) + 256;
     unsigned long long* sorted = reinterpret_cast<unsigned long long*>(sel + exact_select_scratch_bytes(kQ));
     int32_t* overflow = nullptr;
-    if (int e = launch_exact_select(keys0, (long long)g->max_slots, st->counters, g->max_slots, nq, k, sel, sorted, &overflow, stream)) return e;
+    if (int e = launch_exact_select(keys0, (long long)g->max_slots, st->counters, g->max_slots, nq, k, sel, sorted, &overflow, stream,
+                                    /*zeroed=*/true, out_count + q0)) return e;
     // level 0: n is the device-side slot count, but the grid covers the capacity
     long long n_chunks = chunks0;
-    BSC_LAUNCH(k_topk_chunks, dim3((unsigned)n_chunks, (unsigned)nq), 1024, 0, stream, keys0, (long long)g->max_slots,
-               st->counters, 0, bufA, n_chunks * k, k, (const int32_t*)overflow);
+    BSC_LAUNCH_PDL(k_topk_chunks, dim3((unsigned)n_chunks, (unsigned)nq), 1024, 0, stream, keys0, (long long)g->max_slots,
+                   (const int32_t*)st->counters, 0, bufA, (long long)(n_chunks * k), k, (const int32_t*)overflow);
     unsigned long long* in = bufA;
     unsigned long long* out = bufB;
     long long n_in = n_chunks * k, in_stride = n_chunks * k;
     while (n_in > k) {
       n_chunks = (n_in + kChunk - 1) / kChunk;
-      BSC_LAUNCH(k_topk_chunks, dim3((unsigned)n_chunks, (unsigned)nq), 1024, 0, stream, in, in_stride, nullptr, (int)n_in,
-                 out, n_chunks * k, k, (const int32_t*)overflow);
+      BSC_LAUNCH_PDL(k_topk_chunks, dim3((unsigned)n_chunks, (unsigned)nq), 1024, 0, stream, (const unsigned long long*)in, in_stride,
+                     (const int32_t*)nullptr, (int)n_in, out, (long long)(n_chunks * k), k, (const int32_t*)overflow);
       in_stride = n_chunks * k;
       n_in = n_chunks * k;
       unsigned long long* t = in; in = out; out = t;
       if (n_chunks == 1) break;
     }
-    BSC_LAUNCH(k_pick_fallback, (unsigned)nq, 128, 0, stream, overflow, in, in_stride, sorted, k);
+    BSC_LAUNCH_PDL(k_pick_fallback, (unsigned)nq, 128, 0, stream, (const int32_t*)overflow, (const unsigned long long*)in, in_stride, sorted, k);
     in = sorted; in_stride = k;
-    BSC_CUDA(cudaMemsetAsync(out_count + q0, 0, sizeof(int32_t) * nq, stream));
-    BSC_LAUNCH(k_topk_decode, dim3((unsigned)nq, (unsigned)((k + kThreads / 32 - 1) / (kThreads / 32))), kThreads, 0, stream, *g, in, in_stride, k, st->occupied_ids,
-               reinterpret_cast<const unsigned long long*>(st->row_key), st->tok_h, st->feat, st->norm2, q, q0,
-               out_sim + (long long)q0 * k, out_pos + (long long)q0 * k * 3, out_count + q0);
+    // out_count was cleared by k_sort_candidates (launch_exact_select): no memset between the kernels of the chain
+    BSC_LAUNCH_PDL(k_topk_decode, dim3((unsigned)nq, (unsigned)((k + kThreads / 32 - 1) / (kThreads / 32))), kThreads, 0, stream, *g,
+                   (const unsigned long long*)in, in_stride, k, (const int32_t*)st->occupied_ids,
+                   reinterpret_cast<const unsigned long long*>(st->row_key), (const int32_t*)st->tok_h, (const float*)st->feat,
+                   (const float*)st->norm2, q, q0, out_sim + (long long)q0 * k, out_pos + (long long)q0 * k * 3, out_count + q0);
   }
   return BSCNAV_OK;
 }

@@ -37,8 +37,12 @@ int launch_topk_decode(const bscnav_geom_t* g, const bscnav_store_t* st, const u
                        const float* q, int n_query, float* out_sim, int32_t* out_pos, int32_t* out_count, cudaStream_t stream);
 // histogram-select + sort of exact composite keys (query_batch.cu), used by the single-query path
 int64_t exact_select_scratch_bytes(int n_query);
+int64_t exact_select_zero_bytes(int n_query);     // leading bytes of that scratch that must be zero on entry (histogram, counters, flags)
+// zeroed: the caller cleared those bytes already (k_query_slots does it in its prologue); zero_count: int32[n_query] cleared by the
+// sort stage for the decode stage's atomic count, or null
 int launch_exact_select(const unsigned long long* keys, long long stride, const int32_t* counters, int max_slots, int n_query, int k,
-                        void* scratch, unsigned long long* sorted, int32_t** overflow_out, cudaStream_t stream);
+                        void* scratch, unsigned long long* sorted, int32_t** overflow_out, cudaStream_t stream, bool zeroed = false,
+                        int32_t* zero_count = nullptr);
 int mem_num_sms();
 int mem_check_geom(const bscnav_geom_t* g);
 

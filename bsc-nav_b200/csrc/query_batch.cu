@@ -264,6 +264,8 @@ static constexpr int kBlkChunk = 2048;       // block maxima per thread block in
 __global__ void __launch_bounds__(kMemThreads)
 k_blk_hist(const float* __restrict__ bmax, long long ld, int n_blk, uint32_t* __restrict__ hist) {
   __shared__ uint32_t h[kBins];
+  pdl_wait();
+  pdl_launch_dependents();
   const int qi = blockIdx.y;
   const int b0 = blockIdx.x * kBlkChunk;
   for (int b = threadIdx.x; b < kBins; b += kMemThreads) h[b] = 0;
@@ -286,6 +288,8 @@ k_blk_hist(const float* __restrict__ bmax, long long ld, int n_blk, uint32_t* __
 // one block per query: the threshold bin, once (every select block used to re-derive it from the 8 KB histogram)
 __global__ void __launch_bounds__(kMemThreads)
 k_blk_threshold(const uint32_t* __restrict__ hist, int k, int32_t* __restrict__ thr) {
+  pdl_wait();
+  pdl_launch_dependents();
   uint32_t n_sel;
   const int t = threshold_bin(hist + (long long)blockIdx.x * kBins, k, kMarginBins, &n_sel);
   if (threadIdx.x == 0) thr[blockIdx.x] = t;
@@ -295,6 +299,8 @@ __global__ void __launch_bounds__(kMemThreads)
 k_blk_select(const __half* __restrict__ sims16, long long ld, const float* __restrict__ bmax, long long ld_b, int n_blk,
              const int32_t* __restrict__ thr, int32_t* __restrict__ cand, int32_t* __restrict__ cand_count,
              int32_t* __restrict__ overflow) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int qi = blockIdx.y;
   const int b0 = blockIdx.x * kBlkChunk;
   const int t = thr[qi];
@@ -331,6 +337,8 @@ __global__ void __launch_bounds__(kMemThreads)
 k_keys_hist(const unsigned long long* __restrict__ keys, long long stride, const int32_t* __restrict__ counters,
             uint32_t* __restrict__ hist, int chunk) {
   __shared__ uint32_t h[kBins];
+  pdl_wait();
+  pdl_launch_dependents();
   const int qi = blockIdx.y;
   const int n_slots = counters[0];
   const int slot0 = blockIdx.x * chunk;
@@ -354,6 +362,8 @@ __global__ void __launch_bounds__(kMemThreads)
 k_keys_select(const unsigned long long* __restrict__ keys, long long stride, const int32_t* __restrict__ counters,
               const uint32_t* __restrict__ hist, int k, unsigned long long* __restrict__ cand_keys, int32_t* __restrict__ cand_count,
               int32_t* __restrict__ overflow, int chunk) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int qi = blockIdx.y, tid = threadIdx.x;
   const int n_slots = counters[0];
   const int slot0 = blockIdx.x * chunk;
@@ -383,6 +393,8 @@ k_batch_rescore(const bscnav_geom_t g, const float* __restrict__ feat, const flo
                 const uint8_t* __restrict__ row_ok, const int32_t* __restrict__ slot_cell, const float* __restrict__ q,
                 const float* __restrict__ qn2, const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_count,
                 const int32_t* __restrict__ overflow, unsigned long long* __restrict__ keys) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int qi = blockIdx.y, lane = threadIdx.x & 31;
   const int D = g.dim, C = g.cache;
   const int n = overflow[qi] ? 0 : min(cand_count[qi], kCandCap);
@@ -414,9 +426,12 @@ k_batch_rescore(const bscnav_geom_t g, const float* __restrict__ feat, const flo
 // power of two above the candidate count instead of the full 4096 the shared chunk sorter always sorts
 __global__ void __launch_bounds__(1024)
 k_sort_candidates(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ cand_count,
-                  const int32_t* __restrict__ overflow, int k, unsigned long long* __restrict__ sorted) {
+                  const int32_t* __restrict__ overflow, int k, unsigned long long* __restrict__ sorted, int32_t* __restrict__ zero_count) {
   __shared__ unsigned long long s[kCandCap];
+  pdl_wait();
+  pdl_launch_dependents();
   const int qi = blockIdx.x;
+  if (zero_count && threadIdx.x == 0) zero_count[qi] = 0;        // the decode stage counts its results with atomics
   const int n = overflow[qi] ? 0 : min(cand_count[qi], kCandCap);
   int S = 32;
   while (S < n) S <<= 1;
@@ -438,6 +453,8 @@ k_sort_candidates(const unsigned long long* __restrict__ keys, const int32_t* __
 }
 
 __global__ void k_mark_overflow(const int32_t* __restrict__ overflow, int n_query, int32_t* __restrict__ out_count) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_query && overflow[i]) out_count[i] = -1;
 }
@@ -471,6 +488,10 @@ static int64_t batch_layout(const bscnav_geom_t* g, int n_query, int k, long lon
   return off;
 }
 
+int64_t exact_select_zero_bytes(int n_query) {
+  return align_up((long long)n_query * kBins * 4, 256) + 2 * align_up((long long)n_query * 4, 256);
+}
+
 int64_t exact_select_scratch_bytes(int n_query) {
   return align_up((long long)n_query * kBins * 4, 256) + 2 * align_up((long long)n_query * 4, 256) +
          align_up((long long)n_query * kCandCap * 8, 256);
@@ -479,7 +500,8 @@ int64_t exact_select_scratch_bytes(int n_query) {
 // keys [n_query][stride] (composite keys, BSCNAV_KEY_EMPTY = not a candidate) -> sorted [n_query][k] ascending; queries whose
 // k-th bin holds more than kCandCap keys are flagged in *overflow_out (device int32[n_query]) and left to the caller
 int launch_exact_select(const unsigned long long* keys, long long stride, const int32_t* counters, int max_slots, int n_query, int k,
-                        void* scratch, unsigned long long* sorted, int32_t** overflow_out, cudaStream_t stream) {
+                        void* scratch, unsigned long long* sorted, int32_t** overflow_out, cudaStream_t stream, bool zeroed,
+                        int32_t* zero_count) {
   char* base = static_cast<char*>(scratch);
   uint32_t* hist = reinterpret_cast<uint32_t*>(base);
   base += align_up((long long)n_query * kBins * 4, 256);
@@ -488,17 +510,20 @@ int launch_exact_select(const unsigned long long* keys, long long stride, const 
   int32_t* overflow = reinterpret_cast<int32_t*>(base);
   base += align_up((long long)n_query * 4, 256);
   unsigned long long* cand_keys = reinterpret_cast<unsigned long long*>(base);
-  BSC_CUDA(cudaMemsetAsync(hist, 0, (size_t)n_query * kBins * 4, stream));
-  BSC_CUDA(cudaMemsetAsync(cand_count, 0, (size_t)n_query * 4, stream));
-  BSC_CUDA(cudaMemsetAsync(overflow, 0, (size_t)n_query * 4, stream));
+  if (!zeroed) {
+    BSC_CUDA(cudaMemsetAsync(hist, 0, (size_t)n_query * kBins * 4, stream));
+    BSC_CUDA(cudaMemsetAsync(cand_count, 0, (size_t)n_query * 4, stream));
+    BSC_CUDA(cudaMemsetAsync(overflow, 0, (size_t)n_query * 4, stream));
+  }
   // at most eight queries per call: small chunks, so that a few hundred blocks share the 2 MB of keys per query (with the batch
   // path's 8192-cell chunks the two stages were latency-bound at ~21 us each)
   const int chunk = 1024;
   const unsigned blocks = (unsigned)((max_slots + chunk - 1) / chunk);
-  BSC_LAUNCH(k_keys_hist, dim3(blocks, (unsigned)n_query), kMemThreads, 0, stream, keys, stride, counters, hist, chunk);
-  BSC_LAUNCH(k_keys_select, dim3(blocks, (unsigned)n_query), kMemThreads, 0, stream, keys, stride, counters, hist, k, cand_keys,
-             cand_count, overflow, chunk);
-  BSC_LAUNCH(k_sort_candidates, (unsigned)n_query, 1024, 0, stream, cand_keys, cand_count, overflow, k, sorted);
+  BSC_LAUNCH_PDL(k_keys_hist, dim3(blocks, (unsigned)n_query), kMemThreads, 0, stream, keys, stride, counters, hist, chunk);
+  BSC_LAUNCH_PDL(k_keys_select, dim3(blocks, (unsigned)n_query), kMemThreads, 0, stream, keys, stride, counters, (const uint32_t*)hist, k,
+                 cand_keys, cand_count, overflow, chunk);
+  BSC_LAUNCH_PDL(k_sort_candidates, (unsigned)n_query, 1024, 0, stream, (const unsigned long long*)cand_keys, (const int32_t*)cand_count,
+                 (const int32_t*)overflow, k, sorted, zero_count);
   *overflow_out = overflow;
   return BSCNAV_OK;
 }
@@ -567,10 +592,10 @@ int bscnav_query_topk_batch(const bscnav_geom_t* g, const bscnav_store_t* st, co
       epi.mode = kOutSims; epi.mask = s.row_ok; epi.aux = s.bmax; epi.ld_aux = n_blk;
       if (int e = gemm_f16_launch(&map_a, &map_w, &map_o, P, (int)N, D, epi, stream, &map_wh)) return e;
       const unsigned blk_blocks = (unsigned)((n_blk + kBlkChunk - 1) / kBlkChunk);
-      BSC_LAUNCH(k_blk_hist, dim3(blk_blocks, (unsigned)P), kMemThreads, 0, stream, s.bmax, (long long)n_blk, n_blk, s.hist);
-      BSC_LAUNCH(k_blk_threshold, (unsigned)P, kMemThreads, 0, stream, s.hist, k, s.thr);
-      BSC_LAUNCH(k_blk_select, dim3(blk_blocks, (unsigned)P), kMemThreads, 0, stream, reinterpret_cast<const __half*>(s.sims), N,
-                 s.bmax, (long long)n_blk, n_blk, s.thr, s.cand, s.cand_count, s.overflow);
+      BSC_LAUNCH_PDL(k_blk_hist, dim3(blk_blocks, (unsigned)P), kMemThreads, 0, stream, (const float*)s.bmax, (long long)n_blk, n_blk, s.hist);
+      BSC_LAUNCH_PDL(k_blk_threshold, (unsigned)P, kMemThreads, 0, stream, (const uint32_t*)s.hist, k, s.thr);
+      BSC_LAUNCH_PDL(k_blk_select, dim3(blk_blocks, (unsigned)P), kMemThreads, 0, stream, reinterpret_cast<const __half*>(s.sims), (long long)N,
+                     (const float*)s.bmax, (long long)n_blk, n_blk, (const int32_t*)s.thr, s.cand, s.cand_count, s.overflow);
     } else {
       epi.mode = kOutFloat;
       if (int e = gemm_f16_launch(&map_a, &map_w, nullptr, P, (int)N, D, epi, stream)) return e;
@@ -579,12 +604,14 @@ int bscnav_query_topk_batch(const bscnav_geom_t* g, const bscnav_store_t* st, co
       BSC_LAUNCH(k_batch_select, dim3((unsigned)slot_blocks, (unsigned)P), kMemThreads, 0, stream, s.sims, N, s.row_ok, st->counters,
                  C, s.hist, k, s.cand, s.cand_count, s.overflow);
     }
-    BSC_LAUNCH(k_batch_rescore, dim3(16, (unsigned)P), kMemThreads, 0, stream, *g, st->feat, st->norm2, s.row_ok, st->slot_cell, qp,
-               s.qn2, s.cand, s.cand_count, s.overflow, s.keys);
-    BSC_LAUNCH(k_sort_candidates, (unsigned)P, 1024, 0, stream, s.keys, s.cand_count, s.overflow, k, s.sorted);
+    BSC_LAUNCH_PDL(k_batch_rescore, dim3(16, (unsigned)P), kMemThreads, 0, stream, *g, (const float*)st->feat, (const float*)st->norm2,
+                   (const uint8_t*)s.row_ok, (const int32_t*)st->slot_cell, qp, (const float*)s.qn2, (const int32_t*)s.cand,
+                   (const int32_t*)s.cand_count, (const int32_t*)s.overflow, s.keys);
+    BSC_LAUNCH_PDL(k_sort_candidates, (unsigned)P, 1024, 0, stream, (const unsigned long long*)s.keys, (const int32_t*)s.cand_count,
+                   (const int32_t*)s.overflow, k, s.sorted, (int32_t*)nullptr);
     if (int e = launch_topk_decode(g, st, s.sorted, k, k, qp, P, out_sim + (long long)q0 * k, out_pos + (long long)q0 * k * 3,
                                    out_count + q0, stream)) return e;
-    BSC_LAUNCH(k_mark_overflow, (P + 255) / 256, 256, 0, stream, s.overflow, P, out_count + q0);
+    BSC_LAUNCH_PDL(k_mark_overflow, (P + 255) / 256, 256, 0, stream, (const int32_t*)s.overflow, P, out_count + q0);
   }
   return BSCNAV_OK;
 }

@@ -66,7 +66,13 @@ k_build_shadow(const float* __restrict__ feat, const int32_t* __restrict__ count
 // queries: squared norm with the association k_query_slots uses (so the exact re-scoring matches it bit for bit) and
 // the unit-normalised fp16 operand of the GEMM; one warp per query
 __global__ void __launch_bounds__(kMemThreads)
-k_prep_queries(const float* __restrict__ q, int n_query, int D, __half* __restrict__ qh, float* __restrict__ qn2) {
+k_prep_queries(const float* __restrict__ q, int n_query, int D, __half* __restrict__ qh, float* __restrict__ qn2,
+               uint32_t* __restrict__ zero_words, long long n_zero, unsigned long long* __restrict__ empty_keys, long long n_keys) {
+  // the pass's histogram / counters / flags start from zero and its candidate keys from KEY_EMPTY: filled here (grid-stride over
+  // the whole grid) instead of by four memsets between the kernels of the pass
+  for (long long i = (long long)blockIdx.x * kMemThreads + threadIdx.x; i < n_zero; i += (long long)gridDim.x * kMemThreads) zero_words[i] = 0u;
+  for (long long i = (long long)blockIdx.x * kMemThreads + threadIdx.x; i < n_keys; i += (long long)gridDim.x * kMemThreads)
+    empty_keys[i] = BSCNAV_KEY_EMPTY;
   const int lane = threadIdx.x & 31;
   const int qi = blockIdx.x * (kMemThreads / 32) + (threadIdx.x >> 5);
   if (qi >= n_query) return;
@@ -574,13 +580,15 @@ int bscnav_query_topk_batch(const bscnav_geom_t* g, const bscnav_store_t* st, co
   for (int q0 = 0; q0 < n_query; q0 += kPassQueries) {
     const int P = n_query - q0 < kPassQueries ? n_query - q0 : kPassQueries;
     const float* qp = q + (long long)q0 * D;
-    BSC_LAUNCH(k_prep_queries, (P + kMemThreads / 32 - 1) / (kMemThreads / 32), kMemThreads, 0, stream, qp, P, D, s.qh, s.qn2);
+    {
+      // hist, cand_count and overflow are consecutive in the scratch layout: one span of words to clear
+      const long long n_zero = (reinterpret_cast<char*>(s.overflow) + (size_t)P * 4 - reinterpret_cast<char*>(s.hist)) / 4;
+      const int need = (P + kMemThreads / 32 - 1) / (kMemThreads / 32), fill = mem_num_sms() * 4;
+      BSC_LAUNCH(k_prep_queries, need > fill ? need : fill, kMemThreads, 0, stream, qp, P, D, s.qh, s.qn2,
+                 reinterpret_cast<uint32_t*>(s.hist), n_zero, s.keys, (long long)P * kCandCap);
+    }
     CUtensorMap map_a;
     if (int e = make_operand_map(&map_a, s.qh, align_up(P, 128), D, 128)) return e;   // rows past P: never stored (M = P)
-    BSC_CUDA(cudaMemsetAsync(s.hist, 0, (size_t)P * kBins * 4, stream));
-    BSC_CUDA(cudaMemsetAsync(s.cand_count, 0, (size_t)P * 4, stream));
-    BSC_CUDA(cudaMemsetAsync(s.overflow, 0, (size_t)P * 4, stream));
-    BSC_CUDA(cudaMemsetAsync(s.keys, 0xFF, (size_t)P * kCandCap * 8, stream));       // BSCNAV_KEY_EMPTY
     GemmEpilogue epi{};
     epi.out = s.sims; epi.ld_out = N;
     if (C == 1) {

@@ -533,7 +533,28 @@ def run_ours(args):
         whole = cfg.flops_per_frame() * F * K / world / (ms / 1e3) / 1e12
         roofline = {"bound": "tensor", "kernel": "whole step (per rank)", "achieved": whole, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": whole / peak_tf, "traffic": None, "peak_source": peak_src}
-        e2e = None
+        # ---- e2e: the same scene through the public API (dist.fuse_scene_sharded: VoxelTokenMemory.fuse_frames on pinned host
+        # frames per rank, H2D inside the timed region, then the packed all-gather merge and a D2H read of the slot count)
+        scene_poses = poses_of(0, F)
+
+        def load_frames(f0, n):
+            i = f0 % (P - B + 1)
+            return rgb_h[i:i + n], dep_h[i:i + n]
+
+        slots_e2e = []
+
+        def build_scene_api(_s):
+            mem._clear_memory()
+            dmod.fuse_scene_sharded(mem, scene_poses, load_frames, B, max_rows=GS * GS)
+            slots_e2e.append(mem.max_id_wait(mem.max_id_async()))
+
+        build_scene_api(0)
+        ms_e2e = timed(build_scene_api, K)
+        assert slots_e2e[-1] == slots, (slots_e2e, slots)          # same scene, same merged store as the device-resident run
+        e2e = {"value": F * K / (ms_e2e / 1e3), "unit": "frames/s",
+               "h2d_bytes_per_step": F * (H * W * 4 + H * W * 4 + 16 * 8 + 4), "d2h_bytes_per_step": 16 + (8 * world if world > 1 else 0),
+               "api": "dist.fuse_scene_sharded (VoxelTokenMemory.begin_shard + fuse_frames per batch, merge_scene_across_ranks) + max_id",
+               "slots_after": slots_e2e[-1]}
         step_ms = ms / K
         cfg_extra = {"batch_frames_per_gpu": B, "frames_per_step": F, "scene_frames": F,
                      "l2": f"inputs larger than L2: pool of {P} images per rank, poses never repeat",

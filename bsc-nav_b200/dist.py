@@ -78,6 +78,29 @@ def merge_scene_across_ranks(store, ord_lo: int, ord_hi: int, max_rows: int, gro
     return host[:, 0].tolist()
 
 
+def fuse_scene_sharded(mem, poses, load_frames, batch: int, group=None, max_rows=None):
+    """Build ONE scene with its frames sharded over the ranks of `group` (BASELINE configs[4]): rank r fuses the contiguous shard
+    shard_frames(F, r, world) through the facade's batched build step (VoxelTokenMemory.fuse_frames: host buffers in, copies and
+    scatter overlapped with the ViT), then the ranks exchange what they stored (merge_scene_across_ranks: one packed all-gather)
+    so that every rank ends with the kept-token set of the whole scene.  poses: (F, 7) of the whole scene, the same on every
+    rank; load_frames(f0, n) -> (rgb (n,H,W,3|4) uint8, depth (n,H,W) float32) for frames f0 .. f0 + n - 1.  Returns the per-rank
+    export counts (None on one rank)."""
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)
+    poses = np.asarray(poses, dtype=np.float64).reshape(-1, 7)
+    shard = shard_frames(len(poses), rank, world)
+    mem.begin_shard(poses[0], shard.start)
+    for f0 in range(shard.start, shard.stop, batch):
+        n = min(batch, shard.stop - f0)
+        rgb, depth = load_frames(f0, n)
+        mem.fuse_frames(rgb, depth, poses[f0:f0 + n])
+    mem._join()
+    if world == 1:
+        return None
+    npts = mem.args.height * mem.args.width
+    return merge_scene_across_ranks(mem._store, shard.start * npts, shard.stop * npts,
+                                    max_rows if max_rows is not None else mem._store.g.max_slots * mem._store.g.cache, group)
+
+
 def merge_self_check(group=None, cache: int = 3, bev: bool = False) -> list:
     """Parity check of the collective path on the ranks of `group` (run by tests/multi_rank_merge.py and once by every
     `bench.py --gpus N` run, N > 1): a small scene whose frames are sharded over the ranks (shard_frames), fused per rank and

@@ -277,6 +277,15 @@ class VoxelTokenMemory:
             self._in_free[slot] = (ev, done)
         self.tf = self._chain.tf
 
+    def begin_shard(self, origin_pose, first_frame: int):
+        """One scene whose frames are split over ranks (dist.shard_frames, dist.fuse_scene_sharded): anchor the pose chain on the
+        scene's FIRST pose (the reference takes the origin from its first observation, memory_2.py:844-851; a shard that starts
+        later must not take its own) and number this rank's points from its shard's first frame, so that the token-store rule
+        (smaller r^2, then the earlier point) decides across ranks as it does in a single build."""
+        self._chain.reset()
+        self._chain(np.asarray(origin_pose, dtype=np.float64).reshape(7))
+        self._store.next_ordinal = int(first_frame) * self.args.height * self.args.width
+
     def fuse_device(self, rgb_dev, depth_dev, tfs, sample_idx=None, ord_base=None):
         """ViT on the current stream, then unprojection + scatter on the side stream.  Returns the event that marks the
         end of the scatter.  Inputs are device tensors that stay valid until that event."""

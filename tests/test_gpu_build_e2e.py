@@ -160,3 +160,53 @@ def test_numpy_tight_loop_equals_device_path(pkg):
     assert n1 == n2 and n1 > 100
     for k in a1:
         assert torch.equal(a1[k], a2[k]), k
+
+
+def _canon_store(st):
+    """Order-independent view of a store: {cell: [(r^2, ordinal, height, checksum of the token row)]} (slot numbers differ
+    between a joint build and a merged one; the kept-token set may not)."""
+    return {k: [(float(t[0]), int(t[1]), int(t[2]), float(np.dot(t[3].astype(np.float64), np.arange(1, t[3].size + 1)))) for t in v]
+            for k, v in st.snapshot().items()}
+
+
+@pytest.mark.parametrize("cache,bev", [(1, True), (3, False)])
+def test_sharded_build_through_the_facade_equals_joint_build(pkg, cache, bev):
+    """BASELINE configs[4] through the public API: two memories each fuse a contiguous shard of one scene's frames
+    (VoxelTokenMemory.begin_shard + fuse_frames, the calls dist.fuse_scene_sharded makes on every rank), exchange their packed
+    rows, and both end with exactly the joint build's kept tokens.  The second shard's pose chain must hang on the scene's first
+    pose and its points must be numbered after the first shard's (ties between shards go to the earlier frame)."""
+    synth = importlib.import_module("bsc-nav_b200.synth")
+    h, w, gs, n, bsz = 96, 128, 64, 12, 3
+    cfg = pkg.tiny(pkg.CLIP_L14, dim=128, depth=2, heads=2, mlp=256)
+    eng = pkg.ViTEngine(cfg, pkg.random_weights(cfg, seed=2, perturb=True), max_batch=bsz)
+    args = synth.Args(height=h, width=w, grid_size=gs, depth_sample_rate=1, floor_height=-2.0, map_height=2.0)
+    frames = [synth.synthetic_frame(f % 5, h, w, n_frames=9) for f in range(n)]     # frames 5.. repeat 0..: exact r^2 ties across shards
+    rgb, depth, poses = (np.stack([f[i] for f in frames]) for i in range(3))
+
+    def new():
+        return pkg.VoxelTokenMemory(args, preload_dino=eng, need_diffusion=False, cache_size=cache, bev=bev, max_batch=bsz, max_slots=65536)
+
+    joint = new()
+    for f0 in range(0, n, bsz):
+        joint.fuse_frames(rgb[f0:f0 + bsz], depth[f0:f0 + bsz], poses[f0:f0 + bsz])
+    joint._join()
+    cut = 6
+    shards = []
+    for lo, hi in ((0, cut), (cut, n)):
+        m = new()
+        m.begin_shard(poses[0], lo)
+        for f0 in range(lo, hi, bsz):
+            m.fuse_frames(rgb[f0:f0 + bsz], depth[f0:f0 + bsz], poses[f0:f0 + bsz])
+        m._join()
+        shards.append((m, lo * h * w, hi * h * w))
+    packed = [m.store.export_packed(lo, hi, 65536) for m, lo, hi in shards]
+    cap = max(int(nd[0]) for _, nd in packed)
+    rows = torch.cat([p[:cap] for p, _ in packed])
+    counts = torch.cat([nd for _, nd in packed])
+    ref = _canon_store(joint.store)
+    assert len(ref) > 100
+    for r, (m, _, _) in enumerate(shards):
+        m.store.merge_packed(rows, 2, cap, counts, count_stride=2, skip_segment=r)
+        got = _canon_store(m.store)
+        bad = [k for k in set(ref) | set(got) if ref.get(k) != got.get(k)]
+        assert not bad, (r, len(bad), bad[:3], [ref.get(k) for k in bad[:2]], [got.get(k) for k in bad[:2]])

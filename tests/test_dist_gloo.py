@@ -149,3 +149,111 @@ def test_merge_topk_against_brute_force():
             assert [tuple(v) for v in p[qi, :len(exp)].tolist()] == [e[0] for e in exp]
             assert s[qi, :len(exp)].tolist() == [float(np.float32(e[1])) for e in exp]
             assert torch.all(s[qi, len(exp):] == float("-inf")) and torch.all(p[qi, len(exp):] == -1)
+
+
+# ---- dist.fuse_scene_sharded / merge_scene_across_ranks: the collective protocol with a host stand-in for the device store
+_ROW = np.dtype([("cell", "<i4"), ("h", "<i4"), ("key", "<u8"), ("feat", "<f4", (4,))])      # packed export row, 16 + 4 D bytes
+
+
+def _frame_points(f, n_pts):
+    """What frame f writes: (cell, key, h, token row) per point; keys {r^2 bits, ordinal} as the kernels build them."""
+    rng = np.random.default_rng(7 + f % 3)                 # frames f and f + 3 see the same cells at the same r^2: ordinal ties
+    cell = rng.integers(0, 40, size=n_pts).astype(np.int32)
+    r2 = rng.uniform(0.2, 4.0, size=n_pts).astype(np.float32)
+    ordinal = np.arange(n_pts, dtype=np.uint64) + np.uint64(f * n_pts)
+    key = (r2.view(np.uint32).astype(np.uint64) << np.uint64(32)) | ordinal
+    feat = np.stack([np.full(4, f * 1000 + i, dtype=np.float32) for i in range(n_pts)])
+    return cell, key, (cell % 7).astype(np.int32), feat
+
+
+class _HostStore:
+    """C = 1 store under the winner rule min (r^2, ordinal), with the packed export / merge interface of SpatialStore."""
+    device = torch.device("cpu")
+
+    def __init__(self):
+        self.cells = {}
+        self.next_ordinal = 0
+
+    def put(self, cell, key, h, feat):
+        for c, k, hh, ft in zip(cell.tolist(), key.tolist(), h.tolist(), feat):
+            if c not in self.cells or k < self.cells[c][0]:
+                self.cells[c] = (k, hh, ft.copy())
+
+    def export_packed(self, ord_lo, ord_hi, max_out):
+        rows = [(c, hh, k, ft) for c, (k, hh, ft) in sorted(self.cells.items()) if ord_lo <= (k & 0xFFFFFFFF) < ord_hi]
+        out = np.zeros(max_out, dtype=_ROW)
+        for i, r in enumerate(rows[:max_out]):
+            out[i] = r
+        n = torch.tensor([min(len(rows), max_out), len(rows)], dtype=torch.int32)
+        return torch.from_numpy(out.view(np.uint8).reshape(max_out, _ROW.itemsize)), n
+
+    def merge_packed(self, packed, n_segments, seg_capacity, seg_counts, count_stride=2, skip_segment=-1):
+        rows = packed.numpy().reshape(-1).view(_ROW).reshape(n_segments, seg_capacity)
+        for s in range(n_segments):
+            if s != skip_segment:
+                r = rows[s, :int(seg_counts[s * count_stride])]
+                self.put(r["cell"], r["key"], r["h"], r["feat"])
+
+
+class _HostMemory:
+    """The calls fuse_scene_sharded makes on VoxelTokenMemory, recorded and applied to a _HostStore."""
+
+    def __init__(self, h, w):
+        import types
+        self.args = types.SimpleNamespace(height=h, width=w)
+        self._store = _HostStore()
+        self.origin = None
+        self.fed = []
+
+    def begin_shard(self, origin_pose, first_frame):
+        self.origin = np.asarray(origin_pose).copy()
+        self._store.next_ordinal = first_frame * self.args.height * self.args.width
+
+    def fuse_frames(self, rgb, depth, poses):
+        n_pts = self.args.height * self.args.width
+        for f in rgb.tolist():                                         # "rgb" carries the global frame numbers
+            assert self._store.next_ordinal == f * n_pts               # points numbered by GLOBAL frame index on every rank
+            self._store.put(*_frame_points(f, n_pts))
+            self._store.next_ordinal += n_pts
+            self.fed.append(f)
+        assert len(poses) == len(rgb)
+
+    def _join(self):
+        pass
+
+
+def _scene_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = importlib.import_module("bsc-nav_b200.dist")
+    F = 11
+    poses = np.arange(F * 7, dtype=np.float64).reshape(F, 7)
+    mem = _HostMemory(2, 3)
+    counts = d.fuse_scene_sharded(mem, poses, lambda f0, n: (np.arange(f0, f0 + n), None), batch=4, max_rows=64)
+    assert np.array_equal(mem.origin, poses[0])                        # every shard hangs on the scene's first pose
+    assert mem.fed == list(d.shard_frames(F, rank, world))
+    cells = mem._store.cells
+    np.savez(os.path.join(out_dir, f"s{rank}.npz"), cell=np.array(sorted(cells)), key=np.array([cells[c][0] for c in sorted(cells)], dtype=np.uint64),
+             feat=np.stack([cells[c][2] for c in sorted(cells)]), counts=np.array(counts))
+    try:                                                                # a rank that produced more rows than max_rows is an error
+        d.merge_scene_across_ranks(mem._store, 0, 2 ** 32, 3)
+        raised = False
+    except RuntimeError:
+        raised = True
+    assert raised
+    dist.destroy_process_group()
+
+
+def test_fuse_scene_sharded_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_scene_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    joint = _HostStore()
+    for f in range(11):
+        joint.put(*_frame_points(f, 6))
+    want_cells = np.array(sorted(joint.cells))
+    for r in range(2):
+        got = np.load(tmp_path / f"s{r}.npz")
+        assert np.array_equal(got["cell"], want_cells)
+        assert np.array_equal(got["key"], np.array([joint.cells[c][0] for c in want_cells], dtype=np.uint64))
+        assert np.array_equal(got["feat"], np.stack([joint.cells[c][2] for c in want_cells]))
+        assert got["counts"].tolist() == np.load(tmp_path / "s0.npz")["counts"].tolist() and len(got["counts"]) == 2

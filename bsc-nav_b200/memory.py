@@ -94,6 +94,7 @@ class VoxelTokenMemory:
         self._tok_free = [None, None]
         self._tok_slot = 0
         self._last_fuse = None
+        self._last_fuse_stream = None
 
     # ------------------------------------------------------------------ state
     def _init_cache(self):
@@ -321,6 +322,7 @@ class VoxelTokenMemory:
             done.record(side)
         self._tok_free[k] = done
         self._last_fuse = done
+        self._last_fuse_stream = side
         return done
 
     def _join(self):
@@ -329,9 +331,16 @@ class VoxelTokenMemory:
             torch.cuda.current_stream().wait_event(self._last_fuse)
 
     def max_id_async(self):
-        """Non-blocking read of max_id: enqueues the device->host copy, returns a handle for max_id_wait()."""
-        self._join()
-        return self._store.count_async()
+        """Non-blocking read of max_id: enqueues the device->host copy, returns a handle for max_id_wait().  The copy goes on the
+        stream the last scatter ran on, behind it: the current stream does not wait for the scatter, so the next batch's ViT
+        still overlaps it."""
+        side = self._last_fuse_stream
+        if side is None or self._last_fuse is None:
+            return self._store.count_async()
+        with torch.cuda.stream(side):
+            handle = self._store.count_async()
+        self._last_fuse = handle[1]           # a later _join() (reset, query, save) also waits for this copy
+        return handle
 
     def max_id_wait(self, handle) -> int:
         return self._store.count_wait(handle)

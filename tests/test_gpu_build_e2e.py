@@ -210,3 +210,31 @@ def test_sharded_build_through_the_facade_equals_joint_build(pkg, cache, bev):
         got = _canon_store(m.store)
         bad = [k for k in set(ref) | set(got) if ref.get(k) != got.get(k)]
         assert not bad, (r, len(bad), bad[:3], [ref.get(k) for k in bad[:2]], [got.get(k) for k in bad[:2]])
+
+
+def test_max_id_async_per_batch_matches_synchronous_counts(pkg):
+    """bench.py's e2e leg reads max_id after every batch without stalling the pipeline (the copy rides the scatter's stream):
+    every handle must report the slot count a synchronous build reports after the same batch, and a reset issued right after
+    an asynchronous read must not disturb it."""
+    synth = importlib.import_module("bsc-nav_b200.synth")
+    h, w, gs, nb, bsz = 96, 128, 64, 10, 3
+    cfg = pkg.tiny(pkg.CLIP_L14, dim=128, depth=2, heads=2, mlp=256)
+    eng = pkg.ViTEngine(cfg, pkg.random_weights(cfg, seed=2, perturb=True), max_batch=bsz)
+    args = synth.Args(height=h, width=w, grid_size=gs, depth_sample_rate=1, floor_height=-2.0, map_height=2.0)
+    frames = [synth.synthetic_frame(f, h, w, n_frames=nb * bsz) for f in range(nb * bsz)]
+    rgb, depth, poses = (np.stack([f[i] for f in frames]) for i in range(3))
+    sync = pkg.VoxelTokenMemory(args, preload_dino=eng, need_diffusion=False, cache_size=1, max_batch=bsz, max_slots=65536)
+    want = []
+    for b in range(nb):
+        s = slice(b * bsz, (b + 1) * bsz)
+        sync.fuse_frames(rgb[s], depth[s], poses[s])
+        want.append(sync.max_id)
+    mem = pkg.VoxelTokenMemory(args, preload_dino=eng, need_diffusion=False, cache_size=1, max_batch=bsz, max_slots=65536)
+    handles = []
+    for b in range(nb):
+        s = slice(b * bsz, (b + 1) * bsz)
+        mem.fuse_frames(rgb[s], depth[s], poses[s])
+        handles.append(mem.max_id_async())
+    mem._clear_memory()                                     # queued behind the last asynchronous read
+    assert [mem.max_id_wait(hd) for hd in handles] == want and want == sorted(want) and want[-1] > want[0] > 0
+    assert mem.max_id == 0

@@ -186,6 +186,65 @@ k_count_new(const uint4* __restrict__ rec, long long total, const int32_t* __res
   if (threadIdx.x == 0) tile_count[blockIdx.x] = tot;
 }
 
+// K2a / K2c with k_index_points' mask: one WARP per 1024-point tile, lane l owns mask word l (32 consecutive points).  In steady
+// state a batch of 16.9 M points has ~10^3 first touches: nearly every word is zero, and a block per tile with its block-wide
+// scans (the unmasked forms above / below, still used by the merge path) cost 48 + 21 us in launches and barriers alone.
+__device__ __forceinline__ uint32_t first_toucher_bits(uint32_t word, long long word_base, long long total, const uint4* __restrict__ rec,
+                                                       const int32_t* __restrict__ occupied, const uint32_t* __restrict__ first_touch) {
+  uint32_t out = 0;
+  while (word) {
+    const int b = __ffs(word) - 1;
+    word &= word - 1;
+    const long long i = word_base + b;
+    if (i < total && is_first_toucher(rec[i], occupied, first_touch)) out |= 1u << b;
+  }
+  return out;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_count_new_masked(const uint4* __restrict__ rec, long long total, const int32_t* __restrict__ occupied,
+                   const uint32_t* __restrict__ first_touch, int* __restrict__ tile_count, const uint32_t* __restrict__ fresh,
+                   int n_tiles) {
+  const int tile = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (tile >= n_tiles) return;
+  const uint32_t word = fresh[(long long)tile * (kTile / 32) + lane];
+  int c = 0;
+  if (__any_sync(0xffffffffu, word != 0u)) {
+    c = __popc(first_toucher_bits(word, (long long)tile * kTile + lane * 32, total, rec, occupied, first_touch));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  if (lane == 0) tile_count[tile] = c;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_assign_slots_masked(const uint4* __restrict__ rec, long long total, int32_t* __restrict__ occupied,
+                      const uint32_t* __restrict__ first_touch, const int* __restrict__ tile_off, const int* __restrict__ hdr,
+                      int32_t* __restrict__ slot_cell, const uint32_t* __restrict__ fresh, const int* __restrict__ tile_count,
+                      int n_tiles) {
+  const int tile = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (tile >= n_tiles || !hdr[1] || tile_count[tile] == 0) return;
+  const long long word_base = (long long)tile * kTile + lane * 32;
+  uint32_t ft = first_toucher_bits(fresh[(long long)tile * (kTile / 32) + lane], word_base, total, rec, occupied, first_touch);
+  const int c = __popc(ft);
+  int inc = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  int rank = tile_off[tile] + hdr[0] + inc - c;
+  __syncwarp();                         // every flag of the tile is read before any cell of it is marked (see k_assign_slots)
+  while (ft) {
+    const int b = __ffs(ft) - 1;
+    ft &= ft - 1;
+    const int cell = (int)rec[word_base + b].x;
+    slot_cell[rank] = cell;
+    occupied[cell] = rank;
+    ++rank;
+  }
+}
+
 // K2b: exclusive scan of the tile counts (single block), slot-range reservation, capacity check.
 // One block of 1024 threads, every thread owns a contiguous run of tiles: two serial passes over the run around one block-wide
 // scan of the 1024 partial sums (a loop of 256-wide block scans took 57 us for the 16 500 tiles of a 54-frame batch).
@@ -839,10 +898,19 @@ static int run_store_update(const bscnav_geom_t* g, const bscnav_store_t* st, co
                             const float* tokens, long long tok_stride, const uint32_t* fresh, cudaStream_t stream) {
   const int n_tiles = (int)((total + kTile - 1) / kTile);
   const int n_blocks = (int)((total + kThreads - 1) / kThreads);
-  BSC_LAUNCH(k_count_new, n_tiles, kThreads, 0, stream, s.rec, total, st->occupied_ids, st->first_touch, s.tile_count, fresh);
+  const int tile_blocks = (n_tiles + kThreads / 32 - 1) / (kThreads / 32);
+  if (fresh)
+    BSC_LAUNCH(k_count_new_masked, tile_blocks, kThreads, 0, stream, s.rec, total, st->occupied_ids, st->first_touch, s.tile_count,
+               fresh, n_tiles);
+  else
+    BSC_LAUNCH(k_count_new, n_tiles, kThreads, 0, stream, s.rec, total, st->occupied_ids, st->first_touch, s.tile_count, fresh);
   BSC_LAUNCH(k_scan_tiles, 1, kScanThreads, 0, stream, s.tile_count, s.tile_off, n_tiles, s.hdr, st->counters, g->max_slots);
-  BSC_LAUNCH(k_assign_slots, n_tiles, kThreads, 0, stream, s.rec, total, st->occupied_ids, st->first_touch, s.tile_off,
-             s.hdr, st->slot_cell, fresh, s.tile_count);
+  if (fresh)
+    BSC_LAUNCH(k_assign_slots_masked, tile_blocks, kThreads, 0, stream, s.rec, total, st->occupied_ids, st->first_touch, s.tile_off,
+               s.hdr, st->slot_cell, fresh, s.tile_count, n_tiles);
+  else
+    BSC_LAUNCH(k_assign_slots, n_tiles, kThreads, 0, stream, s.rec, total, st->occupied_ids, st->first_touch, s.tile_off,
+               s.hdr, st->slot_cell, fresh, s.tile_count);
   BSC_LAUNCH(k_select, n_blocks, kThreads, 0, stream, s.rec, total, st->occupied_ids, st->first_touch,
              reinterpret_cast<unsigned long long*>(st->slot_keys), g->cache, s.cand, s.cand_n);
   const int want = (n_blocks + kThreads / 32 - 1) / (kThreads / 32), cap = num_sms() * 16;

@@ -329,6 +329,7 @@ class VoxelTokenMemory:
         """Make the current stream wait for the last scatter (before reading the store)."""
         if self._last_fuse is not None:
             torch.cuda.current_stream().wait_event(self._last_fuse)
+        self._last_fuse_stream = None          # what follows (merge, query, reset) runs on the current stream, ordered behind the scatter
 
     def max_id_async(self):
         """Non-blocking read of max_id: enqueues the device->host copy, returns a handle for max_id_wait().  The copy goes on the

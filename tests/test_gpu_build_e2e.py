@@ -210,6 +210,8 @@ def test_sharded_build_through_the_facade_equals_joint_build(pkg, cache, bev):
         got = _canon_store(m.store)
         bad = [k for k in set(ref) | set(got) if ref.get(k) != got.get(k)]
         assert not bad, (r, len(bad), bad[:3], [ref.get(k) for k in bad[:2]], [got.get(k) for k in bad[:2]])
+        # the asynchronous count issued after the merge sees the merged store (it must not ride the scatter stream past the merge)
+        assert m.max_id_wait(m.max_id_async()) == joint.max_id == m.max_id
 
 
 def test_max_id_async_per_batch_matches_synchronous_counts(pkg):

@@ -11,7 +11,7 @@ def __getattr__(name):
     import importlib
     lazy = {
         "SpatialStore": "store", "StoreConfig": "store", "ViTEngine": "vit", "pack_weights": "vit", "gaussian_pool": "vit",
-        "gemm_f16": "vit", "gemm_bf16x3": "vit", "load_state_dict": "weights", "load_checkpoint": "weights", "interpolate_pos_embed": "weights", "attention_f16": "vit", "score_views": "vit", "ViewChecker": "agent", "match_long_memory_label": "agent", "VoxelTokenMemory": "memory",
+        "gemm_f16": "vit", "gemm_f16_sliced": "vit", "gemm_bf16x3": "vit", "load_state_dict": "weights", "load_checkpoint": "weights", "interpolate_pos_embed": "weights", "attention_f16": "vit", "score_views": "vit", "ViewChecker": "agent", "match_long_memory_label": "agent", "VoxelTokenMemory": "memory",
         "Memory": "memory", "GESObjectNavRobot": "agent", "LocalizeAgent": "agent", "PoseChain": "geometry",
     }
     if name in lazy:

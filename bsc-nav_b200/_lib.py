@@ -101,6 +101,8 @@ _SIGS = {
     "bscnav_gemm_bf16x3": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "bscnav_debug_attention_ws2": (C.c_int, [C.c_int32, _P]),
     "bscnav_gemm_f16": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "bscnav_gemm_f16_sliced": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64,
+                                          C.POINTER(C.c_int32), _P]),
 }
 EXPORTS = tuple(_SIGS)
 

@@ -69,6 +69,7 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
   const uint32_t tfull_bar = empty_bar + 8 * C::kStages;          // 2 x 8 B
   const uint32_t tempty_bar = tfull_bar + 16;                     // 2 x 8 B
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 * (2 * C::kStages + 4));
+  volatile int* kflag = reinterpret_cast<volatile int*>(bars + 8 * (2 * C::kStages + 4) + 8);
   const uint32_t smem_base = smem_u32(smem);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -76,6 +77,9 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
   const int m_tiles = (M + BM - 1) / BM, n_tiles = N / BN, k_blocks = split ? 3 * kbk : kbk;
   const int m_groups = (m_tiles + CL - 1) / CL;             // CL == 2: pairs of row blocks (the last pair may be half empty)
   const int total_tiles = m_groups * n_tiles;
+  // K-sliced launches (small M, CL == 1 only): a work item is (tile, slice); the slices of a tile meet in the epilogue (below)
+  const int S = (CL == 1 && BN == 128 && (MODE == kOutResidual || MODE == kOutFloat) && epi.kslices > 1) ? epi.kslices : 1;
+  const int total_items = total_tiles * S;
   const int rank = CL == 2 ? (int)cluster_ctarank() : 0;
   const int tile0 = blockIdx.x / CL, tile_step = gridDim.x / CL;
   // Tile order.  m-fastest: the ~148 resident tiles share one weight panel (good when A fits L2, K <= N).
@@ -114,9 +118,11 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+      for (int item = tile0; item < total_items; item += tile_step) {
+        const int ks = S > 1 ? item / total_tiles : 0, tile = item - ks * total_tiles;
+        const int k_lo = S > 1 ? ks * k_blocks / S : 0, k_hi = S > 1 ? (ks + 1) * k_blocks / S : k_blocks;
         const int m_blk = (n_fastest ? tile / n_tiles : tile % m_groups) * CL + rank, n_blk = n_fastest ? tile % n_tiles : tile / m_groups;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int kb = k_lo; kb < k_hi; ++kb) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);       // CL == 2: released by the leader's commit in both CTAs
           const uint32_t a_dst = smem_base + stage * C::kStageBytes;
           const uint32_t b_dst = a_dst + C::kABytes;
@@ -146,11 +152,13 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+      for (int item = tile0; item < total_items; item += tile_step) {
+        const int ks = S > 1 ? item / total_tiles : 0;
+        const int k_lo = S > 1 ? ks * k_blocks / S : 0, k_hi = S > 1 ? (ks + 1) * k_blocks / S : k_blocks;
         mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int kb = k_lo; kb < k_hi; ++kb) {
           mbar_wait(full_bar + 8 * stage, phase);
           tcgen05_fence_after();
           const uint32_t a_addr = smem_base + stage * C::kStageBytes;
@@ -159,8 +167,8 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
             // advance 32 bytes (16 fp16) inside the swizzle atom: +2 in the (addr >> 4) field
-            if (CL == 2) tcgen05_mma_f16_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-            else tcgen05_mma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CL == 2) tcgen05_mma_f16_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, ((kb - k_lo) | k) != 0 ? 1u : 0u);
+            else tcgen05_mma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, ((kb - k_lo) | k) != 0 ? 1u : 0u);
           }
           if (CL == 2) tcgen05_commit_2sm(empty_bar + 8 * stage, 3);   // both CTAs' stages are free once these MMAs have read them
           else tcgen05_commit(empty_bar + 8 * stage);   // smem stage reusable once these MMAs have read it
@@ -192,7 +200,8 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t range_chk = 0;        // fp16 outputs: bit 15 of a half-word is set when its exponent field is all ones (inf / nan)
-    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+    for (int item = tile0; item < total_items; item += tile_step) {
+      const int ks = S > 1 ? item / total_tiles : 0, tile = item - ks * total_tiles;
       const int m_blk = (n_fastest ? tile / n_tiles : tile % m_groups) * CL + rank, n_blk = n_fastest ? tile % n_tiles : tile / m_groups;
       const int m0 = m_blk * BM + quarter * 32;
       const int m = m0 + lane;
@@ -206,14 +215,83 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       }
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tcgen05_fence_after();
+      // K slices: every slice parks its raw fp32 accumulators in the launch's scratch (slot = (slice, tile); a thread's 32 columns
+      // as eight float4 interleaved over the lanes: coalesced, private layout), then counts itself on the tile's counter.  The
+      // slice that arrives last sums all slots IN SLICE ORDER -- the result does not depend on the arrival order -- and runs the
+      // ordinary epilogue on the sums; it also re-arms the counter for the next launch.
+      constexpr int kChunks = kCols / 32;
+      constexpr bool kSliceable = CL == 1 && BN == 128 && kLd == 1;     // the small-M path; fp32 outputs (the residual GEMMs are the long-K ones)
+      constexpr long long kSlotF4 = (long long)BM * BN / 4;
+      bool from_ws = false;
+      const float4* ws_rd = nullptr;
+      if (kSliceable && S > 1) {
+        float4* slot = reinterpret_cast<float4*>(epi.kws) + ((long long)ks * total_tiles + tile) * kSlotF4 + (long long)warp * kChunks * 256 + lane;
+#pragma unroll 1
+        for (int c = 0; c < kChunks; ++c) {
+          uint32_t r0[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * kCols + 32 * c), r0);
+          tmem_ld_wait();
+          if (c == kChunks - 1) { tcgen05_fence_before(); mbar_arrive(tempty_bar + 8 * acc); }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            __stcg(slot + (c * 8 + j) * 32, make_float4(__uint_as_float(r0[4 * j]), __uint_as_float(r0[4 * j + 1]),
+                                                         __uint_as_float(r0[4 * j + 2]), __uint_as_float(r0[4 * j + 3])));
+        }
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        if (threadIdx.x == 0) {
+          const int last = atomicAdd(epi.kcnt + tile, 1) == S - 1;
+          if (last) epi.kcnt[tile] = 0;
+          *kflag = last;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        if (!*kflag) {
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
+        __threadfence();
+        from_ws = true;
+        ws_rd = reinterpret_cast<const float4*>(epi.kws) + (long long)tile * kSlotF4 + (long long)warp * kChunks * 256 + lane;
+      }
 #pragma unroll 1
       for (int it = 0; it < kCols / kIter; ++it) {
         const int col = half * kCols + it * kIter;
         const int n0 = n_blk * BN + col;
         uint32_t r[kLd][32];
+        if (kSliceable && from_ws) {
+          // kLd == 1.  Two slots' loads in flight at a time (the reads are L2 round trips: one slot at a time cost ~0.7 us each)
+          const float4* p = ws_rd + it * 256;
+          const long long stride = (long long)total_tiles * kSlotF4;
 #pragma unroll
-        for (int u = 0; u < kLd; ++u)
-          tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col + 32 * u), r[u]);
+          for (int j = 0; j < 32; ++j) r[0][j] = 0u;     // 0.0f: the sum starts from slice 0 exactly (0 + a == a)
+#pragma unroll 1
+          for (int s0 = 0; s0 < S; s0 += 2) {
+            float4 t[2][8];
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              if (s0 + g < S) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) t[g][j] = __ldcg(p + (s0 + g) * stride + j * 32);
+              }
+            }
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              if (s0 + g < S) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  r[0][4 * j] = __float_as_uint(__uint_as_float(r[0][4 * j]) + t[g][j].x);
+                  r[0][4 * j + 1] = __float_as_uint(__uint_as_float(r[0][4 * j + 1]) + t[g][j].y);
+                  r[0][4 * j + 2] = __float_as_uint(__uint_as_float(r[0][4 * j + 2]) + t[g][j].z);
+                  r[0][4 * j + 3] = __float_as_uint(__uint_as_float(r[0][4 * j + 3]) + t[g][j].w);
+                }
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < kLd; ++u)
+            tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col + 32 * u), r[u]);
+        }
         float4 bq[kLd][8];
         if (epi.bias) {                                   // in flight together with the TMEM loads
           const float4* b4 = reinterpret_cast<const float4*>(epi.bias + n0);
@@ -224,7 +302,7 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
           for (int j = 0; j < 8 * kLd; ++j) bq[j / 8][j % 8] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         tmem_ld_wait();
-        if (it == kCols / kIter - 1) {                    // accumulator fully read: hand the TMEM stage back to the MMA warp
+        if (it == kCols / kIter - 1 && !from_ws) {        // accumulator fully read: hand the TMEM stage back to the MMA warp
           tcgen05_fence_before();
           if (CL == 2) mbar_arrive_cluster(mapa_shared(tempty_bar + 8 * acc, 0));   // the MMA issuer lives in the leader CTA
           else mbar_arrive(tempty_bar + 8 * acc);
@@ -433,6 +511,22 @@ static int sm_count() {
   return n;
 }
 
+// Few output tiles and a long K (one frame per call: 24 tiles for fc2 of ViT-L, each CTA streaming 1 MB of weights through 64
+// k-blocks alone): slice K over otherwise idle SMs.  fp32-output modes only, K >= 2048, at least eight k-blocks per slice (the
+// meeting of the slices costs ~3 us: slicing the K = 1024 GEMMs was measured slower), never more items than SMs (one wave).
+static int kslices_for(int tiles, int k_blocks, int bn, const GemmEpilogue& epi) {
+  static int use_slices = -1;
+  if (use_slices < 0) { const char* e = getenv("BSCNAV_KSLICE"); use_slices = e ? atoi(e) : 1; }
+  if (!use_slices || !epi.kws || !epi.kcnt || tiles > epi.kcnt_len || k_blocks < 32) return 1;
+  if ((epi.mode != kOutResidual && epi.mode != kOutFloat) || bn != 128) return 1;
+  int s = sm_count() / tiles;
+  if (s > k_blocks / 8) s = k_blocks / 8;
+  if (s > 8) s = 8;
+  const long long slots = epi.kws_floats / ((long long)BM * bn);
+  if ((long long)s * tiles > slots) s = (int)(slots / tiles);
+  return s >= 2 ? s : 1;
+}
+
 static int max_cluster_pairs(const void* fn, int smem) {
   // how many 2-CTA clusters of this kernel the device runs at once (GPCs with an odd SM count leave one SM unpaired)
   cudaLaunchConfig_t cfg = {};
@@ -475,9 +569,12 @@ static int launch_bn_mode(const CUtensorMap* map_a, const CUtensorMap* map_w, co
     return BSCNAV_OK;
   }
   const int tiles = m_tiles * n_tiles;
-  const int grid = tiles < sm_count() ? tiles : sm_count();
+  GemmEpilogue ep = epi;
+  ep.kslices = kslices_for(tiles, (split ? 3 : 1) * (K / BK), BN, epi);
+  const int items = tiles * ep.kslices;
+  const int grid = items < sm_count() ? items : sm_count();
   constexpr int smem1 = Cfg<BN, 1>::kSmem;
-  BSC_LAUNCH_PDL((k_gemm_f16<BN, MODE, ACT, 1>), grid, kGemmThreads, smem1, stream, *map_a, *map_w, *map_out, M, N, K, epi, split);
+  BSC_LAUNCH_PDL((k_gemm_f16<BN, MODE, ACT, 1>), grid, kGemmThreads, smem1, stream, *map_a, *map_w, *map_out, M, N, K, ep, split);
   return BSCNAV_OK;
 }
 
@@ -537,6 +634,28 @@ extern "C" int bscnav_gemm_f16(const void* a, const void* w, const float* bias, 
   GemmEpilogue epi{};
   epi.out = out; epi.bias = bias; epi.table = nullptr; epi.ld_out = n; epi.mode = out_mode; epi.act = act; epi.range_flag = nullptr;
   return gemm_f16_launch(&ma, &mw, via_tma ? &mo : nullptr, m, n, k, epi, (cudaStream_t)stream, half_ok ? &mwh : nullptr);
+}
+
+// The same GEMM with K slices allowed (tests of the small-M path): scratch = [1 KB of zeroed tile counters | partial tiles];
+// out_slices (host, may be null) receives the slice count the launcher chose for this shape.
+extern "C" int bscnav_gemm_f16_sliced(const void* a, const void* w, const float* bias, void* out, int32_t m, int32_t n, int32_t k,
+                                      int32_t out_mode, int32_t act, void* scratch, int64_t scratch_bytes, int32_t* out_slices,
+                                      void* stream) {
+  if (!a || !w || !out || m <= 0 || n <= 0 || k <= 0 || n % 128 != 0 || k % 64 != 0) return BSCNAV_EINVAL;
+  if (out_mode != kOutHalf && out_mode != kOutHalfAct && out_mode != kOutResidual && out_mode != kOutFloat) return BSCNAV_EINVAL;
+  if (!scratch || scratch_bytes < 1024 + 2LL * BM * 128 * 4 || (reinterpret_cast<uintptr_t>(scratch) & 15)) return BSCNAV_EINVAL;
+  CUtensorMap ma, mw, mo;
+  if (int e = make_operand_map(&ma, a, m, k, BM)) return e;
+  if (int e = make_operand_map(&mw, w, n, k, 128)) return e;       // 128-wide tiles, one CTA per tile: the path that slices
+  const bool via_tma = out_mode != kOutFloat;
+  if (via_tma)
+    if (int e = make_store_map(&mo, out, m, n, out_mode == kOutResidual)) return e;
+  GemmEpilogue epi{};
+  epi.out = out; epi.bias = bias; epi.ld_out = n; epi.mode = out_mode; epi.act = act;
+  epi.kcnt = static_cast<int*>(scratch); epi.kcnt_len = 256;
+  epi.kws = reinterpret_cast<float*>(static_cast<char*>(scratch) + 1024); epi.kws_floats = (scratch_bytes - 1024) / 4;
+  if (out_slices) *out_slices = kslices_for(((m + BM - 1) / BM) * (n / 128), k / BK, 128, epi);
+  return launch_bn<128>(&ma, &mw, nullptr, via_tma ? &mo : &ma, m, n, k, epi, (cudaStream_t)stream, 0);
 }
 
 // Stand-alone wide-range GEMM (tests): a [M, 2K] and w [N, 2K] bf16 (hi | lo) rows (vit.py:split_bf16), fp32 out = a w^T + bias.

@@ -37,6 +37,13 @@ struct GemmEpilogue {
   const uint8_t* mask;      // kOutSims: [N] column participates (0 / 1)
   float* aux;               // kOutSims: [M, ld_aux] per-row maxima of 32-column blocks (fp32, before the fp16 rounding)
   long long ld_aux;
+  // K slices (small M, gemm_f16_launch decides): scratch for the slices' fp32 partial tiles and one counter per output tile
+  // (zero before the first launch; the kernel leaves them zero).  Null = never slice.
+  float* kws;
+  long long kws_floats;
+  int* kcnt;
+  int kcnt_len;
+  int kslices;              // set by the launcher
 };
 
 // map_out: store map of the output tensor (make_store_map) for the fp16 / residual epilogues; null for the others

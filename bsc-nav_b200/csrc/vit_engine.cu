@@ -7,7 +7,9 @@
 // Text tower (cfg.text_context > 0, open_clip encode_text for the agent's goal / label matching, BSCAgent.py:541-557, 708-711):
 //   half blob : per layer { qkv_w, proj_w, fc1_w, fc2_w };  float blob: pos [ctx, D] | per layer { ... } | ln_final_w, ln_final_b
 //   causal attention, no patch embedding / cls / registers / pre-LN; the token-embedding table is passed per call.
+#include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <vector>
 #include "gemm_tcgen05.cuh"
 #include "vit_kernels.cuh"
@@ -78,8 +80,12 @@ struct Workspace {
   float* pre_img; // [B, 3, S, S] pre-processed frames (input of the split im2col)
   float* pre_tab; // resize tap tables of the pre-processing kernel
   int* range_flag; // set by the GEMM epilogues when an fp16 activation overflowed
+  float* kws;      // K-sliced GEMMs of small batches: partial tiles (gemm_tcgen05.cuh), kKwsFloats floats
+  int* kcnt;       // and their tile counters (kKcntLen, zero between launches)
   long long total;
 };
+static constexpr long long kKwsFloats = 152LL * 128 * 128;   // one 128 x 128 fp32 partial tile per SM and a little slack
+static constexpr int kKcntLen = 256;
 static void workspace_layout(const bscnav_vit_cfg_t* c, int max_batch, Workspace* w, char* base) {
   const bool text = c->text_context > 0;
   const long long D = c->dim, M = c->mlp, G = text ? 0 : c->image / c->patch, Np = G * G, B = max_batch;
@@ -97,6 +103,8 @@ static void workspace_layout(const bscnav_vit_cfg_t* c, int max_batch, Workspace
   w->pre_img = reinterpret_cast<float*>(take(text || wide == 1 ? 0 : B * 3 * (long long)c->image * c->image * 4));
   w->pre_tab = reinterpret_cast<float*>(take(text ? 0 : preprocess_table_bytes(c->image)));
   w->range_flag = reinterpret_cast<int*>(take(256));
+  w->kws = reinterpret_cast<float*>(take(kKwsFloats * 4));
+  w->kcnt = reinterpret_cast<int*>(take(kKcntLen * 4));
   w->total = off;
 }
 
@@ -122,6 +130,15 @@ struct VitEngine {
   bool profile = false;
   struct Span { int cat; double work; cudaEvent_t e0, e1; };
   std::vector<Span> spans;
+  // CUDA graphs of the transformer blocks for small batches (one frame per call: the 168 launches of a forward cost the host
+  // 1.4 ms to enqueue, more than the kernels take): batch -> {executable graph or null (= run eagerly), launches in it}
+  struct BlockGraph { cudaGraphExec_t exec; int launches; bool warmed; };
+  std::map<int, BlockGraph> graphs;
+  cudaStream_t capture_stream = nullptr;
+  ~VitEngine() {
+    for (auto& g : graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+    if (capture_stream) cudaStreamDestroy(capture_stream);
+  }
 };
 
 enum ProfCat : int { kCatGemm = 0, kCatAttention = 1, kCatLayerNorm = 2, kCatPre = 3, kCatCount = 4 };
@@ -140,6 +157,7 @@ struct ProfScope {
 };
 
 static int run_layers(VitEngine* e, int batch, cudaStream_t stream);
+static int run_blocks(VitEngine* e, int batch, cudaStream_t stream);
 
 // out_tokens: LayerNorm(post) patch tokens [batch, Np, D]; or (proj != null) out_embed: the cls token's image embedding [batch, E]
 static int vit_run(VitEngine* e, int batch, float* out_tokens, cudaStream_t stream, const float* proj = nullptr, int embed_dim = 0,
@@ -158,7 +176,7 @@ static int vit_run(VitEngine* e, int batch, float* out_tokens, cudaStream_t stre
   if (int r = fill_prefix_tokens(e->ws.x, wf + e->L.cls_pos, wf + e->L.reg, batch, T, c.n_reg, D, stream)) return r;
   if (c.ln_pre)
     if (int r = layernorm_inplace(e->ws.x, wf + e->L.ln_pre_w, wf + e->L.ln_pre_b, c.ln_eps, rows, D, stream)) return r;
-  if (int r = run_layers(e, batch, stream)) return r;
+  if (int r = run_blocks(e, batch, stream)) return r;
   if (proj) return cls_embed(e->ws.x, wf + e->L.ln_post_w, wf + e->L.ln_post_b, c.ln_eps, batch, T, D, proj, embed_dim, out_embed, nullptr, stream);
   return layernorm_patch_tokens(e->ws.x, wf + e->L.ln_post_w, wf + e->L.ln_post_b, c.ln_eps, batch, T, 1 + c.n_reg, D,
                                 out_tokens, stream);
@@ -179,6 +197,7 @@ static int run_layers(VitEngine* e, int batch, cudaStream_t stream) {
     { ProfScope ps(e, stream, kCatLayerNorm, (double)rows * D * 6);
       if (int r = layernorm_half(e->ws.x, wf + o.ln1_w, wf + o.ln1_b, c.ln_eps, rows, D, e->ws.y, stream)) return r; }
     GemmEpilogue e1{};
+    e1.kws = e->ws.kws; e1.kws_floats = kKwsFloats; e1.kcnt = e->ws.kcnt; e1.kcnt_len = kKcntLen;
     e1.out = e->ws.qkv; e1.bias = wf + o.qkv_b; e1.ld_out = 3 * D; e1.mode = kOutHalf; e1.range_flag = e->ws.range_flag;
     { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * 3.0 * D * D);
       if (int r = gemm_f16_launch(&e->map_y, &e->map_qkv[i], &e->out_qkv, rows, 3 * D, D, e1, stream, e->has_half[0] ? &e->half_qkv[i] : nullptr)) return r; }
@@ -191,20 +210,74 @@ static int run_layers(VitEngine* e, int batch, cudaStream_t stream) {
       } else if (e->attn_impl == 1) { if (int r = attention_tc_launch(&e->qkv128, &e->qkv16, e->ws.ao, batch, T, c.heads, stream)) return r; }
       else if (int r = attention_f16(e->ws.qkv, e->ws.ao, batch, T, c.heads, c.head_dim ? c.head_dim : 64, causal, stream)) return r; }
     GemmEpilogue e2{};
+    e2.kws = e->ws.kws; e2.kws_floats = kKwsFloats; e2.kcnt = e->ws.kcnt; e2.kcnt_len = kKcntLen;
     e2.out = e->ws.x; e2.bias = wf + o.proj_b; e2.ld_out = D; e2.mode = kOutResidual;
     { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * (double)D * D);
       if (int r = gemm_f16_launch(&e->map_ao, &e->map_proj[i], &e->out_x, rows, D, D, e2, stream, e->has_half[1] ? &e->half_proj[i] : nullptr)) return r; }
     { ProfScope ps(e, stream, kCatLayerNorm, (double)rows * D * 6);
       if (int r = layernorm_half(e->ws.x, wf + o.ln2_w, wf + o.ln2_b, c.ln_eps, rows, D, e->ws.y, stream)) return r; }
     GemmEpilogue e3{};
+    e3.kws = e->ws.kws; e3.kws_floats = kKwsFloats; e3.kcnt = e->ws.kcnt; e3.kcnt_len = kKcntLen;
     e3.out = e->ws.hmid; e3.bias = wf + o.fc1_b; e3.ld_out = M; e3.mode = kOutHalfAct; e3.act = c.act; e3.range_flag = e->ws.range_flag;
     { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * (double)M * D);
       if (int r = gemm_f16_launch(&e->map_y, &e->map_fc1[i], &e->out_h, rows, M, D, e3, stream, e->has_half[2] ? &e->half_fc1[i] : nullptr)) return r; }
     GemmEpilogue e4{};
+    e4.kws = e->ws.kws; e4.kws_floats = kKwsFloats; e4.kcnt = e->ws.kcnt; e4.kcnt_len = kKcntLen;
     e4.out = e->ws.x; e4.bias = wf + o.fc2_b; e4.ld_out = D; e4.mode = kOutResidual;
     { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * (double)M * D);
       if (int r = gemm_f16_launch(&e->map_h, &e->map_fc2[i], &e->out_x, rows, D, M, e4, stream, e->has_half[3] ? &e->half_fc2[i] : nullptr)) return r; }
   }
+  return BSCNAV_OK;
+}
+
+// run_layers, replayed from a CUDA graph when the batch is small.  The blocks read and write only the engine's workspace and
+// weights, so a graph captured once per batch size stays valid; the first call of a batch size runs eagerly (function attributes,
+// module loading), the second is captured -- on a stream of the engine's own, since the caller's may be the legacy default stream,
+// which cannot be captured -- and launched into the caller's stream.  BSCNAV_GRAPH=0 disables it; so does the profiling hook; a
+// caller that is itself capturing gets the plain launches recorded into its own graph.
+static constexpr int kGraphMaxRows = 4096;             // larger batches are bound by the kernels, not by the host's launch rate
+static int run_blocks(VitEngine* e, int batch, cudaStream_t stream) {
+  static int use_graph = -1;
+  if (use_graph < 0) { const char* v = getenv("BSCNAV_GRAPH"); use_graph = v ? atoi(v) : 1; }
+  if (!use_graph || e->profile || batch * e->T > kGraphMaxRows) return run_layers(e, batch, stream);
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) { cudaGetLastError(); return run_layers(e, batch, stream); }
+  auto it = e->graphs.find(batch);
+  if (it == e->graphs.end()) {
+    e->graphs[batch] = VitEngine::BlockGraph{nullptr, 0, true};
+    return run_layers(e, batch, stream);
+  }
+  VitEngine::BlockGraph& bg = it->second;
+  if (bg.warmed && !bg.exec) {
+    bg.warmed = false;                                  // one attempt: on any failure this batch size stays eager
+    if (!e->capture_stream && cudaStreamCreateWithFlags(&e->capture_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaGetLastError(); e->capture_stream = nullptr; return run_layers(e, batch, stream);
+    }
+    const long long l0 = g_launches.load(std::memory_order_relaxed);
+    const cudaError_t cb = cudaStreamBeginCapture(e->capture_stream, cudaStreamCaptureModeThreadLocal);
+    if (cb != cudaSuccess) {
+      fprintf(stderr, "bscnav: graph capture not started (%s); batch %d stays eager\n", cudaGetErrorString(cb), batch);
+      cudaGetLastError();
+      return run_layers(e, batch, stream);
+    }
+    const int r = run_layers(e, batch, e->capture_stream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(e->capture_stream, &graph);
+    const int n = (int)(g_launches.load(std::memory_order_relaxed) - l0);
+    g_launches.fetch_sub(n, std::memory_order_relaxed);  // enqueued into the graph, not run: each replay counts them
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t ci = cudaSuccess;
+    if (r == BSCNAV_OK && ce == cudaSuccess && graph && (ci = cudaGraphInstantiate(&exec, graph, 0)) == cudaSuccess) { bg.exec = exec; bg.launches = n; }
+    else {
+      fprintf(stderr, "bscnav: graph of the blocks at batch %d not built (run %d, end capture: %s, instantiate: %s); stays eager\n", batch, r,
+              cudaGetErrorString(ce), cudaGetErrorString(ci));
+      cudaGetLastError();
+    }
+    if (graph) cudaGraphDestroy(graph);
+  }
+  if (!bg.exec) return run_layers(e, batch, stream);
+  BSC_CUDA(cudaGraphLaunch(bg.exec, stream));
+  g_launches.fetch_add(bg.launches, std::memory_order_relaxed);
   return BSCNAV_OK;
 }
 
@@ -324,6 +397,7 @@ int bscnav_vit_create(const bscnav_vit_cfg_t* c, const void* w_half, const float
     if (e->has_half[3]) r = r ? r : make_operand_map(&e->half_fc2[i], e->wh + o.fc2_w, D, kw * M, 128);
   }
   if (!r && cudaMemset(e->ws.range_flag, 0, 256) != cudaSuccess) r = BSCNAV_ECUDA;
+  if (!r && cudaMemset(e->ws.kcnt, 0, kKcntLen * 4) != cudaSuccess) r = BSCNAV_ECUDA;
   if (r) { delete e; return r; }
   *out_engine = e;
   return BSCNAV_OK;
@@ -426,7 +500,7 @@ int bscnav_text_encode(void* engine, const int32_t* token_ids, int32_t batch, co
   cudaStream_t stream = (cudaStream_t)stream_;
   const bscnav_vit_cfg_t& c = e->cfg;
   if (int r = text_embed(token_ids, token_embedding, vocab, e->wf + e->L.pos, batch, e->T, c.dim, e->ws.x, stream)) return r;
-  if (int r = run_layers(e, batch, stream)) return r;
+  if (int r = run_blocks(e, batch, stream)) return r;
   return cls_embed(e->ws.x, e->wf + e->L.ln_post_w, e->wf + e->L.ln_post_b, c.ln_eps, batch, e->T, c.dim, proj, embed_dim, out_embed,
                    token_ids, stream);
 }

@@ -284,6 +284,24 @@ def gemm_f16(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None,
     return out
 
 
+def gemm_f16_sliced(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, out_mode: int = 0, act: int = 0,
+                    out: torch.Tensor | None = None, scratch: torch.Tensor | None = None):
+    """gemm_f16 on the engine's small-M path (128-wide tiles, K sliced over idle SMs when the launcher decides to); returns
+    (out, slices).  `scratch`: zero-initialised uint8 device tensor, reusable across calls (tests)."""
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float16 if out_mode in (0, 1) else torch.float32, device=a.device)
+        if out_mode == 2:
+            out.zero_()
+    if scratch is None:
+        scratch = torch.zeros(1024 + 152 * 128 * 128 * 4, dtype=torch.uint8, device=a.device)
+    n = C.c_int32(0)
+    _lib.check(_lib.lib().bscnav_gemm_f16_sliced(_lib.ptr(a), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(out), M, N, K, out_mode, act,
+                                                 _lib.ptr(scratch), scratch.numel(), C.byref(n), _lib.stream_ptr()), "gemm_f16_sliced")
+    return out, int(n.value)
+
+
 def gemm_bf16x3(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None) -> torch.Tensor:
     """out = a @ w.T (+bias) from fp32 inputs on the wide-range path: operands split into (hi | lo) bf16 pairs, three tcgen05
     passes, fp32 out (tests)."""

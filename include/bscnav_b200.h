@@ -284,6 +284,14 @@ int bscnav_gaussian_pool(const float* tokens, int32_t batch, int32_t grid, int32
 int bscnav_gemm_f16(const void* a, const void* w, const float* bias, void* out, int32_t m, int32_t n, int32_t k,
                     int32_t out_mode, int32_t act, void* stream);
 
+/* The stand-alone GEMM on the small-M path of the ViT engine (128-wide tiles, one CTA per tile), where the launcher may slice K
+ * over idle SMs: every slice parks its fp32 partial tile in `scratch`, the slice arriving last sums them in slice order (the result
+ * does not depend on arrival order) and runs the epilogue.  scratch: 16-byte aligned device memory, the first 1024 bytes (tile
+ * counters) zero before the first call -- the kernel leaves them zero --, the rest partial tiles (64 KB each).  out_slices
+ * (host, may be NULL): the slice count chosen for this shape (1 = not sliced). */
+int bscnav_gemm_f16_sliced(const void* a, const void* w, const float* bias, void* out, int32_t m, int32_t n, int32_t k,
+                           int32_t out_mode, int32_t act, void* scratch, int64_t scratch_bytes, int32_t* out_slices, void* stream);
+
 /* Stand-alone wide-range GEMM (tests): a [M, 2K] and w [N, 2K] as (hi | lo) bf16 row pairs (hi = bf16(v), lo = bf16(v - hi)),
  * three tcgen05 passes a_hi w_hi + a_lo w_hi + a_hi w_lo, fp32 out [M, N] = a w^T + bias. */
 int bscnav_gemm_bf16x3(const void* a, const void* w, const float* bias, float* out, int32_t m, int32_t n, int32_t k, void* stream);

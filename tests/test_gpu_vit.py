@@ -37,6 +37,37 @@ def test_gemm_modes(pkg, M, N, K):
     torch.testing.assert_close(out, ref - bias, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("M,N,K,want_slices", [(257, 1024, 4096, 6), (257, 1024, 2048, 4), (257, 3072, 1024, 1), (77, 1024, 4096, 8),
+                                               (1028, 1024, 4096, 2), (130, 1280, 5120, 7), (257, 1024, 320, 1), (2056, 1024, 4096, 1)])
+def test_gemm_k_slices(pkg, M, N, K, want_slices):
+    """Small-M launches with a long K and fp32 output slice K over idle SMs (gemm_tcgen05.cu: partial tiles in scratch, the
+    last-arriving slice sums them in slice order): the epilogues against torch, the slice count the launcher chose, bit-repeatable
+    results whatever the arrival order, counters left re-armed; fp16-output modes run unsliced through the same entry."""
+    g = torch.Generator("cuda").manual_seed(M + N + K)
+    a = (torch.randn(M, K, device="cuda", generator=g)).half()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = a.float() @ w.float().t() + bias
+    scratch = torch.zeros(1024 + 152 * 128 * 128 * 4, dtype=torch.uint8, device="cuda")
+    res = torch.randn(M, N, device="cuda", generator=g)
+    first = None
+    for _ in range(4):                                    # the arrival order of the slices varies, the sum must not
+        out, s = pkg.gemm_f16_sliced(a, w, bias, out_mode=2, out=res.clone(), scratch=scratch)
+        if torch.cuda.get_device_properties(0).multi_processor_count == 148:
+            assert s == want_slices
+        torch.testing.assert_close(out, res + ref, rtol=1e-4, atol=1e-4)
+        first = out if first is None else first
+        assert torch.equal(out, first)
+    out, _ = pkg.gemm_f16_sliced(a, w, None, out_mode=4, out=torch.empty(M, N, device="cuda"), scratch=scratch)
+    torch.testing.assert_close(out, ref - bias, rtol=1e-4, atol=1e-4)
+    out, s = pkg.gemm_f16_sliced(a, w, bias, out_mode=0, scratch=scratch)
+    assert s == 1
+    torch.testing.assert_close(out.float(), ref, rtol=2e-3, atol=2e-3)
+    out, _ = pkg.gemm_f16_sliced(a, w, bias, out_mode=1, act=0, scratch=scratch)
+    torch.testing.assert_close(out.float(), torch.nn.functional.gelu(ref), rtol=2e-3, atol=2e-3)
+    assert int(scratch[:1024].view(torch.int32).abs().sum()) == 0
+
+
 def test_gemm_repeatable(pkg):
     g = torch.Generator("cuda").manual_seed(0)
     a = torch.randn(2056, 1024, device="cuda", generator=g).half()
@@ -251,3 +282,22 @@ def test_graph_replay_equals_eager(pkg):
         x = torch.randn(1, 3, 224, 224, generator=torch.Generator().manual_seed(rep)).cuda()
         assert torch.equal(img.encode_image(x, graph=True), img.encode_image(x))
     assert set(txt._graphs) == {("text", 3)} and set(img._graphs) == {("image", 1)}
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_block_graph_equals_eager(pkg, B):
+    """Small batches replay the transformer blocks from a CUDA graph held by the engine (vit_engine.cu run_blocks): first call eager,
+    second captured, later ones replayed.  Every call must return exactly what the eager launches return (the profiling hook
+    forces those), for new frames on every call, also after a different batch size has been through the engine."""
+    cfg = pkg.tiny(pkg.CLIP_L14, dim=256, depth=3, heads=4, mlp=512)
+    eng = pkg.ViTEngine(cfg, pkg.random_weights(cfg, seed=4, perturb=True), max_batch=4)
+    g = torch.Generator().manual_seed(B)
+    for rep in range(5):
+        nb = B if rep != 3 else B + 1                     # a second batch size in between: its own graph, same workspace
+        rgb = torch.randint(0, 256, (nb, 96, 128, 3), dtype=torch.uint8, generator=g).cuda()
+        got = eng.forward_frames(rgb).clone()
+        eng.profile(True)
+        want = eng.forward_frames(rgb).clone()
+        eng.profile(False)
+        assert torch.equal(got, want), (B, rep)
+        assert not eng.range_overflow()

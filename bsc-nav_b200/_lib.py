@@ -56,6 +56,7 @@ _SIGS = {
     "bscnav_last_error": (C.c_char_p, []),
     "bscnav_launch_count": (C.c_int64, []),
     "bscnav_store_reset": (C.c_int, [C.POINTER(Geom), C.POINTER(Store), _P]),
+    "bscnav_store_publish_counts": (C.c_int, [C.POINTER(Store), _P, _P]),
     "bscnav_store_row_norms": (C.c_int, [C.POINTER(Geom), C.POINTER(Store), C.c_int64, _P]),
     "bscnav_fuse_scratch_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "bscnav_fuse_frames": (C.c_int, [C.POINTER(Geom), C.POINTER(Store), _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P,

@@ -961,6 +961,26 @@ int bscnav_store_reset(const bscnav_geom_t* g, const bscnav_store_t* st, void* s
   return BSCNAV_OK;
 }
 
+// counters[0..3] -> four int32 in page-locked host memory, written by a kernel through the mapped address.  A 16-byte
+// cudaMemcpyAsync on the scatter's stream took a copy engine: behind a 133 MB host->device copy of the next batches' frames it held
+// the scatter stream back by milliseconds (0.55 ms per 54-frame step end to end).
+__global__ void k_publish_counts(const int32_t* __restrict__ counters, volatile int32_t* host_dst) {
+  if (threadIdx.x < 4) host_dst[threadIdx.x] = counters[threadIdx.x];
+  __threadfence_system();
+}
+int bscnav_store_publish_counts(const bscnav_store_t* st, int32_t* host_dst, void* stream_) {
+  if (!st || !st->counters || !host_dst) return BSCNAV_EINVAL;
+  void* dptr = nullptr;
+  if (cudaHostGetDevicePointer(&dptr, host_dst, 0) != cudaSuccess || !dptr) {
+    cudaGetLastError();
+    snprintf(g_last_error, sizeof(g_last_error), "publish_counts: destination is not page-locked, device-mapped host memory");
+    return BSCNAV_EINVAL;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  BSC_LAUNCH(k_publish_counts, 1, 32, 0, stream, (const int32_t*)st->counters, static_cast<volatile int32_t*>(dptr));
+  return BSCNAV_OK;
+}
+
 int bscnav_store_row_norms(const bscnav_geom_t* g, const bscnav_store_t* st, int64_t n_rows, void* stream_) {
   if (int e = check_geom(g)) return e;
   if (!st || !st->feat || !st->norm2 || n_rows < 0 || n_rows > (int64_t)g->max_slots * g->cache) return BSCNAV_EINVAL;

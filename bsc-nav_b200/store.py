@@ -187,7 +187,9 @@ class SpatialStore:
         """Enqueue a device->host read of (slots in use, overflow flag, colour mark, rows committed) into pinned memory;
         returns a handle for count_wait / rows_committed_wait."""
         i = self._cnt_i = (self._cnt_i + 1) % self._cnt_ring.shape[0]
-        self._cnt_ring[i].copy_(self.counters[:4], non_blocking=True)
+        # written by a kernel through the mapped address of the pinned ring: no copy-engine operation on the scatter's stream
+        _lib.check(self.lib.bscnav_store_publish_counts(C.byref(self.st), self._cnt_ring[i].data_ptr(), _lib.stream_ptr()),
+                   "store_publish_counts")
         ev = torch.cuda.Event()
         ev.record()
         return i, ev

@@ -79,6 +79,12 @@ typedef struct {
 /* Reset a store to empty (replaces _init_cache, memory_2.py:708-722). */
 int bscnav_store_reset(const bscnav_geom_t* g, const bscnav_store_t* st, void* stream);
 
+/* Asynchronous read-out of counters[0..3] (slots in use = max_id, memory_2.py:894; overflow flag; colour mark; rows committed):
+ * a one-warp kernel on `stream` writes them to host_dst, four int32 of page-locked (device-mapped) host memory; the caller
+ * waits on an event recorded behind it.  No copy-engine operation enters the stream (a 16-byte cudaMemcpyAsync queued behind
+ * the build's large host->device copies and stalled the scatter stream). */
+int bscnav_store_publish_counts(const bscnav_store_t* st, int32_t* host_dst, void* stream);
+
 /* Recompute norm2[0, n_rows) from feat (after filling token rows from a memory directory, memory_2.py:185-200);
  * same summation order as the commit kernel, so a reloaded store scores bit-identically. */
 int bscnav_store_row_norms(const bscnav_geom_t* g, const bscnav_store_t* st, int64_t n_rows, void* stream);

@@ -202,7 +202,11 @@ static int run_layers(VitEngine* e, int batch, cudaStream_t stream) {
     { ProfScope ps(e, stream, kCatGemm, 2.0 * rows * 3.0 * D * D);
       if (int r = gemm_f16_launch(&e->map_y, &e->map_qkv[i], &e->out_qkv, rows, 3 * D, D, e1, stream, e->has_half[0] ? &e->half_qkv[i] : nullptr)) return r; }
     { ProfScope ps(e, stream, kCatAttention, 4.0 * batch * (double)T * T * D);
-      if (e->attn_impl == 3) {
+      if (e->attn_impl == 3 && batch == 1 && !causal) {
+        // one frame: 16 (frame, head) pairs leave the persistent tcgen05 kernel one CTA each on 16 SMs; the mma.sync kernel spreads
+        // the row-group rounds of every pair over three CTAs (1.432 -> 1.394 ms per ViT-L/14 forward; slower from B = 4 on)
+        if (int r = attention_f16(e->ws.qkv, e->ws.ao, batch, T, c.heads, 64, false, stream)) return r;
+      } else if (e->attn_impl == 3) {
         if (int r = attention_ws2_launch(&e->qkv3d128, &e->qkv3d16, &e->ao3d, e->ws.qkv, e->ws.ao, batch, T, c.heads, stream, causal)) return r;
       } else if (e->attn_impl == 2) {
         // the 3-D map's frame extent is the engine's max_batch: frames >= batch are simply never addressed

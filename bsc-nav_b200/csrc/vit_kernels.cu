@@ -360,7 +360,9 @@ k_attention(const __half* __restrict__ qkv, __half* __restrict__ out, int T, int
   const int n_kb = (T + 63) / 64;
   const int n_groups = (T + 15) / 16;
   const float kLog2e = 1.4426950408889634f;
-  for (int g = warp; g < n_groups; g += kAttnWarps) {
+  // gridDim.z CTAs share a (frame, head): each takes every gridDim.z-th round of row groups (small batches: one frame per call
+  // has 16 (frame, head) pairs for 148 SMs; K and V are staged by each of them, 66 KB from L2)
+  for (int g = (int)blockIdx.z * kAttnWarps + warp; g < n_groups; g += kAttnWarps * (int)gridDim.z) {
     // Q fragments (m16k16 A operand, 4 k-steps) straight from global memory: rows r0 and r0+8 of this group
     const int r0 = g * 16 + (lane >> 2), r1 = r0 + 8;
     uint32_t qf[KS][4];
@@ -483,6 +485,17 @@ k_attention(const __half* __restrict__ qkv, __half* __restrict__ out, int T, int
   }
 }
 
+static int sm_count_cached() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <int HD, bool CAUSAL>
 static int attention_launch(const __half* qkv, __half* out, int batch, int T, int heads, cudaStream_t stream) {
   const int t_pad = (T + 15) / 16 * 16;      // only whole 16-key groups are ever read (see `ng` in the kernel)
@@ -493,7 +506,12 @@ static int attention_launch(const __half* qkv, __half* out, int batch, int T, in
     BSC_CUDA(cudaFuncSetAttribute((k_attention<HD, CAUSAL>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem = smem;
   }
-  BSC_LAUNCH((k_attention<HD, CAUSAL>), dim3((unsigned)heads, (unsigned)batch), kAttnThreads, smem, stream, qkv, out, T, heads, t_pad);
+  // row-group rounds of one (frame, head) over up to three CTAs while the grid stays within one wave (two CTAs per SM)
+  const int rounds = ((T + 15) / 16 + kAttnWarps - 1) / kAttnWarps;
+  int z = (2 * sm_count_cached()) / (batch * heads);
+  z = z < 1 ? 1 : (z > rounds ? rounds : z);
+  if (z > 4) z = 4;
+  BSC_LAUNCH((k_attention<HD, CAUSAL>), dim3((unsigned)heads, (unsigned)batch, (unsigned)z), kAttnThreads, smem, stream, qkv, out, T, heads, t_pad);
   return BSCNAV_OK;
 }
 

@@ -116,7 +116,8 @@ struct VitEngine {
   const float* wf;
   int max_batch, Np, T;
   CUtensorMap map_a0, map_y, map_ao, map_h;          // activation operands
-  CUtensorMap map_patch_w;
+  CUtensorMap map_patch_w, half_patch_w;             // half_: 128-row boxes (CTA-pair GEMM, small-M 128-wide tiles)
+  bool has_half_patch = false;
   CUtensorMap out_qkv, out_h, out_x;                 // store maps of the GEMM outputs
   CUtensorMap qkv128, qkv16;                         // qkv tensor as attention operand (128- and 16-row boxes)
   CUtensorMap qkv3d128, qkv3d16;                     // the same tensor as {column, token, frame} (attention_ws.cu)
@@ -172,7 +173,8 @@ static int vit_run(VitEngine* e, int batch, float* out_tokens, cudaStream_t stre
   ep.out = e->ws.x; ep.bias = wf + e->L.patch_b; ep.table = wf + e->L.pos; ep.ld_out = D; ep.mode = kOutPatchEmbed;
   ep.np = Np; ep.tokens = T; ep.row_off = 1 + c.n_reg;
   { ProfScope ps(e, stream, kCatGemm, 2.0 * batch * Np * (double)D * c.patch_k_pad);
-    if (int r = gemm_f16_launch(&e->map_a0, &e->map_patch_w, nullptr, batch * Np, D, c.patch_k_pad, ep, stream, nullptr, c.precision)) return r; }
+    if (int r = gemm_f16_launch(&e->map_a0, &e->map_patch_w, nullptr, batch * Np, D, c.patch_k_pad, ep, stream,
+                                e->has_half_patch ? &e->half_patch_w : nullptr, c.precision)) return r; }
   if (int r = fill_prefix_tokens(e->ws.x, wf + e->L.cls_pos, wf + e->L.reg, batch, T, c.n_reg, D, stream)) return r;
   if (c.ln_pre)
     if (int r = layernorm_inplace(e->ws.x, wf + e->L.ln_pre_w, wf + e->L.ln_pre_b, c.ln_eps, rows, D, stream)) return r;
@@ -387,6 +389,10 @@ int bscnav_vit_create(const bscnav_vit_cfg_t* c, const void* w_half, const float
   }
   r = r ? r : make_store_map(&e->out_x, e->ws.x, rows, D, true);
   if (!text) r = r ? r : make_operand_map(&e->map_patch_w, e->wh + e->L.patch_w, D, kw * c->patch_k_pad, gemm_block_n((int)D));
+  if (!text && gemm_block_n((int)D) == 256) {
+    r = r ? r : make_operand_map(&e->half_patch_w, e->wh + e->L.patch_w, D, kw * c->patch_k_pad, 128);
+    e->has_half_patch = true;
+  }
   for (int i = 0; i < c->depth && !r; ++i) {
     const LayerOff& o = e->L.layer[i];
     r = r ? r : make_operand_map(&e->map_qkv[i], e->wh + o.qkv_w, 3 * D, kw * D, gemm_block_n((int)(3 * D)));

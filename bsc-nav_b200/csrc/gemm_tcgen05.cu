@@ -240,7 +240,9 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         __threadfence();
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
         if (threadIdx.x == 0) {
+          __threadfence();                                 // release: cumulative over the other epilogue threads' stores (ordered by the barrier)
           const int last = atomicAdd(epi.kcnt + tile, 1) == S - 1;
+          __threadfence();                                 // acquire side of the same counter
           if (last) epi.kcnt[tile] = 0;
           *kflag = last;
         }

@@ -53,6 +53,9 @@ def test_null_pointers_are_rejected(env):
     assert lib.bscnav_cluster_centers(None, None, None, 1, 100, 10.0, 5, 8, None, None, None, None, None, None) == EINVAL
     assert lib.bscnav_gemm_f16(None, None, None, None, 128, 128, 64, 0, 0, None) == EINVAL
     assert lib.bscnav_attention_f16(None, None, 1, 257, 16, 2, None) == EINVAL
+    assert lib.bscnav_gemm_f16_sliced(None, None, None, None, 257, 1024, 4096, 2, 0, None, 0, None, None) == EINVAL
+    assert lib.bscnav_store_publish_counts(C.byref(st), None, None) == EINVAL      # null counters, null destination
+    assert lib.bscnav_store_publish_counts(None, None, None) == EINVAL
     col = L.Colour()
     assert lib.bscnav_colour_reset(C.byref(g), C.byref(col), None) == EINVAL
 
@@ -68,6 +71,10 @@ def test_shape_limits(env):
     assert lib.bscnav_gemm_f16(p, p, None, p, 128, 100, 64, 0, 0, None) == EINVAL
     assert lib.bscnav_gemm_f16(p, p, None, p, 128, 128, 60, 0, 0, None) == EINVAL
     assert lib.bscnav_gemm_f16(p, p, None, p, 128, 128, 64, 9, 0, None) == EINVAL
+    # the sliced entry: scratch must hold the counters and at least two partial tiles; fp16-mode numbers only
+    assert lib.bscnav_gemm_f16_sliced(p, p, None, p, 257, 1024, 4096, 2, 0, p, 1024, None, None) == EINVAL
+    assert lib.bscnav_gemm_f16_sliced(p, p, None, p, 257, 1000, 4096, 2, 0, p, 1 << 24, None, None) == EINVAL
+    assert lib.bscnav_gemm_f16_sliced(p, p, None, p, 257, 1024, 4096, 6, 0, p, 1 << 24, None, None) == EINVAL
     # dense fusion needs n_points == H * W when no sample index list is given
     g = _geom(store)
     st = L.Store(*[p] * 9)

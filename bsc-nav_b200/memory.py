@@ -209,52 +209,69 @@ class VoxelTokenMemory:
     def _inputs_to_device(self, rgb, depth):
         """Host frames -> device through a side copy stream and two device buffers, so the copy of batch i+1 overlaps
         the kernels of batch i.  Pinned torch tensors are copied directly (the caller keeps them unchanged until the copy
-        has run, as with any non_blocking copy); numpy arrays go through per-slot pinned staging."""
+        has run, as with any non_blocking copy); numpy arrays go through per-slot pinned staging.
+
+        Returns (rgb_dev, depth_dev, slot, late_depth).  The colour frames are on their way when this returns and the current
+        stream waits for them.  For host depth, `depth_dev` is None and `late_depth()` -- to be called once the ViT has been
+        enqueued -- stages and copies it and returns (depth_dev, event): only the scatter needs the depth, so at one frame per
+        call its staging and its copy run behind the ViT instead of in front of it."""
         if torch.is_tensor(rgb) and rgb.is_cuda and torch.is_tensor(depth) and depth.is_cuda:
-            return rgb.contiguous(), depth.contiguous(), None
+            return rgb.contiguous(), depth.contiguous(), None, None
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
             self._in_bufs = [None, None]
             self._in_free = [None, None]
             self._in_slot = 0
         slot = self._in_slot = self._in_slot ^ 1
-        staged = []
+        staged_rgb = None
         if not torch.is_tensor(rgb):
             rgb = np.asarray(rgb)
-            view, ent = self._staging("rgb", slot, rgb.shape, torch.uint8)
+            view, staged_rgb = self._staging("rgb", slot, rgb.shape, torch.uint8)
             view.numpy()[...] = rgb
             rgb = view
-            staged.append(ent)
-        if not torch.is_tensor(depth):
-            depth = np.asarray(depth, dtype=np.float32)
-            view, ent = self._staging("depth", slot, depth.shape, torch.float32)
-            view.numpy()[...] = depth
-            depth = view
-            staged.append(ent)
+        n_rgb = rgb.numel()
+        n_dep = int(np.prod(depth.shape))
         cur = torch.cuda.current_stream()
         bufs = self._in_bufs[slot]
-        if bufs is None or bufs[0].numel() < rgb.numel() or bufs[1].numel() < depth.numel():
+        if bufs is None or bufs[0].numel() < n_rgb or bufs[1].numel() < n_dep:
             # growing: the kernels that still read the old buffers finish first (they run on other streams than the one the
             # caching allocator would hand the memory back to); the new memory may be recycled from work queued on `cur`
             self._wait_events(self._in_free[slot])
             self._in_free[slot] = None
-            bufs = self._in_bufs[slot] = (torch.empty(rgb.numel(), dtype=torch.uint8, device=self.device),
-                                          torch.empty(depth.numel(), dtype=torch.float32, device=self.device))
+            bufs = self._in_bufs[slot] = (torch.empty(n_rgb, dtype=torch.uint8, device=self.device),
+                                          torch.empty(n_dep, dtype=torch.float32, device=self.device))
             self._copy_stream.wait_stream(cur)
-        rgb_d = bufs[0][: rgb.numel()].view(rgb.shape)
-        dep_d = bufs[1][: depth.numel()].view(depth.shape)
+        rgb_d = bufs[0][:n_rgb].view(rgb.shape)
         if self._in_free[slot] is not None:
             for ev in self._in_free[slot]:
-                self._copy_stream.wait_event(ev)                  # kernels that read this buffer two batches ago are done
+                self._copy_stream.wait_event(ev)                  # kernels that read these buffers two batches ago are done
         with torch.cuda.stream(self._copy_stream):
             rgb_d.copy_(rgb, non_blocking=True)
-            dep_d.copy_(depth, non_blocking=True)
             copied = torch.cuda.Event()
             copied.record(self._copy_stream)
-        for ent in staged:
-            ent[1] = copied
+        if staged_rgb is not None:
+            staged_rgb[1] = copied
         cur.wait_event(copied)
-        return rgb_d, dep_d, slot
+
+        def copy_depth(depth):
+            staged = None
+            if not torch.is_tensor(depth):
+                depth = np.asarray(depth, dtype=np.float32)
+                view, staged = self._staging("depth", slot, depth.shape, torch.float32)
+                view.numpy()[...] = depth
+                depth = view
+            dep_d = bufs[1][:n_dep].view(depth.shape)
+            with torch.cuda.stream(self._copy_stream):        # behind the colour copy, which already waited for the buffers' readers
+                dep_d.copy_(depth, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            if staged is not None:
+                staged[1] = ev
+            return dep_d, ev
+
+        if torch.is_tensor(depth) and depth.is_cuda:
+            return rgb_d, depth.contiguous(), slot, None
+        return rgb_d, None, slot, lambda: copy_depth(depth)
 
     @staticmethod
     def _wait_events(events):
@@ -268,10 +285,10 @@ class VoxelTokenMemory:
         unprojection + scatter on a second side stream (overlapping the next call's ViT)."""
         poses = np.asarray(poses, dtype=np.float64).reshape(-1, 7)
         tfs = self._chain.batch(poses)
-        rgb, depth, slot = self._inputs_to_device(rgb, depth)
+        rgb, depth, slot, late_depth = self._inputs_to_device(rgb, depth)
         if sample_idx is None:
             sample_idx = self._sample_indices(rgb.shape[0])
-        done = self.fuse_device(rgb, depth, tfs, sample_idx=sample_idx)
+        done = self.fuse_device(rgb, depth, tfs, sample_idx=sample_idx, late_depth=late_depth)
         if slot is not None:
             ev = torch.cuda.Event()
             ev.record()                                   # the ViT has read rgb; `done`: the scatter has read depth
@@ -287,9 +304,10 @@ class VoxelTokenMemory:
         self._chain(np.asarray(origin_pose, dtype=np.float64).reshape(7))
         self._store.next_ordinal = int(first_frame) * self.args.height * self.args.width
 
-    def fuse_device(self, rgb_dev, depth_dev, tfs, sample_idx=None, ord_base=None):
+    def fuse_device(self, rgb_dev, depth_dev, tfs, sample_idx=None, ord_base=None, late_depth=None):
         """ViT on the current stream, then unprojection + scatter on the side stream.  Returns the event that marks the
-        end of the scatter.  Inputs are device tensors that stay valid until that event."""
+        end of the scatter.  Inputs are device tensors that stay valid until that event.  `late_depth` (fuse_frames with host
+        frames): called after the ViT has been enqueued, returns (depth_dev, event the scatter waits for)."""
         main = torch.cuda.current_stream()
         if self._fuse_stream is None:
             self._fuse_stream = torch.cuda.Stream(device=self.device)
@@ -307,6 +325,9 @@ class VoxelTokenMemory:
         tokens = self._tokens_of(rgb_dev, out=buf[:B]) if engine else self._tokens_of(rgb_dev)
         ready = torch.cuda.Event()
         ready.record(main)
+        depth_ready = None
+        if late_depth is not None:
+            depth_dev, depth_ready = late_depth()
         side = self._fuse_stream if os.environ.get("BSCNAV_OVERLAP", "1") != "0" else main     # 0: everything on one stream (A/B)
         if side is not main:
             # tensors allocated on the main stream and read on the side stream: the allocator must not recycle them early
@@ -316,6 +337,8 @@ class VoxelTokenMemory:
                     t.record_stream(side)
         with torch.cuda.stream(side):
             side.wait_event(ready)
+            if depth_ready is not None:
+                side.wait_event(depth_ready)
             self._store.fuse(depth_dev, tfs, tokens, sample_idx=sample_idx, ord_base=ord_base,
                              rgb=rgb_dev if self.colour else None)
             done = torch.cuda.Event()

@@ -116,6 +116,24 @@ def test_full_vit_matches_oracle(pkg, base, attn, monkeypatch):
     assert rel < 1e-3
 
 
+@pytest.mark.parametrize("base", ["clip-vit-l14", "dinov2-vitl14-reg"])
+def test_one_frame_per_call_matches_oracle(pkg, base):
+    """The reference's call pattern (memory_2.py:732-742: one frame per forward) takes its own route through the engine -- blocks
+    replayed from a CUDA graph, fc2 in K slices, the row-group-split attention kernel: full-size tokens of three frames passed one
+    at a time (eager, captured, replayed) against the fp32 oracle at the bar, and next to the same frames as one batch."""
+    cfg = pkg.CONFIGS[base]
+    w = pkg.random_weights(cfg, seed=0)
+    eng = pkg.ViTEngine(cfg, w, max_batch=4)
+    rgb = torch.randint(0, 256, (3, 480, 640, 4), dtype=torch.uint8, generator=torch.Generator().manual_seed(6))
+    one = torch.cat([eng.forward_frames(rgb[i:i + 1].cuda()) for i in range(3)]).cpu()
+    batch = eng.forward_frames(rgb.cuda()).cpu()
+    ref = vit_ref.vit_forward(vit_ref.preprocess_frame(rgb[..., :3]), w, cfg)
+    rel1, relb = _rel(one, ref), _rel(batch, ref)
+    print(base, "per-token relative L2 error, one frame per call", rel1, "batched", relb, "between them", _rel(one, batch))
+    assert rel1 < 1e-3 and relb < 1e-3
+    assert not eng.range_overflow()
+
+
 def test_gaussian_pool(pkg):
     t = torch.randn(3, 256, 1024, generator=torch.Generator().manual_seed(0))
     got = pkg.gaussian_pool(t.cuda()).cpu()

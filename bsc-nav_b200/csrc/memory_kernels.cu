@@ -336,19 +336,22 @@ k_assign_slots(const uint4* __restrict__ rec, long long total, int32_t* __restri
 __global__ void __launch_bounds__(kThreads)
 k_select(const uint4* __restrict__ rec, long long total, const int32_t* __restrict__ occupied,
          uint32_t* __restrict__ first_touch, unsigned long long* __restrict__ slot_keys, int C,
-         uint4* __restrict__ cand, int* __restrict__ cand_n) {
+         uint4* __restrict__ cand, int* __restrict__ cand_n, const uint32_t* __restrict__ fresh) {
   __shared__ int warp_off[kThreads / 32 + 1];
   const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
   const int lane = threadIdx.x & 31;
   int cell = -1, slot = -1;
   uint32_t aux = 0;
   unsigned long long key = BSCNAV_KEY_EMPTY;
+  // first_touch holds an ordinal only where k_index_points issued its atomicMin: at the points of its mask.  Only those restore
+  // the scratch invariant for the next batch (was: every point, 16.9 M scattered 4-byte stores per 55 frames); without a mask
+  // (merge path) every record does.
+  const uint32_t fword = (fresh && i - lane < total) ? fresh[i >> 5] : 0xFFFFFFFFu;
   if (i < total) {
     const uint4 r = rec[i];
     cell = (int)r.x;
     if (cell >= 0) {
-      first_touch[cell] = kNoTouch;      // restore the scratch invariant for the next batch
-      slot = occupied[cell];             // < 0 only after a capacity overflow
+      if ((fword >> lane) & 1u) first_touch[cell] = kNoTouch;
       key = rec_key(r);
       aux = r.y;
     }
@@ -363,11 +366,14 @@ k_select(const uint4* __restrict__ rec, long long total, const int32_t* __restri
       if (lane + d < 32 && c2 == cell && k2 < key) { key = k2; aux = a2; }
     }
     const int prev = __shfl_up_sync(0xffffffffu, cell, 1);
-    if (slot >= 0 && (lane == 0 || prev != cell) && key < slot_keys[slot]) {
-      atomicMin(&slot_keys[slot], key);
-      offered = true;
+    if (cell >= 0 && (lane == 0 || prev != cell)) {      // the head of a run of equal cells holds the run's minimum: it alone
+      slot = occupied[cell];                              // looks its slot up (< 0 only after a capacity overflow)
+      if (slot >= 0 && key < slot_keys[slot]) {
+        atomicMin(&slot_keys[slot], key);
+        offered = true;
+      }
     }
-  } else if (slot >= 0) {
+  } else if (cell >= 0 && (slot = occupied[cell]) >= 0) {
     unsigned long long* ks = slot_keys + (long long)slot * C;
     if (key < ks[C - 1]) {
       offered = true;
@@ -912,7 +918,7 @@ static int run_store_update(const bscnav_geom_t* g, const bscnav_store_t* st, co
     BSC_LAUNCH(k_assign_slots, n_tiles, kThreads, 0, stream, s.rec, total, st->occupied_ids, st->first_touch, s.tile_off,
                s.hdr, st->slot_cell, fresh, s.tile_count);
   BSC_LAUNCH(k_select, n_blocks, kThreads, 0, stream, s.rec, total, st->occupied_ids, st->first_touch,
-             reinterpret_cast<unsigned long long*>(st->slot_keys), g->cache, s.cand, s.cand_n);
+             reinterpret_cast<unsigned long long*>(st->slot_keys), g->cache, s.cand, s.cand_n, fresh);
   const int want = (n_blocks + kThreads / 32 - 1) / (kThreads / 32), cap = num_sms() * 16;
   BSC_LAUNCH(k_commit, want < cap ? want : cap, kThreads, 0, stream, s.cand, s.cand_n, n_blocks,
              reinterpret_cast<const unsigned long long*>(st->slot_keys), reinterpret_cast<unsigned long long*>(st->row_key),

@@ -2,6 +2,7 @@
 forward against the torch-fp32 oracle (oracle/vit_ref.py).  Tolerance: 1e-3 relative, per token (L2), as
 BASELINE.json's north_star states for feature vectors."""
 import importlib
+import os
 
 import numpy as np
 import pytest
@@ -53,7 +54,7 @@ def test_gemm_k_slices(pkg, M, N, K, want_slices):
     first = None
     for _ in range(4):                                    # the arrival order of the slices varies, the sum must not
         out, s = pkg.gemm_f16_sliced(a, w, bias, out_mode=2, out=res.clone(), scratch=scratch)
-        if torch.cuda.get_device_properties(0).multi_processor_count == 148:
+        if torch.cuda.get_device_properties(0).multi_processor_count == 148 and os.environ.get("BSCNAV_KSLICE", "1") != "0":
             assert s == want_slices
         torch.testing.assert_close(out, res + ref, rtol=1e-4, atol=1e-4)
         first = out if first is None else first

@@ -32,7 +32,7 @@ static constexpr int kBins = 2048;
 static constexpr int kCandCap = kTopkChunk;
 static constexpr int kMarginBins = 3;
 static constexpr int kSelSlots = 8192;      // cells per block in the histogram / select passes (256 threads x 8 x 4)
-static constexpr int kPassQueries = 256;    // queries per GEMM pass
+static constexpr int kPassQueries = 1024;    // queries per GEMM pass
 
 __device__ __forceinline__ int sim_bin(float s) {
   const int b = (int)((s + 1.0f) * 1024.0f);          // NaN converts to 0

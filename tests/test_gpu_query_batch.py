@@ -1,7 +1,7 @@
 """Batched query path (csrc/query_batch.cu: tcgen05 candidate GEMM + exact fp32 re-scoring) against the exact single-query
 path (k_query_slots): similarities, positions and counts must be IDENTICAL, bit for bit -- including ties (the same ViT
 patch token is scattered to many cells, so duplicate rows are the norm), near-ties around the K-th value, filters, cells
-with several tokens (C > 1) and empty rows, fewer than K candidates, more than 256 queries (several GEMM passes), and the
+with several tokens (C > 1) and empty rows, fewer than K candidates, more than 1024 queries (several GEMM passes), and the
 overflow fall-back.  The exact path itself is checked against the oracle in test_gpu_memory.py."""
 import numpy as np
 import pytest
@@ -43,7 +43,7 @@ def _same(a, b):
 
 @pytest.mark.parametrize("C,bev,n,D,dup", [(1, True, 5000, 256, 0), (1, True, 20000, 1024, 300), (3, False, 3000, 384, 0),
                                           (10, False, 700, 1024, 40), (2, True, 4097, 128, 0)])
-@pytest.mark.parametrize("Q", [1, 7, 300])
+@pytest.mark.parametrize("Q", [1, 7, 300, 1100])      # 1100: two GEMM passes (1024 queries per pass)
 def test_batch_equals_exact(pkg, C, bev, n, D, dup, Q):
     cfg = pkg.StoreConfig(height=96, width=128, grid_size=160, token_dim=D, cache_size=C, bev=bev, floor_height=-1.0, map_height=1.0,
                           max_slots=25600)

@@ -387,12 +387,12 @@ class VoxelTokenMemory:
             self.dinov2.check_range()
 
     def update_memory_surp_base(self):
-        """memory_2.py:360-536, the surprise-based store rule (accept a token when its cosine distance to the 26 neighbouring voxels'
+        """memory_2.py:364-536, the surprise-based store rule (accept a token when its cosine distance to the 26 neighbouring voxels'
         tokens exceeds a threshold, merge near-duplicates by union-find, average the groups).  No driver or method of the reference
-        calls it (the build loop flushes through update_memory_dist_base, :1101-1134), and every decision reads the groups the previous
+        calls it (the build loop flushes through update_memory_dist_base, :881 and :1135), and every decision reads the groups the previous
         tokens wrote, so it is sequential per token by construction.  Not built: the distance-based rule is the store contract
         (SURVEY 8a)."""
-        raise NotImplementedError("update_memory_surp_base has no call site in the reference (memory_2.py:360-536 is dead code); "
+        raise NotImplementedError("update_memory_surp_base has no call site in the reference (memory_2.py:364-536 is dead code); "
                                   "this memory keeps the distance-based store rule of update_memory_dist_base")
 
     def initial_memory(self):

@@ -229,6 +229,8 @@ class VoxelTokenMemory:
             view, staged_rgb = self._staging("rgb", slot, rgb.shape, torch.uint8)
             view.numpy()[...] = rgb
             rgb = view
+        if not torch.is_tensor(depth):
+            depth = np.asarray(depth, dtype=np.float32)      # no copy for a float32 array; lists and other dtypes are converted here
         n_rgb = rgb.numel()
         n_dep = int(np.prod(depth.shape))
         cur = torch.cuda.current_stream()
@@ -256,7 +258,6 @@ class VoxelTokenMemory:
         def copy_depth(depth):
             staged = None
             if not torch.is_tensor(depth):
-                depth = np.asarray(depth, dtype=np.float32)
                 view, staged = self._staging("depth", slot, depth.shape, torch.float32)
                 view.numpy()[...] = depth
                 depth = view

@@ -116,3 +116,42 @@ def test_text_goal_branch_matches_reference(cfg1, golden):
     del mem.imaginary                       # back to the class's NotImplementedError for the next user of the fixture
     with pytest.raises(NotImplementedError):
         mem.voxel_localized("no generator injected")
+
+
+def test_fuse_frames_input_forms_agree(pkg):
+    """fuse_frames takes numpy arrays, nested lists, other dtypes for the depth, pinned host tensors and device tensors; the depth is
+    staged and copied behind the ViT (memory.py: _inputs_to_device).  Every form must build the same store, bit for bit."""
+    synth = importlib.import_module("bsc-nav_b200.synth")
+    cfg = pkg.tiny(pkg.CLIP_L14, dim=128, depth=2, heads=2, mlp=256)
+    eng = pkg.ViTEngine(cfg, pkg.random_weights(cfg, seed=3, perturb=True), max_batch=4)
+    H, W = 96, 128
+    frames = [synth.synthetic_frame(f, H, W, n_frames=12) for f in range(6)]
+    rgb = np.stack([f[0] for f in frames]); depth = np.stack([f[1] for f in frames]).astype(np.float32)
+    poses = np.stack([synth.tour_pose(f) for f in range(6)])
+    forms = {
+        "numpy": lambda a, b: (rgb[a:b], depth[a:b]),
+        "float64 depth": lambda a, b: (rgb[a:b], depth[a:b].astype(np.float64)),
+        "lists": lambda a, b: (rgb[a:b], depth[a:b].tolist()),
+        "pinned": lambda a, b: (torch.from_numpy(rgb[a:b].copy()).pin_memory(), torch.from_numpy(depth[a:b].copy()).pin_memory()),
+        "device": lambda a, b: (torch.from_numpy(rgb[a:b]).cuda(), torch.from_numpy(depth[a:b]).cuda()),
+        "host rgb, device depth": lambda a, b: (rgb[a:b], torch.from_numpy(depth[a:b]).cuda()),
+    }
+    snaps = {}
+    for name, form in forms.items():
+        mem = pkg.VoxelTokenMemory(synth.Args(height=H, width=W, grid_size=64, depth_sample_rate=1), preload_dino=eng,
+                                   need_diffusion=False, cache_size=1, max_batch=4)      # C = 1: the row layout itself is deterministic
+        keep = []
+        for a, b in ((0, 3), (3, 4), (4, 6)):                 # ragged batches: the staging and device buffers are re-used and re-sized
+            r, d = form(a, b)
+            keep.append((r, d))                               # pinned inputs stay alive and unchanged until the copies have run
+            mem.fuse_frames(r, d, poses[a:b])
+        mem.update_memory_dist_base()
+        st = mem.store
+        n = mem.max_id
+        snaps[name] = (n, st.slot_cell[:n].cpu(), st.row_key[:n].cpu(), st.tok_h[:n].cpu(), st.feat[:n].cpu())
+    ref = snaps["device"]
+    assert ref[0] > 0
+    for name, s in snaps.items():
+        assert s[0] == ref[0], name
+        for x, y in zip(s[1:], ref[1:]):
+            assert torch.equal(x, y), name
